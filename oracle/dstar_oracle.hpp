@@ -1,0 +1,266 @@
+// dStar hot-path ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A CPU restatement (C++17, FP64, compiled -O2 -ffp-contract=off) of the
+// reference's algorithm for the NScool hot path.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may build, link or call anything in this directory.  The
+// product (dstar_b200/) never includes or links it.
+//
+// The reference (serial Fortran + MESA r15140) cannot be compiled in this
+// image (no Fortran compiler, no MESA, data files are LFS stubs), so this
+// restatement is pinned against the reference's own golden test outputs where
+// those are data-free (see tests/test_oracle_golden.py):
+//   constants/test/sample_output.data, nucchem/test/sample_output,
+//   neutrino/test/sample_output.data (crust rows), conductivity/test/
+//   sample_output.data, dStar_atm/test/sample_output.data (pcy97 rows),
+//   dStar_eos/test/sample_output.data, superfluid/test/sample_output.data.
+// PARITY UNPINNED (no golden exists upstream): the stiff integrator (MESA
+// isolve/rodasp, not in tree) and therefore Teff(t); see DESIGN.md.
+//
+// Fortran semantics reproduced on purpose:
+//   * default-kind REAL literals are REAL(4): R4(x) == (double)(x##f).
+//   * x**n with integer n is repeated multiplication (ipow), x**y is pow.
+//   * evaluation order follows the source expression left to right.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace dso {
+
+#ifndef DSO_REAL4_LITERALS
+#define DSO_REAL4_LITERALS 1
+#endif
+#if DSO_REAL4_LITERALS
+#define R4(x) (static_cast<double>(x##f))
+#else
+#define R4(x) (static_cast<double>(x))
+#endif
+
+// ---------------------------------------------------------------- constants
+// MESA r15140 const_def (CODATA 2018) extended by constants/public/constants_def.f:9-68
+namespace cst {
+constexpr double pi = 3.1415926535897932384626433832795028841971693993751;
+constexpr double ln10 = 2.3025850929940456840179914546843642076011014886288;
+constexpr double one_third = 1.0 / 3.0;
+constexpr double two_thirds = 2.0 / 3.0;
+constexpr double five_thirds = 5.0 / 3.0;
+constexpr double planck_h = 6.62607015e-27;
+constexpr double hbar = planck_h / (2.0 * pi);
+constexpr double clight = 2.99792458e10;
+constexpr double avo = 6.02214076e23;
+constexpr double kerg = 1.380649e-16;
+constexpr double amu = 1.0 / avo;
+constexpr double mn = 1.67492749804e-24;
+constexpr double mp = 1.67262192369e-24;
+constexpr double me = 9.1093837015e-28;
+constexpr double fine = 7.2973525693e-3;
+constexpr double ev2erg = 1.602176634e-12;
+constexpr double mev_to_ergs = 1.0e6 * ev2erg;
+constexpr double boltz_sigma =
+    (pi * pi * kerg * kerg * kerg * kerg) / (60.0 * hbar * hbar * hbar * clight * clight);
+constexpr double crad = boltz_sigma * 4.0 / clight;
+constexpr double standard_cgrav = 6.67430e-8;
+constexpr double mu_sun = 1.3271244e26;
+constexpr double Msun = mu_sun / standard_cgrav;
+// constants_def.f
+constexpr double twopi = 2.0 * pi;
+constexpr double threepi = 3.0 * pi;
+constexpr double fourpi = 4.0 * pi;
+constexpr double onethird = one_third;
+constexpr double twothird = two_thirds;
+constexpr double fivethird = five_thirds;
+constexpr double seventhird = 7.0 * onethird;
+constexpr double threepisquare = 3.0 * pi * pi;
+constexpr double boltzmann = kerg;
+constexpr double avogadro = avo;
+constexpr double clight2 = clight * clight;
+constexpr double sigma_SB = boltz_sigma;
+constexpr double arad = crad;
+constexpr double finestructure = fine;
+constexpr double electroncharge2 = finestructure * hbar * clight;
+constexpr double Gnewton = standard_cgrav;
+constexpr double Mneutron = mn;
+constexpr double Mproton = mp;
+constexpr double Melectron = me;
+constexpr double Mmuon = 1.883531627e-25;
+constexpr double r_e_cl = electroncharge2 / Melectron / clight2;
+constexpr double Thomson = 8.0 * pi * onethird * r_e_cl * r_e_cl;
+constexpr double julian_day = 86400.0;
+constexpr double GMsun = mu_sun;
+constexpr double fm_to_cm = 1.0e-13;
+constexpr double ergs_to_mev = 1.0 / mev_to_ergs;
+constexpr double cm_to_fm = 1.0 / fm_to_cm;
+constexpr double a_Bohr = hbar * hbar / electroncharge2 / Melectron;
+constexpr double Rydberg = 0.5 * electroncharge2 / a_Bohr;
+constexpr double hbarc_n = hbar * clight / mev_to_ergs / fm_to_cm;
+constexpr double mass_n = mev_to_ergs / clight2;
+constexpr double length_n = fm_to_cm;
+constexpr double density_n = 1.0 / (fm_to_cm * fm_to_cm * fm_to_cm);
+constexpr double pressure_n = mev_to_ergs * density_n;
+constexpr double temperature_n = mev_to_ergs / boltzmann;
+constexpr double Mn_n = Mneutron * clight2 * ergs_to_mev;
+constexpr double Mp_n = Mproton * clight2 * ergs_to_mev;
+constexpr double Me_n = Melectron * clight2 * ergs_to_mev;
+constexpr double amu_n = amu * clight2 * ergs_to_mev;
+constexpr double mass_g = Msun;
+constexpr double potential_g = clight2;
+constexpr double length_g = Gnewton * mass_g / potential_g;
+constexpr double density_g = mass_g / (length_g * length_g * length_g);
+constexpr double pressure_g = density_g * potential_g;
+constexpr double time_g = length_g / clight;
+}  // namespace cst
+
+double electroncharge();  // sqrt(electroncharge2) (constants_def.f:30)
+
+// x**n for integer n >= 0, as repeated multiplication
+inline double ipow(double x, int n) {
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r *= x;
+    return r;
+}
+// MESA math_lib exp10: exp(x*ln10)
+inline double dexp10(double x) { return std::exp(x * cst::ln10); }
+
+// ------------------------------------------------------------- composition
+// nucchem/public/nucchem_def.f:23-35 (same field order)
+struct Composition {
+    double A, Z, Z53, Z2, Z73, Z52, ZZ1_32, Z2XoA2, Ye, Yn, Q;
+};
+
+// nucchem/public/nucchem_lib.f:47-133.  Zs/As are the per-nuclide charge and
+// mass numbers (neutron: Z=0,A=1); returns ncharged and fills Zion/Aion/Yion.
+struct MomentsOptions {
+    bool abunds_are_mass_fractions = false;
+    bool exclude_neutrons = false;
+    bool renormalize_mass_fractions = false;
+};
+void compute_composition_moments(int n, const double* Zs, const double* As, const double* abunds,
+                                 const MomentsOptions& opt, Composition& comp, double& Xsum,
+                                 int& ncharged, int* charged_idx, double* Yion);
+
+// --------------------------------------------------------- interpolation
+// MESA interp_1d: interp_pm (Steffen 1990 monotone cubic), f is (4,n) column-major
+// with f(1,i) preloaded; interp_value_and_slope.
+void interp_pm(const double* x, int n, double* f);
+void interp_value_and_slope(const double* x, int n, const double* f, double xval, double& val,
+                            double& slope);
+double interp_value(const double* x, int n, const double* f, double xval);
+
+// ------------------------------------------------------------- superfluid
+// superfluid/public/superfluid_def.f:14-21, superfluid_lib.f:65-101
+struct SfTable {
+    bool loaded = false;
+    double kF_min = 0, kF_max = 0;
+    std::vector<double> kF, f;  // f = (4,nv)
+};
+struct SfTables {
+    SfTable tab[3];  // 0 = proton 1S0, 1 = neutron 1S0, 2 = neutron 3P2
+    double scale[3] = {1.0, 1.0, 1.0};
+};
+void sf_load(SfTable& t, int nv, double kFmin, double kFmax, const double* kF, const double* Tc);
+void sf_get_results(const SfTables& sf, double kFp, double kFn, double Tc[3]);
+
+// -------------------------------------------------------------------- HELM
+// dStar_eos/public/helm_results.f (type Helm_Table), helm_alloc.f:120-330
+struct HelmTable {
+    int imax = 0, jmax = 0;
+    double logtlo, logthi, templo, temphi, logtstp, logtstpi;
+    double logdlo, logdhi, denlo, denhi, logdstp, logdstpi;
+    std::vector<double> d, t;
+    // 21 arrays (imax,jmax) column-major, i fastest
+    std::vector<double> f, fd, ft, fdd, ftt, fdt, fddt, fdtt, fddtt;
+    std::vector<double> dpdf, dpdfd, dpdft, dpdfdt;
+    std::vector<double> ef, efd, eft, efdt;
+    std::vector<double> xf, xfd, xft, xfdt;
+    std::vector<double> dt_sav, dt2_sav, dti_sav, dt2i_sav, dt3i_sav;
+    std::vector<double> dd_sav, dd2_sav, ddi_sav, dd2i_sav, dd3i_sav;
+};
+// arrays21: 21 pointers in the read order of helm_alloc.f:176-196
+void helm_setup(HelmTable& h, int imax, int jmax, const double* const arrays21[21]);
+struct HelmElectron {
+    double eele, pele, sele, deept, dpepd, dpept, etaele;  // electron.f:43-50
+    // extras kept for tests of the full interpolant
+    double free_, df_d, df_t, df_dd, df_tt, df_dt, df_ttt, df_dtt, df_ddt;
+    double xnefer, dxnedd, dxnedt, detadd, detadt;
+};
+// helm_core.f:12-158 (+ helmeos2aux :161-503, helm_electron_positron.dek) for lgT >= 3;
+// returns ierr
+int helmeos2_electron(const HelmTable& h, double T, double logT, double Rho, double logRho,
+                      double abar, double zbar, HelmElectron& r);
+
+// --------------------------------------------------------------------- EOS
+struct EosControls {  // dStar_eos_private_def.f:12-21, dStar_eos_def.f:58-62
+    double Gamma_melt = 175.0;
+    double rsi_melt = 140.0;
+    double Ythresh = R4(1.0e-9);
+    double pasta_transition = R4(0.01);
+    double cluster_transition = R4(0.08);
+};
+enum { i_lnP = 0, i_lnE, i_lnS, i_grad_ad, i_chiRho, i_chiT, i_Cp, i_Cv, i_Chi, i_Gamma,
+       i_Theta, i_mu_e, i_mu_n, i_Gamma1, i_Gamma3, num_eos_results };
+constexpr int liquid_phase = 1, solid_phase = 2;
+constexpr double default_nuclear_radius = R4(1.13);
+constexpr double use_default_nuclear_size = -1.0;
+
+struct Thermo {
+    double f, u, p, s, cv, dpr, dpt;
+};
+void lattice_properties(double rho, double T, const Composition& c, double& ne, double& rs,
+                        double& Gamma_e, double& Gamma, double& ionQ);
+double nuclear_volume_fraction(double rho, const Composition& c, double nuclear_radius);
+double neutron_wavenumber(double rho, const Composition& c, double chi);
+void ee_exchange(double Gamma_e, double rs, Thermo& r);
+int get_helm_eos_results(const HelmTable& h, double rho, double T, const Composition& c,
+                         Thermo& r, double& eta);
+int ion_mixture(const EosControls& rq, double rs, double Gamma_e, const Composition& c,
+                int ncharged, const double* Zion, const double* Aion, const double* Yion,
+                double& Gamma, double& ionQ, int& phase, Thermo& r);
+void MB77(double n, double T, double Tns, Thermo& r);
+void get_radiation_eos(double rho, double T, Thermo& r);
+double zfermim12(double x);
+double zfermi12(double x);
+double zfermi32(double x);
+double ifermi12(double f);
+// dStar_eos_lib.f:123-297.  Zion/Aion replace nuclib%Z/A(charged_ids).
+int eval_crust_eos(const HelmTable& h, const EosControls& rq, double rho, double T,
+                   const Composition& c, int ncharged, const double* Zion, const double* Aion,
+                   const double* Yion, const double Tcs[3], double res[num_eos_results],
+                   int& phase, double& chi, Thermo comps[4] = nullptr);
+
+// ---------------------------------------------------------------- neutrino
+struct CrustNeutrino {
+    double total, pair, photo, plasma, brems, pbf;
+};
+void crust_neutrino_emissivity(double rho, double T, const Composition& c, double chi, double Tcn,
+                               const bool channels[5], CrustNeutrino& eps);
+
+// ------------------------------------------------------------ conductivity
+struct CondControls {  // conductivity_def.f:29-52
+    bool include_neutrons = false;
+    bool include_superfluid_phonons = false;
+    int ee_scattering_fmla = 1;  // 1 = SY06, 2 = PCY
+    int eQ_scattering_fmla = 1;  // 1 = Potekhin, 2 = Page
+    double rad_full_off_lgrho = 10.0;
+    double rad_full_on_lgrho = 9.0;
+};
+struct CondComponents {
+    double total, ee, ei, eQ, sf, nQ, np, kap, electron_total, neutron_total;
+};
+void conductivity(const CondControls& rq, double rho, double T, double chi, double Gamma,
+                  double eta, double mu_e, const Composition& c, double Tns, CondComponents& k);
+
+// ----------------------------------------------------------------- dop853
+// Hairer, Norsett & Wanner DOP853 (as wrapped by MESA num_lib), scalar-tolerance form.
+struct Dop853Stats {
+    int nfcn = 0, nstep = 0, naccpt = 0, nrejct = 0;
+};
+typedef void (*OdeRhs)(int n, double x, const double* y, double* dy, void* ctx);
+int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double h0,
+           double max_step, int max_steps, double rtol, double atol, Dop853Stats* st = nullptr);
+
+// -------------------------------------------------------------- atmosphere
+void pcy97_Teff(double grav, double Plight, int n, const double* lgTb, double* lgTeff,
+                double* lgflux);
+
+}  // namespace dso
