@@ -1,0 +1,684 @@
+// dstar_b200 C ABI (include/dstar_b200.h): contexts, HBM-resident batches, kernel launches.
+// Single translation unit: all device code is header-inlined into the kernels below.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dstar_b200.h"
+#include "kernels_evolve.cuh"
+#include "kernels_micro.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) std::snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else std::snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                 \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) return fail(DSTAR_ERR_CUDA, #call, e_);           \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+        if (count > n || !p) { cudaError_t e = alloc(count); if (e != cudaSuccess) return e; }
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t download(T* h, size_t count, cudaStream_t s) const {
+        return cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s);
+    }
+};
+}  // namespace
+
+struct dstar_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    bool helm_loaded = false;
+    DsHelmDev helm{};
+    DevBuf<double> helm_node, helm_t, helm_d;
+    DsSfDev sf{};
+    DevBuf<double> sf_kF[3], sf_f[3];
+    DevBuf<double> tab_lnT, tab_T, tab_lgT;
+    double h_tab_lnT[DS_NTAB];
+};
+
+struct dstar_batch {
+    dstar_ctx* ctx = nullptr;
+    int n_star = 0, total = 0, ncharged = 0, n_epoch = 0, n_atm = 0, atm_nv = 0, trace_cap = 0;
+    std::vector<int> h_zone_offset;
+    int max_nz = 0;
+    bool have_structure = false, have_tables = false, have_evolve = false, have_Tc_cell = false, have_Tc_face = false,
+         have_enuc = false;
+    DevBuf<int> zone_offset, zone_star, status, atm_index, idid, counters, model, trace_count, trace_model;
+    DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
+    DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
+    DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
+        lnT, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
+    DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double ms[3] = {0, 0, 0};
+    int launches = 0;
+};
+
+namespace {
+void fill_host_consts(DsHostConsts& h) {
+    using namespace dsc;
+    h.theta_fac = 2.0 * std::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
+    h.ctf_fac = (double)(18.0f / 175.0f) * std::pow(12.0 / pi, 2.0 * onethird);
+    h.xrs = finestructure * std::pow(9.0 * pi / 4.0, onethird);
+    h.atf = (double)(54.0f / 175.0f) * std::pow(12.0 / pi, onethird) * finestructure;
+    h.e1 = std::exp(1.0);
+    h.half_log_6_over_pi = 0.5 * std::log(6.0 / pi);
+    h.aei_fac = std::pow((double)(4.0f / 9.0f) / pi, onethird);
+    h.befac = std::pow(finestructure / pi, 1.5);
+    h.yfac = std::sqrt(4.0 * finestructure / pi);
+    h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
+}
+DsEosCtrl eos_ctrl_from(const dstar_micro_ctrl* c) {
+    DsEosCtrl e{175.0, 140.0, DS_R4(1.0e-9)};  // dStar_eos_def.f:58-62
+    if (c) {
+        if (c->eos_gamma_melt_pt > 0.0) e.Gamma_melt = c->eos_gamma_melt_pt;
+        if (c->eos_rsi_melt_pt > 0.0) e.rsi_melt = c->eos_rsi_melt_pt;
+        if (c->eos_nuclide_abundance_threshold > 0.0) e.Ythresh = c->eos_nuclide_abundance_threshold;
+    }
+    return e;
+}
+DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
+    DsCondCtrl k{0, 0, 1, 1, 10.0, 9.0};  // conductivity_def.f:49-50
+    if (c) {
+        k.include_neutrons = c->use_neutron_conductivity;
+        k.include_sf_phonons = c->use_superfluid_phonon_conductivity;
+        k.ee_fmla = c->use_pcy_for_ee_scattering ? 2 : 1;
+        k.eQ_fmla = c->use_page_for_eQ_scattering ? 2 : 1;
+        if (c->rad_full_off_lgrho > 0.0) k.rad_full_off_lgrho = c->rad_full_off_lgrho;
+        if (c->rad_full_on_lgrho > 0.0) k.rad_full_on_lgrho = c->rad_full_on_lgrho;
+    }
+    return k;
+}
+}  // namespace
+
+extern "C" {
+
+const char* dstar_last_error(void) { return g_err.c_str(); }
+
+int dstar_ctx_create(int device, dstar_ctx** out) {
+    if (!out) return fail(DSTAR_ERR_ARG, "ctx == NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(DSTAR_ERR_CUDA, "no CUDA device: dstar_b200 has no CPU fallback", e);
+    if (device < 0 || device >= ndev) return fail(DSTAR_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    dstar_ctx* c = new dstar_ctx;
+    c->device = device;
+    CK(cudaGetDeviceProperties(&c->prop, device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DsHostConsts hc;
+    fill_host_consts(hc);
+    CK(cudaMemcpyToSymbol(ds_hc, &hc, sizeof hc));
+    // table knots (create_model.f:340-341), exp and log10 taken on the host
+    double T[DS_NTAB], lgT[DS_NTAB];
+    for (int i = 0; i < DS_NTAB; ++i) {
+        c->h_tab_lnT[i] = 7.0 * dsc::ln10 + (10.0 - 7.0) * dsc::ln10 * (double)i / (double)(DS_NTAB - 1);
+        T[i] = std::exp(c->h_tab_lnT[i]);
+        lgT[i] = std::log10(T[i]);
+    }
+    CK(c->tab_lnT.upload(c->h_tab_lnT, DS_NTAB, c->stream));
+    CK(c->tab_T.upload(T, DS_NTAB, c->stream));
+    CK(c->tab_lgT.upload(lgT, DS_NTAB, c->stream));
+    for (int i = 0; i < 3; ++i) { c->sf.loaded[i] = 0; c->sf.scale[i] = 1.0; c->sf.nv[i] = 0; }
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return DSTAR_OK;
+}
+
+void dstar_ctx_destroy(dstar_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dstar_device_info(dstar_ctx* c, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char name[256]) {
+    if (!c) return fail(DSTAR_ERR_ARG, "ctx");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (name) { std::strncpy(name, c->prop.name, 255); name[255] = 0; }
+    return DSTAR_OK;
+}
+
+int dstar_ctx_set_helm(dstar_ctx* c, int imax, int jmax, const double* const a[21]) {
+    if (!c || !a || imax < 2 || jmax < 2) return fail(DSTAR_ERR_ARG, "set_helm");
+    CK(cudaSetDevice(c->device));
+    // helm_alloc.f:150-165 geometry
+    DsHelmDev& h = c->helm;
+    h.imax = imax; h.jmax = jmax;
+    const double logtlo = 3.0, logthi = 13.0, logdlo = -12.0, logdhi = 14.0;
+    const double logtstp = (logthi - logtlo) / (double)(float)(jmax - 1);
+    const double logdstp = (logdhi - logdlo) / (double)(float)(imax - 1);
+    h.logtlo = logtlo; h.logtstpi = 1.0 / logtstp; h.logdlo = logdlo; h.logdstpi = 1.0 / logdstp;
+    h.templo = std::pow(10.0, logtlo); h.temphi = std::pow(10.0, logthi); h.logthi = logthi;
+    h.denlo = std::pow(10.0, logdlo); h.denhi = std::pow(10.0, logdhi);
+    std::vector<double> t(jmax), d(imax);
+    for (int j = 0; j < jmax; ++j) t[j] = std::exp((logtlo + j * logtstp) * dsc::ln10);
+    for (int i = 0; i < imax; ++i) d[i] = std::exp((logdlo + i * logdstp) * dsc::ln10);
+    // repack the 17 hot arrays into per-node records (see helm.cuh)
+    static const int src[DS_HELM_REC] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9, 11, 10, 12, 13, 15, 14, 16};
+    const size_t n = (size_t)imax * jmax;
+    std::vector<double> node(n * DS_HELM_REC);
+    for (size_t p = 0; p < n; ++p)
+        for (int k = 0; k < DS_HELM_REC; ++k) node[p * DS_HELM_REC + k] = a[src[k]][p];
+    CK(c->helm_node.upload(node.data(), node.size(), c->stream));
+    CK(c->helm_t.upload(t.data(), t.size(), c->stream));
+    CK(c->helm_d.upload(d.data(), d.size(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    h.node = c->helm_node.p; h.t = c->helm_t.p; h.d = c->helm_d.p;
+    c->helm_loaded = true;
+    return DSTAR_OK;
+}
+
+int dstar_ctx_set_gaps(dstar_ctx* c, int type, int nv, double kF_min, double kF_max, const double* kF,
+                       const double* f4) {
+    if (!c || type < 0 || type > 2 || nv < 2 || !kF || !f4) return fail(DSTAR_ERR_ARG, "set_gaps");
+    CK(cudaSetDevice(c->device));
+    CK(c->sf_kF[type].upload(kF, nv, c->stream));
+    CK(c->sf_f[type].upload(f4, (size_t)4 * nv, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->sf.loaded[type] = 1; c->sf.nv[type] = nv; c->sf.kF_min[type] = kF_min; c->sf.kF_max[type] = kF_max;
+    c->sf.kF[type] = c->sf_kF[type].p; c->sf.f[type] = c->sf_f[type].p;
+    return DSTAR_OK;
+}
+
+int dstar_ctx_set_sf_scale(dstar_ctx* c, const double s[3]) {
+    if (!c || !s) return fail(DSTAR_ERR_ARG, "set_sf_scale");
+    for (int i = 0; i < 3; ++i) c->sf.scale[i] = s[i];
+    return DSTAR_OK;
+}
+
+// ------------------------------------------------------------ point evaluators
+int dstar_eval_crust_eos(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic, int ncharged,
+                         const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
+                         const double* chi_in, const double* eos_ctrl, double* res, int32_t* phase,
+                         double* chi_out, int32_t* ierr) {
+    if (!c || n <= 0) return fail(DSTAR_ERR_ARG, "eval_crust_eos");
+    if (!c->helm_loaded) return fail(DSTAR_ERR_STATE, "HELM table not loaded (dstar_ctx_set_helm)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> d_rho, d_T, d_ion, d_Z, d_A, d_Y, d_Tc, d_chi, d_res, d_chio;
+    DevBuf<int> d_ph, d_ie;
+    CK(d_rho.upload(rho, n, s)); CK(d_T.upload(T, n, s)); CK(d_ion.upload(ionic, (size_t)11 * n, s));
+    CK(d_Z.upload(Zion, ncharged, s)); CK(d_A.upload(Aion, ncharged, s));
+    CK(d_Y.upload(Yion, (size_t)ncharged * n, s)); CK(d_Tc.upload(Tcs, (size_t)3 * n, s));
+    if (chi_in) CK(d_chi.upload(chi_in, n, s));
+    CK(d_res.alloc((size_t)15 * n)); CK(d_chio.alloc(n)); CK(d_ph.alloc(n)); CK(d_ie.alloc(n));
+    DsEvalEosArgs a{};
+    a.n = n; a.ncharged = ncharged; a.rho = d_rho.p; a.T = d_T.p; a.ionic = d_ion.p; a.Zion = d_Z.p; a.Aion = d_A.p;
+    a.Yion = d_Y.p; a.Tcs = d_Tc.p; a.chi_in = chi_in ? d_chi.p : nullptr;
+    a.eos = DsEosCtrl{175.0, 140.0, DS_R4(1.0e-9)};
+    if (eos_ctrl) a.eos = DsEosCtrl{eos_ctrl[0], eos_ctrl[1], eos_ctrl[2]};
+    a.res = d_res.p; a.phase = d_ph.p; a.chi_out = d_chio.p; a.ierr = d_ie.p;
+    ds_eval_eos_kernel<<<(n + 63) / 64, 64, 0, s>>>(a, c->helm);
+    CK(cudaGetLastError());
+    CK(d_res.download(res, (size_t)15 * n, s));
+    if (phase) CK(d_ph.download(phase, n, s));
+    if (chi_out) CK(d_chio.download(chi_out, n, s));
+    std::vector<int> ie(n);
+    CK(d_ie.download(ie.data(), n, s));
+    CK(cudaStreamSynchronize(s));
+    int worst = 0;
+    for (int i = 0; i < n; ++i) { if (ierr) ierr[i] = ie[i]; if (ie[i] != 0) worst = ie[i]; }
+    return worst;
+}
+
+int dstar_crust_neutrino(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic,
+                         const double* chi, const double* Tcn, const int32_t ch[5], double* eps) {
+    if (!c || n <= 0) return fail(DSTAR_ERR_ARG, "crust_neutrino");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> d_rho, d_T, d_ion, d_chi, d_Tc, d_eps;
+    CK(d_rho.upload(rho, n, s)); CK(d_T.upload(T, n, s)); CK(d_ion.upload(ionic, (size_t)11 * n, s));
+    CK(d_chi.upload(chi, n, s)); CK(d_Tc.upload(Tcn, n, s)); CK(d_eps.alloc((size_t)6 * n));
+    DsEvalNuArgs a{};
+    a.n = n; a.rho = d_rho.p; a.T = d_T.p; a.ionic = d_ion.p; a.chi = d_chi.p; a.Tcn = d_Tc.p; a.eps = d_eps.p;
+    for (int i = 0; i < 5; ++i) a.channels[i] = ch ? ch[i] : 1;
+    ds_eval_nu_kernel<<<(n + 63) / 64, 64, 0, s>>>(a);
+    CK(cudaGetLastError());
+    CK(d_eps.download(eps, (size_t)6 * n, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_conductivity(dstar_ctx* c, int n, const double* rho, const double* T, const double* chi,
+                       const double* Gamma, const double* eta, const double* mu_e, const double* ionic,
+                       const double* Tns, const double cc[6], double* K) {
+    if (!c || n <= 0 || !cc) return fail(DSTAR_ERR_ARG, "conductivity");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> d_rho, d_T, d_chi, d_G, d_eta, d_mu, d_ion, d_Tn, d_K;
+    CK(d_rho.upload(rho, n, s)); CK(d_T.upload(T, n, s)); CK(d_chi.upload(chi, n, s)); CK(d_G.upload(Gamma, n, s));
+    CK(d_eta.upload(eta, n, s)); CK(d_mu.upload(mu_e, n, s)); CK(d_ion.upload(ionic, (size_t)11 * n, s));
+    CK(d_Tn.upload(Tns, n, s)); CK(d_K.alloc((size_t)10 * n));
+    DsEvalCondArgs a{};
+    a.n = n; a.rho = d_rho.p; a.T = d_T.p; a.chi = d_chi.p; a.Gamma = d_G.p; a.eta = d_eta.p; a.mu_e = d_mu.p;
+    a.ionic = d_ion.p; a.Tns = d_Tn.p; a.K = d_K.p;
+    a.cond = DsCondCtrl{cc[0] != 0, cc[1] != 0, (int)cc[2], (int)cc[3], cc[4], cc[5]};
+    ds_eval_cond_kernel<<<(n + 31) / 32, 32, 0, s>>>(a);
+    CK(cudaGetLastError());
+    CK(d_K.download(K, (size_t)10 * n, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_sf_get_results(dstar_ctx* c, int n, const double* kFp, const double* kFn, double* Tc) {
+    if (!c || n <= 0) return fail(DSTAR_ERR_ARG, "sf_get_results");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> a, b, o;
+    CK(a.upload(kFp, n, s)); CK(b.upload(kFn, n, s)); CK(o.alloc((size_t)3 * n));
+    ds_sf_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, a.p, b.p, o.p, c->sf);
+    CK(cudaGetLastError());
+    CK(o.download(Tc, (size_t)3 * n, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_crust_composition_info(dstar_ctx* c, int nv, int nisos, const double* lgP_tab, const double* Ycoef,
+                                 const double* Ziso, const double* Aiso, int nz, const double* lgP, double* ionic,
+                                 double* Yion, int32_t* ncharged) {
+    if (!c || nv < 2 || nisos < 1 || nz < 1) return fail(DSTAR_ERR_ARG, "crust_composition_info");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    int nch = 0;
+    std::vector<double> z53(nisos), z73(nisos), z52(nisos), zz1(nisos);
+    for (int i = 0; i < nisos; ++i) {
+        if (Ziso[i] > 0.0 && Aiso[i] > 0.0) ++nch;
+        z53[i] = std::pow(Ziso[i], 5.0 / 3.0); z73[i] = std::pow(Ziso[i], 7.0 / 3.0);
+        z52[i] = std::pow(Ziso[i], 2.5); zz1[i] = Ziso[i] * std::pow(Ziso[i] + 1.0, 1.5);
+    }
+    DevBuf<double> d_tab, d_Y, d_Z, d_A, d_53, d_73, d_52, d_zz, d_lgP, d_ion, d_Yion;
+    CK(d_tab.upload(lgP_tab, nv, s)); CK(d_Y.upload(Ycoef, (size_t)4 * nv * nisos, s));
+    CK(d_Z.upload(Ziso, nisos, s)); CK(d_A.upload(Aiso, nisos, s)); CK(d_53.upload(z53.data(), nisos, s));
+    CK(d_73.upload(z73.data(), nisos, s)); CK(d_52.upload(z52.data(), nisos, s)); CK(d_zz.upload(zz1.data(), nisos, s));
+    CK(d_lgP.upload(lgP, nz, s)); CK(d_ion.alloc((size_t)11 * nz)); CK(d_Yion.alloc((size_t)nch * nz));
+    DsCompArgs a{nz, nv, nisos, nch, d_tab.p, d_Y.p, d_Z.p, d_A.p, d_53.p, d_73.p, d_52.p, d_zz.p, d_lgP.p, d_ion.p,
+                 d_Yion.p};
+    ds_crust_composition_kernel<<<(nz + 127) / 128, 128, 0, s>>>(a);
+    CK(cudaGetLastError());
+    CK(d_ion.download(ionic, (size_t)11 * nz, s));
+    CK(d_Yion.download(Yion, (size_t)nch * nz, s));
+    CK(cudaStreamSynchronize(s));
+    if (ncharged) *ncharged = nch;
+    return DSTAR_OK;
+}
+
+// ------------------------------------------------------------------ batches
+int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int ncharged, dstar_batch** out) {
+    if (!c || !out || n_star < 1 || !zone_offset || ncharged < 1) return fail(DSTAR_ERR_ARG, "batch_create");
+    CK(cudaSetDevice(c->device));
+    dstar_batch* b = new dstar_batch;
+    b->ctx = c; b->n_star = n_star; b->ncharged = ncharged;
+    b->h_zone_offset.assign(zone_offset, zone_offset + n_star + 1);
+    b->total = zone_offset[n_star];
+    std::vector<int> zs(b->total);
+    for (int s = 0; s < n_star; ++s) {
+        int nz = zone_offset[s + 1] - zone_offset[s];
+        if (nz < 3 || nz > DS_MAXZ) { delete b; return fail(DSTAR_ERR_ARG, "each star needs 3 <= nz <= 512 zones"); }
+        b->max_nz = std::max(b->max_nz, nz);
+        for (int z = zone_offset[s]; z < zone_offset[s + 1]; ++z) zs[z] = s;
+    }
+    cudaStream_t st = c->stream;
+    CK(b->zone_offset.upload(b->h_zone_offset.data(), n_star + 1, st));
+    CK(b->zone_star.upload(zs.data(), b->total, st));
+    CK(b->status.alloc(n_star)); CK(cudaMemsetAsync(b->status.p, 0, n_star * sizeof(int), st));
+    CK(b->rho_bar1.alloc(n_star));
+    CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
+    CK(cudaStreamSynchronize(st));
+    *out = b;
+    return DSTAR_OK;
+}
+
+void dstar_batch_destroy(dstar_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    delete b;
+}
+
+int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double* rho_bar, const double* P,
+                                 const double* P_bar, const double* dm, const double* ionic, const double* ionic_bar,
+                                 const double* Yion, const double* Yion_bar, const double* Zion, const double* Aion,
+                                 const double* Tc_cell, const double* Tc_face) {
+    if (!b || !rho || !rho_bar || !P || !P_bar || !dm || !ionic || !ionic_bar || !Yion || !Yion_bar || !Zion || !Aion)
+        return fail(DSTAR_ERR_ARG, "batch_upload_structure");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t n = b->total;
+    CK(b->rho.upload(rho, n, s)); CK(b->rho_bar.upload(rho_bar, n, s)); CK(b->P.upload(P, n, s));
+    CK(b->P_bar.upload(P_bar, n, s)); CK(b->dm.upload(dm, n, s)); CK(b->ionic.upload(ionic, 11 * n, s));
+    CK(b->ionic_bar.upload(ionic_bar, 11 * n, s)); CK(b->Yion.upload(Yion, b->ncharged * n, s));
+    CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, s)); CK(b->Zion.upload(Zion, b->ncharged, s));
+    CK(b->Aion.upload(Aion, b->ncharged, s));
+    b->have_Tc_cell = Tc_cell != nullptr; b->have_Tc_face = Tc_face != nullptr;
+    if (Tc_cell) CK(b->Tc_cell.upload(Tc_cell, 3 * n, s));
+    if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, s));
+    // rho_bar(1) starts from the uploaded value of each star's first face
+    std::vector<double> rb1(b->n_star);
+    for (int i = 0; i < b->n_star; ++i) rb1[i] = rho_bar[b->h_zone_offset[i]];
+    CK(b->rho_bar1.upload(rb1.data(), b->n_star, s));
+    CK(cudaStreamSynchronize(s));
+    b->have_structure = true;
+    return DSTAR_OK;
+}
+
+int dstar_batch_set_Tc_face(dstar_batch* b, const double* Tc_face) {
+    if (!b || !Tc_face) return fail(DSTAR_ERR_ARG, "set_Tc_face");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(b->Tc_face.upload(Tc_face, (size_t)3 * b->total, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    b->have_Tc_face = true;
+    return DSTAR_OK;
+}
+int dstar_batch_set_ionic_bar(dstar_batch* b, const double* ionic_bar) {
+    if (!b || !ionic_bar) return fail(DSTAR_ERR_ARG, "set_ionic_bar");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(b->ionic_bar.upload(ionic_bar, (size_t)11 * b->total, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    return DSTAR_OK;
+}
+int dstar_batch_get_rho_bar1(dstar_batch* b, double* rho_bar1) {
+    if (!b || !rho_bar1) return fail(DSTAR_ERR_ARG, "get_rho_bar1");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(b->rho_bar1.download(rho_bar1, b->n_star, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    return DSTAR_OK;
+}
+
+int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int which) {
+    if (!b || which < 1 || which > 3) return fail(DSTAR_ERR_ARG, "batch_micro_tables");
+    if (!b->have_structure) return fail(DSTAR_ERR_STATE, "structure not uploaded");
+    dstar_ctx* c = b->ctx;
+    if (!c->helm_loaded) return fail(DSTAR_ERR_STATE, "HELM table not loaded (dstar_ctx_set_helm)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t tsz = (size_t)4 * DS_NTAB * b->total;
+    if (!b->tab_lnCp.p) {
+        CK(b->tab_lnCp.alloc(tsz)); CK(b->tab_lnGamma.alloc(tsz)); CK(b->tab_lnEnu.alloc(tsz)); CK(b->tab_lnK.alloc(tsz));
+    }
+    DsMicroArgs a{};
+    a.total_zones = b->total; a.ncharged = b->ncharged; a.zone_star = b->zone_star.p; a.zone_offset = b->zone_offset.p;
+    a.rho = b->rho.p; a.rho_bar = b->rho_bar.p; a.P = b->P.p; a.P_bar = b->P_bar.p; a.dm = b->dm.p;
+    a.ionic = b->ionic.p; a.ionic_bar = b->ionic_bar.p; a.Yion = b->Yion.p; a.Yion_bar = b->Yion_bar.p;
+    a.Zion = b->Zion.p; a.Aion = b->Aion.p;
+    a.Tc_cell = b->have_Tc_cell ? b->Tc_cell.p : nullptr;
+    a.Tc_face = b->have_Tc_face ? b->Tc_face.p : nullptr;
+    a.tab_lnT = c->tab_lnT.p; a.tab_T = c->tab_T.p; a.tab_lgT = c->tab_lgT.p;
+    a.eos = eos_ctrl_from(ctrl); a.cond = cond_ctrl_from(ctrl);
+    const int defch[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) a.nu_channels[i] = defch[i];
+    if (ctrl) {
+        a.nu_channels[0] = ctrl->use_crust_nu_pair; a.nu_channels[1] = ctrl->use_crust_nu_photo;
+        a.nu_channels[2] = ctrl->use_crust_nu_plasma; a.nu_channels[3] = ctrl->use_crust_nu_bremsstrahlung;
+        a.nu_channels[4] = ctrl->use_crust_nu_pbf;
+        a.turn_on_shell_Urca = ctrl->turn_on_shell_Urca;
+        a.shell_Urca_luminosity_coeff = ctrl->shell_Urca_luminosity_coeff; a.lgP_shell_Urca = ctrl->lgP_shell_Urca;
+    }
+    a.rho_bar1 = b->rho_bar1.p; a.status = b->status.p;
+    a.tab_lnCp = b->tab_lnCp.p; a.tab_lnGamma = b->tab_lnGamma.p; a.tab_lnEnu = b->tab_lnEnu.p; a.tab_lnK = b->tab_lnK.p;
+    b->launches = 0;
+    if (which & 1) {
+        CK(cudaEventRecord(b->ev0, s));
+        ds_micro_kernel<false><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev1, s));
+        CK(cudaEventSynchronize(b->ev1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[0] = ms;
+        ++b->launches;
+    }
+    if (which & 2) {
+        CK(cudaEventRecord(b->ev0, s));
+        ds_micro_kernel<true><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev1, s));
+        CK(cudaEventSynchronize(b->ev1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[1] = ms;
+        ++b->launches;
+    }
+    b->have_tables = true;
+    return DSTAR_OK;
+}
+
+int dstar_batch_download_tables(dstar_batch* b, double* tab_lnT, double* tab_lnCp, double* tab_lnGamma,
+                                double* tab_lnEnu, double* tab_lnK, double* rho_bar1, int32_t* status) {
+    if (!b) return fail(DSTAR_ERR_ARG, "batch_download_tables");
+    if (!b->have_tables) return fail(DSTAR_ERR_STATE, "tables not computed");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t tsz = (size_t)4 * DS_NTAB * b->total;
+    if (tab_lnT) std::memcpy(tab_lnT, b->ctx->h_tab_lnT, sizeof(double) * DS_NTAB);
+    if (tab_lnCp) CK(b->tab_lnCp.download(tab_lnCp, tsz, s));
+    if (tab_lnGamma) CK(b->tab_lnGamma.download(tab_lnGamma, tsz, s));
+    if (tab_lnEnu) CK(b->tab_lnEnu.download(tab_lnEnu, tsz, s));
+    if (tab_lnK) CK(b->tab_lnK.download(tab_lnK, tsz, s));
+    if (rho_bar1) CK(b->rho_bar1.download(rho_bar1, b->n_star, s));
+    if (status) CK(b->status.download(status, b->n_star, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_batch_upload_tables(dstar_batch* b, const double* tab_lnT, const double* tab_lnCp, const double* tab_lnGamma,
+                              const double* tab_lnEnu, const double* tab_lnK) {
+    if (!b || !tab_lnCp || !tab_lnGamma || !tab_lnEnu || !tab_lnK) return fail(DSTAR_ERR_ARG, "batch_upload_tables");
+    (void)tab_lnT;
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t tsz = (size_t)4 * DS_NTAB * b->total;
+    CK(b->tab_lnCp.upload(tab_lnCp, tsz, s)); CK(b->tab_lnGamma.upload(tab_lnGamma, tsz, s));
+    CK(b->tab_lnEnu.upload(tab_lnEnu, tsz, s)); CK(b->tab_lnK.upload(tab_lnK, tsz, s));
+    CK(cudaStreamSynchronize(s));
+    b->have_tables = true;
+    return DSTAR_OK;
+}
+
+int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double* area, const double* ePhi,
+                              const double* e2Phi, const double* ePhi_bar, const double* e2Phi_bar, int n_atm,
+                              int atm_nv, const double* atm_lgTb, const double* atm_lgTeff, const double* atm_lgflux,
+                              const int32_t* atm_index, const double* heat, const double* T_atm, const double* lnT0,
+                              int n_epoch, const double* epoch_boundaries, const double* epoch_Mdots,
+                              const double* enuc_per_Mdot) {
+    if (!b || !dm_bar || !area || !ePhi || !e2Phi || !ePhi_bar || !e2Phi_bar || n_atm < 1 || atm_nv < 2 || !atm_lgTb ||
+        !atm_lgTeff || !atm_lgflux || !atm_index || !heat || !T_atm || !lnT0 || n_epoch < 1 || !epoch_boundaries ||
+        !epoch_Mdots)
+        return fail(DSTAR_ERR_ARG, "batch_upload_evolve");
+    if (!b->have_structure) return fail(DSTAR_ERR_STATE, "structure not uploaded");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t n = b->total, ns = b->n_star;
+    CK(b->dm_bar.upload(dm_bar, n, s)); CK(b->area.upload(area, n, s)); CK(b->ePhi.upload(ePhi, n, s));
+    CK(b->e2Phi.upload(e2Phi, n, s)); CK(b->ePhi_bar.upload(ePhi_bar, n, s)); CK(b->e2Phi_bar.upload(e2Phi_bar, n, s));
+    CK(b->atm_lgTb.upload(atm_lgTb, (size_t)n_atm * atm_nv, s));
+    CK(b->atm_lgTeff.upload(atm_lgTeff, (size_t)n_atm * 4 * atm_nv, s));
+    CK(b->atm_lgflux.upload(atm_lgflux, (size_t)n_atm * 4 * atm_nv, s));
+    CK(b->atm_index.upload(atm_index, ns, s)); CK(b->heat.upload(heat, 9 * ns, s)); CK(b->T_atm.upload(T_atm, ns, s));
+    CK(b->lnT.upload(lnT0, n, s));
+    CK(b->epoch_boundaries.upload(epoch_boundaries, (size_t)(n_epoch + 1) * ns, s));
+    CK(b->epoch_Mdots.upload(epoch_Mdots, (size_t)n_epoch * ns, s));
+    b->have_enuc = enuc_per_Mdot != nullptr;
+    if (enuc_per_Mdot) CK(b->enuc.upload(enuc_per_Mdot, n, s));
+    b->n_epoch = n_epoch; b->n_atm = n_atm; b->atm_nv = atm_nv;
+    CK(b->dt.alloc(ns)); CK(b->tsec.alloc(ns)); CK(b->model.alloc(ns));
+    CK(cudaMemsetAsync(b->dt.p, 0, ns * sizeof(double), s));   // NScool_init.f:59-62
+    CK(cudaMemsetAsync(b->tsec.p, 0, ns * sizeof(double), s));
+    CK(cudaMemsetAsync(b->model.p, 0, ns * sizeof(int), s));
+    CK(b->t_mon.alloc((size_t)n_epoch * ns)); CK(b->Teff_mon.alloc((size_t)n_epoch * ns));
+    CK(b->Qb_mon.alloc((size_t)n_epoch * ns)); CK(b->idid.alloc((size_t)n_epoch * ns));
+    CK(b->counters.alloc(7 * ns)); CK(b->Teff.alloc(ns)); CK(b->Lsurf.alloc(ns));
+    CK(cudaStreamSynchronize(s));
+    b->have_evolve = true;
+    return DSTAR_OK;
+}
+
+int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
+    if (!b || !ctrl) return fail(DSTAR_ERR_ARG, "batch_evolve");
+    if (!b->have_evolve || !b->have_tables) return fail(DSTAR_ERR_STATE, "evolve inputs / tables missing");
+    dstar_ctx* c = b->ctx;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t ns = b->n_star;
+    if (trace_cap < 0) trace_cap = 0;
+    if (trace_cap != b->trace_cap || (trace_cap > 0 && !b->trace_model.p)) {
+        const size_t tn = (size_t)trace_cap * ns;
+        CK(b->trace_count.alloc(ns)); CK(b->trace_model.alloc(tn)); CK(b->tr_tsec.alloc(tn)); CK(b->tr_dt.alloc(tn));
+        CK(b->tr_Teff.alloc(tn)); CK(b->tr_Lsurf.alloc(tn)); CK(b->tr_Lnu.alloc(tn)); CK(b->tr_Lnuc.alloc(tn));
+        CK(b->tr_Mdot.alloc(tn));
+        b->trace_cap = trace_cap;
+    }
+    DsEvolveArgs a{};
+    a.n_star = b->n_star; a.n_epoch = b->n_epoch; a.n_tab = DS_NTAB; a.zone_offset = b->zone_offset.p;
+    a.tab_lnT = c->tab_lnT.p; a.tab_lnK = b->tab_lnK.p; a.tab_lnCp = b->tab_lnCp.p; a.tab_lnGamma = b->tab_lnGamma.p;
+    a.tab_lnEnu = b->tab_lnEnu.p;
+    a.dm = b->dm.p; a.dm_bar = b->dm_bar.p; a.area = b->area.p; a.rho_bar = b->rho_bar.p; a.ePhi = b->ePhi.p;
+    a.e2Phi = b->e2Phi.p; a.ePhi_bar = b->ePhi_bar.p; a.e2Phi_bar = b->e2Phi_bar.p; a.P = b->P.p;
+    a.atm_index = b->atm_index.p; a.atm_nv = b->atm_nv; a.atm_lgTb = b->atm_lgTb.p; a.atm_lgTeff = b->atm_lgTeff.p;
+    a.atm_lgflux = b->atm_lgflux.p; a.heat = b->heat.p; a.enuc_override = b->have_enuc ? b->enuc.p : nullptr;
+    a.T_atm = b->T_atm.p; a.epoch_boundaries = b->epoch_boundaries.p; a.epoch_Mdots = b->epoch_Mdots.p;
+    a.turn_on_extra_heating = ctrl->turn_on_extra_heating; a.fix_core_temperature = ctrl->fix_core_temperature;
+    a.make_inner_boundary_insulating = ctrl->make_inner_boundary_insulating;
+    a.fix_atmosphere_temperature_when_accreting = ctrl->fix_atmosphere_temperature_when_accreting;
+    a.suppress_first_step_output = ctrl->suppress_first_step_output;
+    a.starting_number_for_profile = ctrl->starting_number_for_profile;
+    a.maximum_number_of_models = ctrl->maximum_number_of_models;
+    a.integration_tolerance = ctrl->integration_tolerance; a.min_lg_T = ctrl->min_lg_temperature_integration;
+    a.max_lg_T = ctrl->max_lg_temperature_integration; a.maximum_timestep = ctrl->maximum_timestep;
+    a.lnT = b->lnT.p; a.dt = b->dt.p; a.tsec = b->tsec.p; a.model = b->model.p;
+    a.t_monitor = b->t_mon.p; a.Teff_monitor = b->Teff_mon.p; a.Qb_monitor = b->Qb_mon.p; a.Teff = b->Teff.p;
+    a.Lsurf = b->Lsurf.p; a.idid = b->idid.p; a.counters = b->counters.p;
+    a.trace_cap = trace_cap; a.trace_count = trace_cap ? b->trace_count.p : nullptr; a.trace_model = b->trace_model.p;
+    a.trace_tsec = b->tr_tsec.p; a.trace_dt = b->tr_dt.p; a.trace_Teff = b->tr_Teff.p; a.trace_Lsurf = b->tr_Lsurf.p;
+    a.trace_Lnu = b->tr_Lnu.p; a.trace_Lnuc = b->tr_Lnuc.p; a.trace_Mdot = b->tr_Mdot.p;
+    // the star's rho_bar(1) is the fixed-up one (create_model.f:367-369): patch it into rho_bar
+    // (the evolve kernel never reads face 0's rho_bar, L(1) comes from the atmosphere; kept for symmetry)
+    CK(cudaEventRecord(b->ev0, s));
+    const int threads = ((b->max_nz + 31) / 32) * 32;
+    if (threads <= 256) ds_evolve_kernel<256><<<b->n_star, threads, 0, s>>>(a);
+    else ds_evolve_kernel<512><<<b->n_star, threads, 0, s>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, s));
+    CK(cudaEventSynchronize(b->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[2] = ms;
+    b->launches = 1;
+    return DSTAR_OK;
+}
+
+int dstar_batch_download_results(dstar_batch* b, double* t_monitor, double* Teff_monitor, double* Qb_monitor,
+                                 int32_t* idid, int32_t* counters, double* lnT, double* Teff, double* Lsurf,
+                                 double* dt, double* tsec, int32_t* model) {
+    if (!b) return fail(DSTAR_ERR_ARG, "batch_download_results");
+    if (!b->have_evolve) return fail(DSTAR_ERR_STATE, "nothing evolved");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t ns = b->n_star, ne = b->n_epoch;
+    if (t_monitor) CK(b->t_mon.download(t_monitor, ne * ns, s));
+    if (Teff_monitor) CK(b->Teff_mon.download(Teff_monitor, ne * ns, s));
+    if (Qb_monitor) CK(b->Qb_mon.download(Qb_monitor, ne * ns, s));
+    if (idid) CK(b->idid.download(idid, ne * ns, s));
+    if (counters) CK(b->counters.download(counters, 7 * ns, s));
+    if (lnT) CK(b->lnT.download(lnT, b->total, s));
+    if (Teff) CK(b->Teff.download(Teff, ns, s));
+    if (Lsurf) CK(b->Lsurf.download(Lsurf, ns, s));
+    if (dt) CK(b->dt.download(dt, ns, s));
+    if (tsec) CK(b->tsec.download(tsec, ns, s));
+    if (model) CK(b->model.download(model, ns, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_batch_download_trace(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* dt, double* Teff,
+                               double* Lsurf, double* Lnu, double* Lnuc, double* Mdot) {
+    if (!b || b->trace_cap <= 0) return fail(DSTAR_ERR_STATE, "no trace kept");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t tn = (size_t)b->trace_cap * b->n_star;
+    if (count) CK(b->trace_count.download(count, b->n_star, s));
+    if (model) CK(b->trace_model.download(model, tn, s));
+    if (tsec) CK(b->tr_tsec.download(tsec, tn, s));
+    if (dt) CK(b->tr_dt.download(dt, tn, s));
+    if (Teff) CK(b->tr_Teff.download(Teff, tn, s));
+    if (Lsurf) CK(b->tr_Lsurf.download(Lsurf, tn, s));
+    if (Lnu) CK(b->tr_Lnu.download(Lnu, tn, s));
+    if (Lnuc) CK(b->tr_Lnuc.download(Lnuc, tn, s));
+    if (Mdot) CK(b->tr_Mdot.download(Mdot, tn, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+double dstar_batch_last_kernel_ms(dstar_batch* b, int which) {
+    if (!b || which < 0 || which > 2) return -1.0;
+    return b->ms[which];
+}
+int dstar_batch_last_launch_count(dstar_batch* b) { return b ? b->launches : 0; }
+
+int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, int ncharged, const double* rho,
+                       const double* rho_bar, const double* P, const double* P_bar, const double* dm,
+                       const double* ionic, const double* ionic_bar, const double* Yion, const double* Yion_bar,
+                       const double* Zion, const double* Aion, const double* Tc_cell, const double* Tc_face,
+                       const dstar_micro_ctrl* ctrl, double* tab_lnT, double* tab_lnCp, double* tab_lnGamma,
+                       double* tab_lnEnu, double* tab_lnK, double* rho_bar1, int32_t* status) {
+    dstar_batch* b = nullptr;
+    int rc = dstar_batch_create(ctx, n_star, zone_offset, ncharged, &b);
+    if (rc != DSTAR_OK) return rc;
+    rc = dstar_batch_upload_structure(b, rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion,
+                                      Tc_cell, Tc_face);
+    if (rc == DSTAR_OK) rc = dstar_batch_micro_tables(b, ctrl, 3);
+    if (rc == DSTAR_OK)
+        rc = dstar_batch_download_tables(b, tab_lnT, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK, rho_bar1, status);
+    dstar_batch_destroy(b);
+    return rc;
+}
+
+int dstar_fp64_peak_tflops(dstar_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(DSTAR_ERR_ARG, "fp64_peak");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int blocks = c->prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    DevBuf<double> out;
+    CK(out.alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, s));
+        ds_fp64_peak_kernel<<<blocks, threads, 0, s>>>(out.p, iters, 1.0 + rep);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return DSTAR_OK;
+}
+
+}  // extern "C"

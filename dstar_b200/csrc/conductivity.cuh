@@ -1,0 +1,457 @@
+// Device thermal conductivity (sm_100a, FP64).
+//
+// B200-native replacement for get_thermal_conductivity (conductivity/public/conductivity_lib.f:108-125)
+// -> conductivity (conductivity/private/eval_conductivity.f:6-143): electron channels ee_SY06 /
+// ee_PCY / eion / eQ / eQ_page (electron_conductivity.f:7-222), radiative opacity
+// (photon_conductivity.f:7-108), neutron-impurity / neutron-phonon scattering
+// (neutron_conductivity.f:69-383; two adaptive DOP853 quadratures per evaluation) and superfluid
+// phonons sPh (:12-67).
+//
+// The impurity structure-factor integral does not depend on T (neutron_conductivity.f:382), so
+// the coefficient-pass kernel evaluates it once per zone (ds_lambda_imp) and shares it across
+// the 128 temperature lanes; the phonon integral is per lane.
+#pragma once
+#include "dconst.cuh"
+#include "coef_tables.cuh"
+#include "eos.cuh"
+
+struct DsCondCtrl {  // conductivity_def.f:29-52
+    int include_neutrons, include_sf_phonons, ee_fmla, eQ_fmla;
+    double rad_full_off_lgrho, rad_full_on_lgrho;
+};
+struct DsCond {
+    double total, ee, ei, eQ, sf, nQ, np, kap, electron_total, neutron_total;
+};
+
+namespace dsk {
+using namespace dsc;
+
+
+DS_D double ee_PCY(double ne, double T) {
+    const double onesixth = (double)(1.0f / 6.0f);
+    double yfac = ds_hc.yfac;
+    double mec2 = Melectron * clight * clight;
+    double eefac = 1.5 * (finestructure * finestructure) * mec2 / dsd::ipow<3>(pi) / hbar;
+    double befac = ds_hc.befac;
+    double kF = pow(3.0 * (pi * pi) * ne, onethird);
+    double x = kF * hbar / Melectron / clight;
+    double eF = sqrt(1.0 + x * x);
+    double beta = x / eF;
+    double b2 = beta * beta;
+    double be3 = befac / pow(beta, 1.5);
+    double plasma_theta = boltzmann * T / mec2;
+    double y = yfac * pow(x, 1.5) / plasma_theta / sqrt(eF);
+    double lJ = 1.0 + (DS_R4(2.810) - DS_R4(0.810) * b2) / y;
+    double llJ = log(lJ);
+    double J0 = onethird / dsd::ipow<3>(1.0 + DS_R4(0.07414) * y);
+    double J1 = J0 * llJ + onesixth * dsd::ipow<5>(pi) * y / dsd::ipow<4>(DS_R4(13.91) + y);
+    double J2 = 1.0 + DS_R4(0.4) * (3.0 + 1.0 / (x * x)) / (x * x);
+    double J = dsd::ipow<3>(y) * J1 * J2;
+    return eefac * (plasma_theta * plasma_theta) * J / eF / be3;
+}
+
+DS_D double ee_SY06(double ne, double T) {
+    double nu_pre = 36.0 * (finestructure * finestructure) * (hbar * hbar) * clight / pi / boltzmann / Melectron;
+    double Tp_pre = ds_hc.Tp_pre;
+    double kF = pow(threepisquare * ne, onethird);
+    double xF = hbar * kF / Melectron / clight;
+    double eF = sqrt(1.0 + xF * xF);
+    double u = xF / eF;
+    double Tp = Tp_pre * sqrt(ne / eF);
+    double theta = (double)sqrtf(3.0f) * Tp / T;
+    double u2 = u * u, u3 = u * u * u, u4 = dsd::ipow<4>(u);
+    double tu = theta * u;
+    double At = 20.0 + 450.0 * u3;
+    double Ct1 = DS_R4(0.05067) + DS_R4(0.03216) * u2;
+    double Ct2 = DS_R4(0.0254) + DS_R4(0.04127) * u4;
+    double Ct = At * exp(Ct1 / Ct2);
+    double Alt = DS_R4(12.2) + DS_R4(25.2) * u3;
+    double Blt = 1.0 - 0.75 * u;
+    double Clt1 = DS_R4(0.123636) + DS_R4(0.016234) * u2;
+    double Clt2 = DS_R4(0.0762) + DS_R4(0.05714) * u4;
+    double Clt = Alt * exp(Clt1 / Clt2);
+    double Il = (1.0 / u) * (DS_R4(0.1587) - DS_R4(0.02538) / (1.0 + DS_R4(0.0435) * theta)) *
+                log(1.0 + DS_R4(128.56) / theta / (DS_R4(37.1) + theta * (DS_R4(10.83) + theta)));
+    double It = u3 * (DS_R4(2.404) / Ct + (Ct2 - DS_R4(2.404) / Ct) / (1.0 + DS_R4(0.1) * tu)) *
+                log(1.0 + Ct / tu / (At + tu));
+    double Ilt = u * (DS_R4(18.52) * u2 / Clt + (Clt2 - DS_R4(18.2) * u2 / Clt) / (1.0 + DS_R4(0.1558) * pow(theta, Blt))) *
+                 log(1.0 + Clt / (Alt * theta + DS_R4(10.83) * (tu * tu) + pow(tu, (double)(8.0f / 3.0f))));
+    double I = Il + It + Ilt;
+    return nu_pre * ne * I / eF / T;
+}
+
+DS_D double eone(double z) {
+    const double a0 = DS_R4(0.1397), a1 = DS_R4(0.5772), a2 = DS_R4(2.2757);
+    double z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+    return exp(-z4 / (z3 + a0)) * (log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
+}
+
+DS_D double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z2, double Z53, double A) {
+    (void)Ye;
+    const double um1 = DS_R4(2.8), um2 = DS_R4(12.973);
+    const double onesixth = (double)(1.0f / 6.0f), fourthird = 4.0 * onethird;
+    double sw_max = dbl_max_log;
+    double electroncompton = hbar / Melectron / clight;
+    double eifac = fourthird * clight * (finestructure * finestructure) / electroncompton / pi;
+    double kF2 = kF * kF;
+    double x = electroncompton * kF;
+    double eF = sqrt(1.0 + x * x);
+    double v = x / eF;
+    double v2 = v * v;
+    double Gamma = Gamma_e * Z53;
+    double s = finestructure / pi / v;
+    double kTF2 = 4.0 * s * kF2;
+    double eta02 = dsd::ipow<2>(DS_R4(0.19) / pow(Z, onesixth));
+    double aei = ds_hc.aei_fac * kF;
+    double qD2 = 3.0 * Gamma_e * (aei * aei) * Z2 / Z;
+    double beta = pi * finestructure * Z * v;
+    double qi2 = qD2 * (1.0 + DS_R4(0.06) * Gamma) * exp(-sqrt(Gamma));
+    double qs2 = (qi2 + kTF2) * exp(-beta);
+    (void)qs2;
+    double Gs = eta / sqrt(eta * eta + eta02) * (1.0 + DS_R4(0.122) * (beta * beta));
+    double Gk0 = 1.0 / pow(eta * eta + DS_R4(0.0081), 1.5);
+    double Gk1 = 1.0 + beta * dsd::ipow<3>(v);
+    double GkZ = 1.0 - 1.0 / Z;
+    double Gk = Gs + DS_R4(0.0105) * GkZ * Gk1 * Gk0 * eta;
+    double a0 = 4.0 * kF2 / qD2 / eta;
+    double D1 = exp(DS_R4(-9.1) * eta);
+    double D = exp(-a0 * um1 * D1 * 0.25);
+    double w1 = 1.0 + onethird * beta;
+    double w = 4.0 * um2 * kF2 / qD2 * w1;
+    double sw = s * w;
+    double L1, L2;
+    if (sw < sw_max) {
+        double fac = exp(sw) * (eone(sw) - eone(sw + w));
+        L1 = 0.5 * (log(1.0 + 1.0 / s) + (1.0 - exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
+        L2 = 0.5 * (1.0 - (1.0 - exp(-w)) / w +
+                    s * (s / (1.0 + s) * (1.0 - exp(-w)) - 2.0 * log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
+    } else {
+        L1 = 0.5 * (log((s + 1.0) / s) - 1.0 / (s + 1.0));
+        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * log((s + 1.0) / s);
+    }
+    double Lei = (Z2 / A) * (L1 - v2 * L2) * Gk * D;
+    return eifac * eF * Lei * A / Z;
+}
+
+DS_D double eQ(double kF, double Z, double A, double Q) {
+    double electron_compton = hbar / Melectron / clight;
+    double fac = 4.0 * onethird * clight * (finestructure * finestructure) / electron_compton / pi;
+    double dZ2 = Q / A;
+    double x = electron_compton * kF;
+    double gamma = sqrt(1.0 + x * x);
+    double v = x / gamma;
+    double v2 = v * v;
+    double s = finestructure / pi / v;
+    double L1 = 1.0 + 4.0 * v2 * s;
+    double L = 0.5 * (L1 * log(1.0 + 1.0 / s) - v2 - 1.0 / (s + 1.0) - v2 * s / (1.0 + s));
+    return fac * gamma * dZ2 * L * A / Z;
+}
+
+DS_D double eQ_page(double kF, double Z, double A, double Q) {
+    double electron_compton = hbar / Melectron / clight;
+    double fac = 4.0 * onethird * clight * (finestructure * finestructure) / electron_compton / pi;
+    double dZ2 = Q / A;
+    double x = electron_compton * kF;
+    double gamma = sqrt(1.0 + x * x);
+    double v = x / gamma;
+    double qs = DS_R4(0.048196) / sqrt(v);
+    double L = log(1.0 / qs) - 0.5 * (1 + v * v);
+    return fac * gamma * dZ2 * L * A / Z;
+}
+
+DS_D double electron_scattering(double eta_e, double theta, double Ye) {
+    double xi = exp(DS_R4(0.8168) * eta_e - DS_R4(0.05522) * (eta_e * eta_e));
+    double xi2 = xi * xi;
+    double theta2 = theta * theta;
+    double t1 = DS_R4(1.129) + DS_R4(0.2965) * xi - DS_R4(0.005594) * xi2;
+    double t2 = DS_R4(11.47) + DS_R4(0.3570) * xi + DS_R4(0.1078) * xi2;
+    double t3 = DS_R4(-3.249) + DS_R4(0.1678) * xi - DS_R4(0.04706) * xi2;
+    double Gbar = t1 + t2 * theta + t3 * theta2;
+    return Thomson * avogadro * Ye / Gbar;
+}
+
+DS_D double freefree(double rho, double T, double eta_e, const DsComp& c) {
+    const double bfac = DS_R4(0.753);
+    double rY = rho * c.Ye;
+    double T8 = T * 1.0e-8;
+    double T8_32 = pow(T8, 1.5);
+    double xx;
+    if (eta_e > dbl_max_log) xx = eta_e;
+    else xx = log(1.0 + exp(eta_e));
+    double norm = 1.16 * 8.02e3 * xx * T8_32 / rY;
+    double x = pow(1.0 + xx, twothird);
+    double gam = sqrt(DS_R4(1.58e-3) / T8) * c.Z;
+    double sxpt = sqrt(x + 10.0);
+    double sx = sqrt(x);
+    double tpg = 2.0 * pi * gam;
+    double expnum = exp(-tpg / sxpt);
+    double expden = exp(-tpg / sx);
+    double elwert = (1.0 - expnum) / (1.0 - expden);
+    double relfactor = 1.0 + pow(T8 / DS_R4(7.7), 1.5);
+    double gff = norm * elwert * relfactor;
+    return bfac * (rY / 1.0e5) / pow(T8, 3.5) * gff * c.Z2 / c.A;
+}
+
+DS_D double Rosseland_kappa(double rho, double T, double mu_e, const DsComp& c) {
+    double eta_e = mu_e * mev_to_ergs / boltzmann / T;
+    double theta = T * boltzmann / Melectron / clight2;
+    double kap_th = electron_scattering(eta_e, theta, c.Ye);
+    double kap_ff = freefree(rho, T, eta_e, c);
+    double T6 = T * 1.0e-6;
+    double T_Ry = T6 / 0.15789 / c.Z2;
+    double f = kap_ff / (kap_ff + kap_th);
+    double A = 1.0 + (1.097 + 0.777 * T_Ry) / (1.0 + 0.536 * T_Ry) * pow(f, 0.617) * pow(1.0 - f, 0.77);
+    return (kap_th + kap_ff) * A;
+}
+
+// ---------------------------------------------------------------- neutron channels
+// Structure-factor integrands of Deibel et al. (2017), neutron_conductivity.f:291-383.
+struct SfacPar {
+    double T, Z, A, Yn, kfn, R_a;
+};
+template <bool PHONON>
+DS_D double sfac(double x, const SfacPar& p) {
+    double formfac = fabs(3.0 * (sin(x) - x * cos(x)) / dsd::ipow<3>(x));
+    if (!PHONON) return dsd::ipow<3>(x) * (formfac * formfac);
+    double nn = dsd::ipow<3>(p.kfn) / threepisquare;
+    double nion = nn / p.Yn * (1.0 - p.Yn) / p.A;
+    double aion = pow(3.0 / (4.0 * pi * nion), onethird);
+    double mion = (p.A - p.Z) * Mneutron + p.Z * Mproton;
+    double omegaP = pow(hbar * clight * 4. * pi * (p.Z * p.Z) * finestructure * nion / mion, 0.5);
+    double eta = boltzmann * p.T / (hbar * omegaP);
+    double Gamma = hbar * clight * (p.Z * p.Z) * finestructure / (boltzmann * p.T * aion);
+    double a1 = dsd::ipow<2>(x / p.R_a * aion) / (3. * Gamma * eta);
+    double um1 = DS_R4(2.8);
+    double um2 = 13.0;
+    double w = a1 * (um1 * exp(DS_R4(-9.1) * eta) + 2. * eta * um2) / 4.;
+    double w1 = a1 * um2 * (eta * eta) / (2. * pow(eta * eta + dsd::ipow<2>(um2 / 117.), 0.5));
+    double ssig = exp(-2. * (w - w1)) * (1.0 - exp(-2. * w1));
+    double dskappa2 = a1 * 91. * (eta * eta) * exp(-2. * w) / dsd::ipow<2>(1. + DS_R4(111.4) * (eta * eta));
+    double dskappa4 = a1 * DS_R4(0.101) * dsd::ipow<4>(eta) /
+                      ((DS_R4(0.06408) + eta * eta) * pow(DS_R4(0.001377) + eta * eta, 1.5));
+    double dskappa = dskappa2 + dskappa4;
+    return dsd::ipow<3>(x) * (formfac * formfac) * (ssig + (3. * dsd::ipow<2>(p.kfn * p.R_a / x) - 0.5) * dskappa);
+}
+
+// Scalar DOP853 (Hairer, Norsett & Wanner; the integrator behind MESA's num_lib dop853 that
+// neutron_conductivity.f:149,255 calls), specialised to one equation y' = g(x): rtol, atol scalar,
+// h0 = 0 (automatic), no dense output.  Returns idid (1 ok, -2 too many steps, -3 step too small).
+template <bool PHONON>
+DS_D int dop853_quad(const SfacPar& par, double x, double xend, int max_steps, double rtol, double atol,
+                     double& yout) {
+    const double uround = 2.3e-16, safe = 0.9, facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0;
+    double y = 0.0;
+    const double hmax = fabs(xend - x);
+    const double posneg = copysign(1.0, xend - x);
+    double k[13];
+    double facold = 1.0e-4;
+    bool last = false, reject = false;
+    int nstep = 0, naccpt = 0;
+    k[0] = sfac<PHONON>(x, par);
+    // hinit (iord = 8)
+    double h;
+    {
+        double sk = atol + rtol * fabs(y);
+        double dnf = (k[0] / sk) * (k[0] / sk), dny = (y / sk) * (y / sk);
+        if (dnf <= 1.0e-10 || dny <= 1.0e-10) h = 1.0e-6; else h = sqrt(dny / dnf) * 0.01;
+        h = fmin(h, hmax);
+        h = copysign(h, posneg);
+        double f1 = sfac<PHONON>(x + h, par);
+        double der2 = ((f1 - k[0]) / sk) * ((f1 - k[0]) / sk);
+        der2 = sqrt(der2) / h;
+        double der12 = fmax(fabs(der2), sqrt(dnf));
+        double h1;
+        if (der12 <= 1.0e-15) h1 = fmax(1.0e-6, fabs(h) * 1.0e-3); else h1 = pow(0.01 / der12, 1.0 / 8);
+        h = fmin(fmin(100.0 * fabs(h), h1), hmax);
+        h = copysign(h, posneg);
+    }
+    int idid = 1;
+    for (;;) {
+        if (nstep > max_steps) { idid = -2; break; }
+        if (0.1 * fabs(h) <= fabs(x) * uround) { idid = -3; break; }
+        if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
+        ++nstep;
+#pragma unroll
+        for (int s = 1; s < 12; ++s) k[s] = sfac<PHONON>(x + dop_c[s] * h, par);  // y' = g(x): stages need no y
+        double xph = x + h;
+        double k4 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) k4 += dop_b[j] * k[j];
+        double ynew = y + h * k4;
+        double sk = atol + rtol * fmax(fabs(y), fabs(ynew));
+        double e3 = 0.0, e5 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { e3 += dop_e3[j] * k[j]; e5 += dop_e5[j] * k[j]; }
+        double err2 = (e3 / sk) * (e3 / sk);
+        double err = (e5 / sk) * (e5 / sk);
+        double deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * sqrt(1.0 / (1 * deno));
+        double fac11 = pow(err, 0.125);
+        double fac = fac11 / pow(facold, 0.0);
+        fac = fmax(facc2, fmin(facc1, fac / safe));
+        double hnew = h / fac;
+        if (err <= 1.0) {
+            facold = fmax(err, 1.0e-4);
+            ++naccpt;
+            k[0] = sfac<PHONON>(xph, par);
+            y = ynew;
+            x = xph;
+            if (last) break;
+            if (fabs(hnew) > hmax) hnew = posneg * hmax;
+            if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
+            reject = false;
+        } else {
+            hnew = h / fmin(facc1, fac11 / safe);
+            reject = true;
+            last = false;
+        }
+        h = hnew;
+    }
+    yout = y;
+    return idid;
+}
+
+struct DsNucleus {  // SLy4 nuclear size model, neutron_conductivity.f:130-135
+    double n_in, R_a;
+};
+DS_D DsNucleus nucleus_model(const DsComp& c) {
+    double isospin = 1.0 - 2.0 * c.Z / c.A;
+    double n_0 = DS_R4(0.1740) / dsd::ipow<3>(fm_to_cm);
+    double n_2 = DS_R4(-0.0157) / dsd::ipow<3>(fm_to_cm);
+    double n_l = n_0 + n_2 * (isospin * isospin);
+    DsNucleus r;
+    r.n_in = n_l / 2.0 * (1.0 + DS_R4(0.9208) * isospin);
+    r.R_a = pow(3.0 * (c.A - c.Z) / 4.0 / pi / r.n_in, onethird);
+    return r;
+}
+// Lambda_n,imp: T-independent (neutron_conductivity.f:338-383, :149-153)
+DS_D int ds_lambda_imp(double nn, const DsComp& c, double& lambda) {
+    double kFn = pow(threepisquare * nn, onethird);
+    DsNucleus nuc = nucleus_model(c);
+    SfacPar par{0.0, c.Z, c.A, c.Yn, kFn, nuc.R_a};
+    return dop853_quad<false>(par, 1.0e-10, 2.0 * kFn * nuc.R_a, 1000, DS_R4(1.0e-4), DS_R4(1.0e-5), lambda);
+}
+DS_D int ds_lambda_phonon(double nn, double T, const DsComp& c, double& lambda) {
+    double kFn = pow(threepisquare * nn, onethird);
+    DsNucleus nuc = nucleus_model(c);
+    SfacPar par{T, c.Z, c.A, c.Yn, kFn, nuc.R_a};
+    return dop853_quad<true>(par, 1.0e-10, 2.0 * kFn * nuc.R_a, 1000, DS_R4(1.0e-4), DS_R4(1.0e-5), lambda);
+}
+// common prefactor of n_imp (:155-164) and n_phonon (:261-269): nu = pre * [Q/Z^2] * Lambda
+DS_D double neutron_nu_prefactor(double nn, double nion, const DsComp& c) {
+    const double twothird4 = (double)(2.0f / 3.0f);
+    DsNucleus nuc = nucleus_model(c);
+    double fac = (double)(4.0f / 27.0f) / pi / dsd::ipow<3>(hbar) / (clight * clight);
+    double V = hbar * hbar * pow(threepisquare * nuc.n_in, twothird4) / 2.0 / Mneutron *
+               (1.0 - pow(nn / nuc.n_in, twothird4));
+    double mnstar = Mneutron;
+    double EFn = DS_R4(15.1) * mev_to_ergs * pow(c.Yn, twothird4) *
+                     pow(nn * amu / c.Yn / DS_R4(1.0E14), twothird4) * (2.0 * Mneutron / mnstar) +
+                 Mneutron * (clight * clight);
+    return fac * EFn * (nion / nn) * dsd::ipow<2>(V * nuc.R_a);
+}
+
+// superfluid phonons, Aguilera et al. (2009); neutron_conductivity.f:12-67 (nn, nion in fm^-3)
+DS_D double sPh(double nn, double nion, double temperature, const DsComp& c) {
+    const double anl = DS_R4(10.0);
+    double K_n = boltzmann * clight * fm_to_cm / dsd::ipow<3>(hbarc_n * fm_to_cm);
+    double etwo = finestructure * hbarc_n;
+    double Mu_n = amu * clight2 * ergs_to_mev;
+    double T = temperature * boltzmann * ergs_to_mev;
+    double ai = pow(3.0 / fourpi / nion, onethird);
+    double kFn = pow(threepisquare * nn, onethird);
+    double kFe = pow(threepisquare * nion * c.Z, onethird);
+    double vs = hbarc_n * kFn / Mn_n / (double)sqrtf(3.0f);
+    double Cv = 2.0 * (pi * pi) * dsd::ipow<3>(T) / 15.0 / dsd::ipow<3>(vs);
+    double omega_p = sqrt(fourpi * etwo * c.Z2 * nion / c.A / Mu_n);
+    double qTFe = ds_hc.yfac * kFe;
+    double cs = omega_p / qTFe;
+    double alpha = cs / vs;
+    double anlt = anl / (1.0 + DS_R4(0.4) * kFn * anl + 0.5 * 2.0 * anl * (kFn * kFn));
+    double gmix = 2.0 * anlt * hbarc_n * sqrt(nion * kFn / c.A / (Mu_n * Mu_n));
+    double TUm = onethird * etwo * omega_p * pow(c.Z, onethird);
+    double omega = 3.0 * T / hbarc_n;
+    double fu = exp(-TUm / T);
+    double Llphn = 2.0 / pi / omega;
+    double Llphu = 100.0 * ai;
+    double Llph = 1.0 / (fu / Llphu + (1.0 - fu) / Llphn);
+    double tau_lph = Llph / cs;
+    double wt = tau_lph * omega;
+    double Lsph = Llph * dsd::ipow<2>(vs / gmix) * (1.0 + dsd::ipow<2>(1.0 - alpha * alpha) * (wt * wt)) / alpha / (wt * wt);
+    return onethird * Cv * vs * Lsph * K_n;
+}
+
+// eval_conductivity.f:6-143.  lambda_imp: the zone's precomputed impurity integral, or NaN to have
+// it evaluated here; imp_ierr its status.
+DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi, double Gamma,
+                          double eta, double mu_e, const DsComp& c, double Tns, double lambda_imp,
+                          int imp_ierr, DsCond& kap) {
+    const double eQ_threshold = 1.0e-8, sf_reduction_threshold = 1.0e-10;
+    kap = DsCond{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const double lgrho = log10(rho);
+    const double ne = rho / amu * c.Ye;
+    const double kF = pow(threepisquare * ne, onethird);
+    const double xF = hbar * kF / Melectron / clight;
+    const double eF = sqrt(1.0 + xF * xF);
+    const double Gamma_e = Gamma / c.Z53;
+    const double kappa_e_pre = onethird * (pi * pi) * (boltzmann * boltzmann) * T * ne / Melectron / eF;
+    double nu = 0.0, nu_c;
+
+    nu_c = (rq.ee_fmla == 2) ? ee_PCY(ne, T) : ee_SY06(ne, T);
+    nu = nu + nu_c;
+    if (nu_c > dbl_tiny) kap.ee = kappa_e_pre / nu_c;
+    nu_c = eion(kF, Gamma_e, eta, c.Ye, c.Z, c.Z2, c.Z53, c.A);
+    nu = nu + nu_c;
+    if (nu_c > dbl_tiny) kap.ei = kappa_e_pre / nu_c;
+    nu_c = (rq.eQ_fmla == 2) ? eQ_page(kF, c.Z, c.A, c.Q) : eQ(kF, c.Z, c.A, c.Q);
+    nu = nu + nu_c;
+    if (c.Q > eQ_threshold) kap.eQ = kappa_e_pre / nu_c;
+    kap.electron_total = kappa_e_pre / nu;
+
+    if (c.Yn > 0.0) {
+        const double nn = rho / amu * c.Yn / (1.0 - chi);
+        const double nion = rho / amu * (1.0 - c.Yn) / c.A;
+        if (rq.include_neutrons) {
+            nu = 0.0;
+            const double kappa_n_pre = onethird * (pi * pi) * (boltzmann * boltzmann) * T * nn / Mneutron;
+            double R = 1.0;
+            if (T < Tns) {
+                double tau = T / Tns;
+                double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / sqrt(tau) + DS_R4(1.764) / tau);
+                R = pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
+                    exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
+                if (R < sf_reduction_threshold) R = 0.0;
+            }
+            const double pre = neutron_nu_prefactor(nn, nion, c);
+            double lam = lambda_imp;
+            int ierr = imp_ierr;
+            if (isnan(lam)) ierr = ds_lambda_imp(nn, c, lam);
+            if (ierr >= 0) {
+                nu_c = pre * c.Q / (c.Z * c.Z) * lam;
+                kap.nQ = kappa_n_pre / nu_c * R;
+                nu = nu + nu_c;
+            }
+            ierr = ds_lambda_phonon(nn, T, c, lam);
+            if (ierr >= 0) {
+                nu_c = pre * lam;
+                kap.np = kappa_n_pre / nu_c * R;
+                nu = nu + nu_c;
+            }
+            if (nu > 0.0) kap.neutron_total = kappa_n_pre / nu * R;
+        }
+        if (rq.include_sf_phonons && T < Tns) kap.sf = sPh(nn / density_n, nion / density_n, T, c);
+    }
+
+    double K_opacity = 0.0;
+    if (lgrho < rq.rad_full_off_lgrho) {
+        kap.kap = Rosseland_kappa(rho, T, mu_e, c);
+        if (lgrho > rq.rad_full_on_lgrho) {
+            double alpha = (lgrho - rq.rad_full_on_lgrho) / (rq.rad_full_off_lgrho - rq.rad_full_on_lgrho);
+            kap.kap = kap.kap * (1.0 - alpha);
+        }
+        K_opacity = 4.0 * onethird * arad * clight * dsd::ipow<3>(T) / rho / kap.kap;
+    }
+    kap.total = kap.electron_total + kap.neutron_total + kap.sf + K_opacity;
+}
+}  // namespace dsk

@@ -1,0 +1,332 @@
+// Seam A kernels: the NScool coefficient pass (do_setup_crust_transport,
+// NScool/private/NScool_create_model.f:289-444) for a whole batch of stars, plus the batched
+// point evaluators behind the generic C-ABI entry points and the device-resident crust
+// composition lookup (dStar_crust_get_composition_info, dStar_crust/public/dStar_crust_lib.f:109-147).
+//
+// Mapping: one CTA per (star, zone), 128 threads = the 128 lnT knots of the zone's tables
+// (create_model.f:16-18, :340).  Density, composition, chi, kn and Tc are CTA-uniform, only T
+// varies across lanes, so the liquid/solid switch (ion.f:55) and the photo-neutrino temperature
+// bands (eval_crust_neutrino.f:209-228) flip at most once along the CTA.  The monotone-cubic
+// (interp_pm) coefficients are built in shared memory by the same CTA and written out as the
+// (4*128, nz) column-major blocks NScool_def.f:130-134 declares, 32 B per lane, 4 KB per CTA,
+// fully coalesced.
+#pragma once
+#include "conductivity.cuh"
+#include "dconst.cuh"
+#include "eos.cuh"
+#include "neutrino.cuh"
+
+constexpr int DS_NTAB = 128;
+
+// device-resident gap tables (superfluid_def.f:14-21): f = (4,nv) monotone-cubic coefficients
+struct DsSfDev {
+    int loaded[3], nv[3];
+    double kF_min[3], kF_max[3], scale[3];
+    const double* kF[3];
+    const double* f[3];
+};
+
+// k (0-based) with x[k] <= xv < x[k+1], clamped to [0, n-2]
+DS_D int ds_locate(const double* __restrict__ x, int n, double xv) {
+    if (xv <= x[0]) return 0;
+    if (xv >= x[n - 1]) return n - 2;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (x[mid] <= xv) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// MESA interp_1d interp_value / interp_value_and_slope on (4,n) coefficients
+DS_D double ds_interp_value(const double* __restrict__ x, int n, const double* __restrict__ f, double xv) {
+    int k = ds_locate(x, n, xv);
+    double dx = xv - x[k];
+    const double* c = f + 4 * k;
+    return c[0] + dx * (c[1] + dx * (c[2] + dx * c[3]));
+}
+// sf_get_results (superfluid/public/superfluid_lib.f:65-101)
+DS_D void ds_sf_get_results(const DsSfDev& sf, double kFp, double kFn, double Tc[3]) {
+#pragma unroll
+    for (int id = 0; id < 3; ++id) {
+        double kF = (id == 0) ? kFp : kFn;
+        double v = 0.0;
+        if (sf.loaded[id] && !(kF < sf.kF_min[id] || kF > sf.kF_max[id]))
+            v = fmax(ds_interp_value(sf.kF[id], sf.nv[id], sf.f[id], kF), 0.0) * sf.scale[id];
+        Tc[id] = v;
+    }
+}
+
+struct DsMicroArgs {
+    int total_zones, ncharged;
+    const int* zone_star;    // (total_zones) star index of each flattened zone
+    const int* zone_offset;  // (n_star+1)
+    const double *rho, *rho_bar, *P, *P_bar, *dm;  // (total_zones)
+    const double *ionic, *ionic_bar;               // (11, total_zones)
+    const double *Yion, *Yion_bar;                 // (ncharged, total_zones)
+    const double *Zion, *Aion;                     // (ncharged)
+    const double *Tc_cell, *Tc_face;               // (3, total_zones) or null -> gap tables
+    const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, exp(lnT), log10(T)
+    DsEosCtrl eos;
+    DsCondCtrl cond;
+    int nu_channels[5];
+    int turn_on_shell_Urca;
+    double shell_Urca_luminosity_coeff, lgP_shell_Urca;
+    double* rho_bar1;  // (n_star) in/out
+    int* status;       // (n_star) sticky error word
+    double *tab_lnCp, *tab_lnGamma, *tab_lnEnu, *tab_lnK;  // (4*128, total_zones)
+};
+
+// MESA interp_pm (Steffen 1990) on the CTA's 128 knots; v holds f(1,:) on entry.
+DS_D void ds_cta_interp_pm(const double* __restrict__ x, double* v, double* hh, double* sm, double* sl,
+                           double* __restrict__ out) {
+    const int i = threadIdx.x, n = DS_NTAB;
+    if (i < n - 1) {
+        hh[i] = x[i + 1] - x[i];
+        sm[i] = (v[i + 1] - v[i]) / hh[i];
+    }
+    __syncthreads();
+    double s;
+    if (i > 0 && i < n - 1) {
+        double p = (sm[i - 1] * hh[i] + sm[i] * hh[i - 1]) / (hh[i - 1] + hh[i]);
+        double sg = copysign(1.0, sm[i - 1]) + copysign(1.0, sm[i]);
+        s = sg * fmin(fmin(fabs(sm[i - 1]), fabs(sm[i])), 0.5 * fabs(p));
+    } else if (i == 0) {
+        double p1 = sm[0] * (1.0 + hh[0] / (hh[0] + hh[1])) - sm[1] * hh[0] / (hh[0] + hh[1]);
+        if (p1 * sm[0] <= 0.0) s = 0.0;
+        else if (fabs(p1) > 2.0 * fabs(sm[0])) s = 2.0 * sm[0];
+        else s = p1;
+    } else {
+        double pn = sm[n - 2] * (1.0 + hh[n - 2] / (hh[n - 2] + hh[n - 3])) -
+                    sm[n - 3] * hh[n - 2] / (hh[n - 2] + hh[n - 3]);
+        if (pn * sm[n - 2] <= 0.0) s = 0.0;
+        else if (fabs(pn) > 2.0 * fabs(sm[n - 2])) s = 2.0 * sm[n - 2];
+        else s = pn;
+    }
+    sl[i] = s;
+    __syncthreads();
+    double c2 = 0.0, c3 = 0.0;
+    if (i < n - 1) {
+        c2 = (3.0 * sm[i] - 2.0 * sl[i] - sl[i + 1]) / hh[i];
+        c3 = (sl[i] + sl[i + 1] - 2.0 * sm[i]) / (hh[i] * hh[i]);
+    }
+    double4 r = make_double4(v[i], s, c2, c3);
+    reinterpret_cast<double4*>(out)[i] = r;
+    __syncthreads();
+}
+
+template <bool FACE>
+__global__ void __launch_bounds__(DS_NTAB) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
+    __shared__ double s_x[DS_NTAB], s_v[3][DS_NTAB], s_h[DS_NTAB], s_m[DS_NTAB], s_s[DS_NTAB];
+    __shared__ double s_lam;
+    __shared__ int s_lam_ierr, s_err;
+    const int g = blockIdx.x, it = threadIdx.x;
+    const int star = a.zone_star[g];
+    const int iz = g - a.zone_offset[star];
+    const int nz = a.zone_offset[star + 1] - a.zone_offset[star];
+    if (it == 0) { s_err = 0; s_lam = nan(""); s_lam_ierr = 0; }
+    s_x[it] = a.tab_lnT[it];
+    const DsComp c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
+    const double rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
+    const double chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
+    const double kn = dse::neutron_wavenumber(rho, c, chi);
+    double Tc[3];
+    const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
+    if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
+    else ds_sf_get_results(sf, 0.0, kn, Tc);
+    const double T = a.tab_T[it], lgT = a.tab_lgT[it];
+    __syncthreads();
+
+    if (FACE && a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
+        // impurity Coulomb logarithm: T-independent, once per zone (neutron_conductivity.f:382)
+        double nn = rho / dsc::amu * c.Yn / (1.0 - chi);
+        double lam;
+        s_lam_ierr = dsk::ds_lambda_imp(nn, c, lam);
+        s_lam = lam;
+    }
+    if (FACE) __syncthreads();
+
+    DsEosRes r;
+    ds_eval_crust_eos(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion,
+                      (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
+    if (r.ierr != 0) s_err = r.ierr;
+    if (!FACE) {
+        s_v[0][it] = log(r.Cp);
+        s_v[1][it] = log(r.Gamma);
+        if (iz == 0 && it == 0)  // create_model.f:367-369
+            a.rho_bar1[star] = rho * pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+        DsNeutrino eps;
+        dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
+        double lnenu = log(eps.total / rho);
+        if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
+            if (log10(a.P_bar[g]) < a.lgP_shell_Urca && log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
+                lnenu = log(exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
+                                             dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
+        }
+        s_v[2][it] = lnenu;
+    } else {
+        DsCond K;
+        dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, Tc[1], s_lam, s_lam_ierr, K);
+        s_v[0][it] = log(K.total);
+    }
+    __syncthreads();
+    const size_t ob = (size_t)4 * DS_NTAB * g;
+    if (!FACE) {
+        ds_cta_interp_pm(s_x, s_v[2], s_h, s_m, s_s, a.tab_lnEnu + ob);
+        ds_cta_interp_pm(s_x, s_v[0], s_h, s_m, s_s, a.tab_lnCp + ob);
+        ds_cta_interp_pm(s_x, s_v[1], s_h, s_m, s_s, a.tab_lnGamma + ob);
+    } else {
+        ds_cta_interp_pm(s_x, s_v[0], s_h, s_m, s_s, a.tab_lnK + ob);
+    }
+    if (it == 0 && s_err != 0) a.status[star] = s_err;
+}
+
+// ---------------------------------------------------------------- batched point evaluators
+struct DsEvalEosArgs {
+    int n, ncharged;
+    const double *rho, *T, *ionic, *Zion, *Aion, *Yion, *Tcs, *chi_in;
+    DsEosCtrl eos;
+    double* res;  // (15, n)
+    int* phase;
+    double* chi_out;
+    int* ierr;
+};
+__global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    DsComp c = ds_load_comp(a.ionic + (size_t)11 * k);
+    double rho = a.rho[k], T = a.T[k];
+    double chi = a.chi_in ? a.chi_in[k] : -1.0;
+    if (chi == -1.0) chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
+    DsEosRes r;
+    ds_eval_crust_eos(helm, a.eos, rho, T, log10(T), c, a.ncharged, a.Zion, a.Aion,
+                      a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r);
+    double* o = a.res + (size_t)15 * k;
+    o[0] = r.lnP; o[1] = r.lnE; o[2] = r.lnS; o[3] = r.grad_ad; o[4] = r.chiRho; o[5] = r.chiT; o[6] = r.Cp;
+    o[7] = r.Cv; o[8] = r.Chi; o[9] = r.Gamma; o[10] = r.Theta; o[11] = r.mu_e; o[12] = r.mu_n;
+    o[13] = r.Gamma1; o[14] = r.Gamma3;
+    a.phase[k] = r.phase;
+    a.chi_out[k] = chi;
+    a.ierr[k] = r.ierr;
+}
+
+struct DsEvalNuArgs {
+    int n;
+    const double *rho, *T, *ionic, *chi, *Tcn;
+    int channels[5];
+    double* eps;  // (6, n)
+};
+__global__ void ds_eval_nu_kernel(DsEvalNuArgs a) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    DsNeutrino e;
+    dsn::ds_crust_neutrino(a.rho[k], a.T[k], ds_load_comp(a.ionic + (size_t)11 * k), a.chi[k], a.Tcn[k],
+                           a.channels, e);
+    double* o = a.eps + (size_t)6 * k;
+    o[0] = e.total; o[1] = e.pair; o[2] = e.photo; o[3] = e.plasma; o[4] = e.brems; o[5] = e.pbf;
+}
+
+struct DsEvalCondArgs {
+    int n;
+    const double *rho, *T, *chi, *Gamma, *eta, *mu_e, *ionic, *Tns;
+    DsCondCtrl cond;
+    double* K;  // (10, n)
+};
+__global__ void ds_eval_cond_kernel(DsEvalCondArgs a) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    DsCond c;
+    dsk::ds_conductivity(a.cond, a.rho[k], a.T[k], a.chi[k], a.Gamma[k], a.eta[k], a.mu_e[k],
+                         ds_load_comp(a.ionic + (size_t)11 * k), a.Tns[k], nan(""), 0, c);
+    double* o = a.K + (size_t)10 * k;
+    o[0] = c.total; o[1] = c.ee; o[2] = c.ei; o[3] = c.eQ; o[4] = c.sf; o[5] = c.nQ; o[6] = c.np; o[7] = c.kap;
+    o[8] = c.electron_total; o[9] = c.neutron_total;
+}
+
+__global__ void ds_sf_kernel(int n, const double* kFp, const double* kFn, double* Tc, DsSfDev sf) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double t[3];
+    ds_sf_get_results(sf, kFp[k], kFn[k], t);
+    Tc[3 * (size_t)k] = t[0]; Tc[3 * (size_t)k + 1] = t[1]; Tc[3 * (size_t)k + 2] = t[2];
+}
+
+// ------------------------------------------------------------ crust composition lookup
+// Device-resident composition table Y_i(lgP) (dStar_crust_def.f:10-24): per isotope a (4,nv)
+// monotone-cubic coefficient block.  One thread per zone: interpolate every isotope, clip
+// negatives, renormalise, moments with neutrons excluded (nucchem_lib.f:47-133).
+struct DsCompArgs {
+    int nz, nv, nisos, ncharged;
+    const double* lgP_tab;  // (nv)
+    const double* Ycoef;    // (4*nv, nisos)
+    const double *Ziso, *Aiso;  // (nisos)
+    // host-evaluated per-isotope powers: Z^(5/3), Z^(7/3), Z^2.5, Z*(Z+1)^1.5
+    const double *Z53, *Z73, *Z52, *ZZ1;
+    const double* lgP;  // (nz)
+    double* ionic;      // (11, nz)
+    double* Yion;       // (ncharged, nz)
+};
+__global__ void ds_crust_composition_kernel(DsCompArgs a) {
+    int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= a.nz) return;
+    double lgP_c = fmax(a.lgP[z], a.lgP_tab[0]);
+    lgP_c = fmin(lgP_c, a.lgP_tab[a.nv - 1]);
+    const int k = ds_locate(a.lgP_tab, a.nv, lgP_c);
+    const double dx = lgP_c - a.lgP_tab[k];
+    double* Yout = a.Yion + (size_t)a.ncharged * z;
+    // pass 1: Xsum = sum(Y*A) in isotope order (dot_product, nucchem_lib.f:94)
+    double Xsum = 0.0;
+    int ic = 0;
+    for (int i = 0; i < a.nisos; ++i) {
+        const double* c = a.Ycoef + (size_t)4 * a.nv * i + 4 * k;
+        double Y = c[0] + dx * (c[1] + dx * (c[2] + dx * c[3]));
+        if (Y < 0.0) Y = 0.0;
+        Xsum += Y * a.Aiso[i];
+    }
+    // pass 2: renormalise, Ye, Yn in isotope order
+    double Ye = 0.0, Yn = 0.0;
+    ic = 0;
+    for (int i = 0; i < a.nisos; ++i) {
+        const double* c = a.Ycoef + (size_t)4 * a.nv * i + 4 * k;
+        double Y = c[0] + dx * (c[1] + dx * (c[2] + dx * c[3]));
+        if (Y < 0.0) Y = 0.0;
+        Y = Y / Xsum;
+        Ye += Y * a.Ziso[i];
+        if (a.Ziso[i] == 0.0 && a.Aiso[i] == 1.0) Yn += Y;
+        if (a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0) Yout[ic++] = Y;
+    }
+    if (Yn > 0.0 && Yn != 1.0)
+        for (int j = 0; j < a.ncharged; ++j) Yout[j] = Yout[j] / (1.0 - Yn);
+    double sA = 0, sZ = 0, sZ53 = 0, sZ2 = 0, sZ73 = 0, sZ52 = 0, sZZ1 = 0, sX = 0;
+    ic = 0;
+    for (int i = 0; i < a.nisos; ++i)
+        if (a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0) sA += fmin(1.0, fmax(Yout[ic++], 1.0e-50));
+    const double A = 1.0 / sA;
+    ic = 0;
+    for (int i = 0; i < a.nisos; ++i) {
+        if (!(a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0)) continue;
+        const double Y = Yout[ic++], Z = a.Ziso[i];
+        sZ += Y * Z;
+        sZ53 += Y * a.Z53[i];
+        sZ2 += Y * (Z * Z);
+        sZ73 += Y * a.Z73[i];
+        sZ52 += Y * a.Z52[i];
+        sZZ1 += Y * a.ZZ1[i];
+        sX += Z * Z * Y / a.Aiso[i];
+    }
+    double* o = a.ionic + (size_t)11 * z;
+    o[0] = A; o[1] = sZ * A; o[2] = sZ53 * A; o[3] = sZ2 * A; o[4] = sZ73 * A; o[5] = sZ52 * A;
+    o[6] = sZZ1 * A; o[7] = sX; o[8] = Ye; o[9] = Yn; o[10] = o[3] - o[1] * o[1];
+}
+
+// ------------------------------------------------------------ FP64 peak probe (roofline denominator)
+// Eight independent DFMA chains per thread; flops = 2 * 8 * iters * threads.
+__global__ void ds_fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double m = 0.999999, b = 1.0e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+        a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

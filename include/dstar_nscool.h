@@ -1,0 +1,73 @@
+/* dstar_b200 -- host-side mirror of the reference's module API for the hot path.
+ *
+ * The reference's host language is Fortran (NScool/public/NScool_lib.f); no Fortran compiler exists
+ * in the build image, so the host layer above the kernel ABI (dstar_b200.h) is C++ with the same
+ * entry points, argument meaning and `ierr` conventions.  A Fortran program binds these through
+ * ISO_C_BINDING exactly like dstar_b200.h.
+ */
+#ifndef DSTAR_NSCOOL_H
+#define DSTAR_NSCOOL_H
+#include <stdint.h>
+
+#include "dstar_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- data files (replace the *_startup readers) ---- */
+/* read_helm_table (dStar_eos/private/helm_alloc.f:120): binary written by tools/gen_helm_table */
+int dstar_ctx_load_helm_file(dstar_ctx* ctx, const char* path);
+/* load_sf_table (superfluid/private/load_sf.f:5): Tc_data text file -> monotone cubic -> device */
+int dstar_ctx_load_gap_file(dstar_ctx* ctx, int type, const char* path);
+/* MESA interp_pm on (4,n) column-major f with f(1,:) preloaded (host utility) */
+int dstar_host_interp_pm(const double* x, int n, double* f);
+
+/* ---- NScool_lib (NScool/public/NScool_lib.f:6-91) ---- */
+/* NScool_init(my_dStar_dir, ierr): data_dir holds helm_table.bin and Tc_data/ */
+int dstar_NScool_init(const char* data_dir, int device);
+void dstar_NScool_shutdown(void);
+/* alloc_NScool(ierr) -> id >= 1, or < 0 */
+int dstar_alloc_NScool(void);
+int dstar_dealloc_NScool(int id);
+/* NScool_setup(id, inlist, ierr): read the &controls namelist */
+int dstar_NScool_setup(int id, const char* inlist);
+/* set one control by name after setup (what a driver does through get_NScool_info_ptr) */
+int dstar_NScool_set_control(int id, const char* name, const char* value);
+/* NScool_create_model(id, ierr) / NScool_evolve_model(id, ierr) for ONE star */
+int dstar_NScool_create_model(int id);
+int dstar_NScool_evolve_model(int id);
+/* the same two calls for MANY stars at once (a sweep / MCMC batch): one coefficient-pass launch pair and
+ * one evolve launch for all of them */
+int dstar_NScool_create_models(int n, const int32_t* ids);
+int dstar_NScool_evolve_models(int n, const int32_t* ids);
+/* hooks (NScool_def.f:148-155), evaluated on the host before upload:
+ *   other_set_Qimp(id): may rewrite ionic_bar%Q via dstar_NScool_set_zone_array(id,"Qimp_bar",...)
+ *   other_sf_get_results(id,kp,kn,Tc): called per zone for cells and faces */
+typedef void (*dstar_set_Qimp_fn)(int id, int* ierr);
+typedef void (*dstar_sf_fn)(int id, double kp, double kn, double Tc[3]);
+int dstar_NScool_set_hooks(int id, dstar_set_Qimp_fn qimp, dstar_sf_fn sf);
+/* accessors to type NScool_info (NScool_def.f:33-157) */
+int dstar_NScool_get_int(int id, const char* name, int32_t* value);     /* nz, number_epochs, ncharged, model */
+int dstar_NScool_get_real(int id, const char* name, double* value);     /* grav, Mtotal, Rtotal, Teff, Lsurf, ... */
+/* zone arrays by name (dm, P, rho, rho_bar, ePhi, ..., lnT, ionic(11,nz), ionic_bar, tab_lnK(4*128,nz), ...) */
+int dstar_NScool_get_zone_array(int id, const char* name, double* out, int capacity);
+int dstar_NScool_set_zone_array(int id, const char* name, const double* in, int count);
+/* monitors (NScool_def.f:136-144), length number_epochs */
+int dstar_NScool_get_monitors(int id, double* t_monitor, double* Teff_monitor, double* Qb_monitor);
+/* isolve statistics iwork(14:20) of the last evolve (NScool_evolve.f:124-130) */
+int dstar_NScool_get_counters(int id, int32_t counters[7]);
+/* history rows kept from the last evolve (NScool_history.f:84-86); returns the row count */
+int dstar_NScool_get_history(int id, int capacity, int32_t* model, double* time_d, double* lg_Mdot,
+                             double* lg_Teff, double* lg_Lsurf, double* lg_Lnu, double* lg_Lnuc);
+/* write LOGS/history.data in the reference's format (readable by tools/reader.py) */
+int dstar_NScool_write_history(int id, const char* path);
+/* device timing of the last batch calls [ms]: which = 0 cell loop, 1 face loop, 2 evolve */
+double dstar_NScool_last_kernel_ms(int which);
+/* message of the last failed dstar_NScool_* call */
+const char* dstar_NScool_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSTAR_NSCOOL_H */

@@ -66,6 +66,7 @@ int dso_helm_eval(double T, double rho, double abar, double zbar, double* out) {
 
 void dso_sf_load(int type, int nv, double kFmin, double kFmax, const double* kF, const double* Tc) {
     sf_load(g_sf.tab[type], nv, kFmin, kFmax, kF, Tc);
+    set_micro_sf_tables(&g_sf);
 }
 void dso_sf_scale(const double* s) { for (int i = 0; i < 3; ++i) g_sf.scale[i] = s[i]; }
 void dso_sf_get_results(double kFp, double kFn, double* Tc) { sf_get_results(g_sf, kFp, kFn, Tc); }

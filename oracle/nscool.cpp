@@ -389,11 +389,17 @@ int rodasp_selftest(int problem, double tend, double rtol, double atol, double h
             }
             sup[0] = 0; sub[n - 1] = 0;
             return 0; };
-    } else {  // Prothero-Robinson stiff scalar: y' = -1e6 (y - cos t) - sin t, y = cos t
-        pb.n = 1;
-        pb.fcn = [](double t, const double* yy, double* f) { f[0] = -1.0e6 * (yy[0] - std::cos(t)) - std::sin(t); return 0; };
-        pb.jac = [](double, const double*, double*, double* sup, double* d, double* sub) {
-            sup[0] = 0; sub[0] = 0; d[0] = -1.0e6; return 0; };
+    } else {  // Prothero-Robinson, autonomous form: y1' = -1e6 (y1 - cos y2) - sin y2, y2' = 1 ; y1 = cos t
+        pb.n = 2;
+        pb.fcn = [](double, const double* yy, double* f) {
+            f[0] = -1.0e6 * (yy[0] - std::cos(yy[1])) - std::sin(yy[1]);
+            f[1] = 1.0;
+            return 0; };
+        pb.jac = [](double, const double* yy, double*, double* sup, double* d, double* sub) {
+            d[0] = -1.0e6; d[1] = 0.0;
+            sup[0] = 0.0; sup[1] = -1.0e6 * std::sin(yy[1]) - std::cos(yy[1]);  // df(0)/dy(1), stored at column 1
+            sub[0] = 0.0; sub[1] = 0.0;
+            return 0; };
     }
     double x = 0.0, h = h0;
     return rodasp(pb, x, y, tend, h, 0.0, 1000000, rtol, atol, 0.0, 0.0, counters);

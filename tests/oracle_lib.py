@@ -186,3 +186,69 @@ class Oracle:
         cnt = np.zeros(7, dtype=np.int32)
         idid = self.lib.dso_rodasp_test(problem, tend, rtol, atol, h0, _ptr(y), _ptr(cnt, ip))
         return idid, y, cnt
+
+
+def _micro_tables(self, nz, ncharged, rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion,
+                  Tc_cell=None, Tc_face=None, eos_ctrl=(175.0, 140.0, float(np.float32(1e-9))),
+                  cond_ctrl=(0, 0, 1, 1, 10.0, 9.0), nu_channels=(1, 1, 1, 1, 1), shell_Urca=(0, 1.0, 28.5),
+                  do_cells=1, do_faces=1, rho_bar1_override=0.0):
+    """do_setup_crust_transport for ONE star on the CPU oracle."""
+    keep = [f64(x) for x in (rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion)]
+    tc = None if Tc_cell is None else f64(Tc_cell)
+    tf = None if Tc_face is None else f64(Tc_face)
+    m = MicroTablesIn()
+    m.nz = nz; m.ncharged = ncharged
+    (m.rho, m.rho_bar, m.P, m.P_bar, m.dm, m.ionic, m.ionic_bar, m.Yion, m.Yion_bar, m.Zion, m.Aion) = \
+        [_ptr(x) for x in keep]
+    m.Tc_cell = _ptr(tc); m.Tc_face = _ptr(tf)
+    m.eos_ctrl = (C.c_double * 3)(*eos_ctrl)
+    m.cond_ctrl = (C.c_double * 6)(*cond_ctrl)
+    m.nu_channels = (C.c_int32 * 5)(*nu_channels)
+    m.turn_on_shell_Urca = int(shell_Urca[0]); m.shell_Urca_luminosity_coeff = shell_Urca[1]
+    m.lgP_shell_Urca = shell_Urca[2]
+    m.do_cells = do_cells; m.do_faces = do_faces; m.rho_bar1_override = rho_bar1_override
+    n = 4 * 128 * nz
+    lnT = np.zeros(128)
+    out = [np.zeros(n) for _ in range(4)]
+    rb1 = C.c_double(0.0)
+    ierr = self.lib.dso_micro_tables(C.byref(m), _ptr(lnT), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                     C.byref(rb1))
+    return {"ierr": ierr, "tab_lnT": lnT, "tab_lnCp": out[0], "tab_lnGamma": out[1], "tab_lnEnu": out[2],
+            "tab_lnK": out[3], "rho_bar1": rb1.value}
+
+
+def _evolve_epoch(self, ein_kwargs, lnT, dt, trace_cap=0):
+    """do_integrate_crust for ONE star, ONE epoch.  ein_kwargs: dict of EvolveIn fields (arrays as numpy)."""
+    e = EvolveIn()
+    keep = []
+    for k, v in ein_kwargs.items():
+        if isinstance(v, np.ndarray):
+            a = f64(v); keep.append(a); setattr(e, k, _ptr(a))
+        elif k == "heat":
+            e.heat = (C.c_double * 9)(*v)
+        else:
+            setattr(e, k, v)
+    st = EvolveState()
+    y = f64(lnT).copy()
+    st.lnT = _ptr(y); st.dt = dt; st.tsec = 0.0; st.model = 0
+    tr = None
+    arrs = {}
+    if trace_cap > 0:
+        tr = EvolveTrace()
+        tr.capacity = trace_cap; tr.count = 0
+        arrs["model"] = np.zeros(trace_cap, dtype=np.int32)
+        tr.model = _ptr(arrs["model"], ip)
+        for nm in ("tsec", "dt", "Teff", "Lsurf", "Lnu", "Lnuc"):
+            arrs[nm] = np.zeros(trace_cap); setattr(tr, nm, _ptr(arrs[nm]))
+        tr.lnT_rows = dp()
+    rc = self.lib.dso_evolve_epoch(C.byref(e), C.byref(st), C.byref(tr) if tr is not None else None)
+    out = {"rc": rc, "lnT": y, "dt": st.dt, "tsec": st.tsec, "model": st.model, "Teff": st.Teff, "Lsurf": st.Lsurf,
+           "idid": st.idid, "counters": np.array(list(st.counters))}
+    if tr is not None:
+        n = tr.count
+        out["trace"] = {k: v[:n] for k, v in arrs.items()}
+    return out
+
+
+Oracle.micro_tables = _micro_tables
+Oracle.evolve_epoch = _evolve_epoch
