@@ -11,6 +11,7 @@
 #include "../../include/dstar_b200.h"
 #include "kernels_evolve.cuh"
 #include "kernels_micro.cuh"
+#include "kernels_test.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -82,14 +83,14 @@ struct dstar_batch {
 namespace {
 void fill_host_consts(DsHostConsts& h) {
     using namespace dsc;
-    h.theta_fac = 2.0 * std::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
-    h.ctf_fac = (double)(18.0f / 175.0f) * std::pow(12.0 / pi, 2.0 * onethird);
-    h.xrs = finestructure * std::pow(9.0 * pi / 4.0, onethird);
-    h.atf = (double)(54.0f / 175.0f) * std::pow(12.0 / pi, onethird) * finestructure;
-    h.e1 = std::exp(1.0);
-    h.half_log_6_over_pi = 0.5 * std::log(6.0 / pi);
-    h.aei_fac = std::pow((double)(4.0f / 9.0f) / pi, onethird);
-    h.befac = std::pow(finestructure / pi, 1.5);
+    h.theta_fac = 2.0 * dsm::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
+    h.ctf_fac = (double)(18.0f / 175.0f) * dsm::pow(12.0 / pi, 2.0 * onethird);
+    h.xrs = finestructure * dsm::pow(9.0 * pi / 4.0, onethird);
+    h.atf = (double)(54.0f / 175.0f) * dsm::pow(12.0 / pi, onethird) * finestructure;
+    h.e1 = dsm::exp(1.0);
+    h.half_log_6_over_pi = 0.5 * dsm::log(6.0 / pi);
+    h.aei_fac = dsm::pow((double)(4.0f / 9.0f) / pi, onethird);
+    h.befac = dsm::pow(finestructure / pi, 1.5);
     h.yfac = std::sqrt(4.0 * finestructure / pi);
     h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
 }
@@ -139,8 +140,8 @@ int dstar_ctx_create(int device, dstar_ctx** out) {
     double T[DS_NTAB], lgT[DS_NTAB];
     for (int i = 0; i < DS_NTAB; ++i) {
         c->h_tab_lnT[i] = 7.0 * dsc::ln10 + (10.0 - 7.0) * dsc::ln10 * (double)i / (double)(DS_NTAB - 1);
-        T[i] = std::exp(c->h_tab_lnT[i]);
-        lgT[i] = std::log10(T[i]);
+        T[i] = dsm::exp(c->h_tab_lnT[i]);
+        lgT[i] = dsm::log10(T[i]);
     }
     CK(c->tab_lnT.upload(c->h_tab_lnT, DS_NTAB, c->stream));
     CK(c->tab_T.upload(T, DS_NTAB, c->stream));
@@ -177,11 +178,11 @@ int dstar_ctx_set_helm(dstar_ctx* c, int imax, int jmax, const double* const a[2
     const double logtstp = (logthi - logtlo) / (double)(float)(jmax - 1);
     const double logdstp = (logdhi - logdlo) / (double)(float)(imax - 1);
     h.logtlo = logtlo; h.logtstpi = 1.0 / logtstp; h.logdlo = logdlo; h.logdstpi = 1.0 / logdstp;
-    h.templo = std::pow(10.0, logtlo); h.temphi = std::pow(10.0, logthi); h.logthi = logthi;
-    h.denlo = std::pow(10.0, logdlo); h.denhi = std::pow(10.0, logdhi);
+    h.templo = 1.0e3; h.temphi = 1.0e13; h.logthi = logthi;
+    h.denlo = 1.0e-12; h.denhi = 1.0e14;
     std::vector<double> t(jmax), d(imax);
-    for (int j = 0; j < jmax; ++j) t[j] = std::exp((logtlo + j * logtstp) * dsc::ln10);
-    for (int i = 0; i < imax; ++i) d[i] = std::exp((logdlo + i * logdstp) * dsc::ln10);
+    for (int j = 0; j < jmax; ++j) t[j] = dsm::exp((logtlo + j * logtstp) * dsc::ln10);
+    for (int i = 0; i < imax; ++i) d[i] = dsm::exp((logdlo + i * logdstp) * dsc::ln10);
     // repack the 17 hot arrays into per-node records (see helm.cuh)
     static const int src[DS_HELM_REC] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9, 11, 10, 12, 13, 15, 14, 16};
     const size_t n = (size_t)imax * jmax;
@@ -216,10 +217,10 @@ int dstar_ctx_set_sf_scale(dstar_ctx* c, const double s[3]) {
 }
 
 // ------------------------------------------------------------ point evaluators
-int dstar_eval_crust_eos(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic, int ncharged,
+static int eval_crust_eos_impl(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic, int ncharged,
                          const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
                          const double* chi_in, const double* eos_ctrl, double* res, int32_t* phase,
-                         double* chi_out, int32_t* ierr) {
+                         double* chi_out, int32_t* ierr, double* components) {
     if (!c || n <= 0) return fail(DSTAR_ERR_ARG, "eval_crust_eos");
     if (!c->helm_loaded) return fail(DSTAR_ERR_STATE, "HELM table not loaded (dstar_ctx_set_helm)");
     CK(cudaSetDevice(c->device));
@@ -231,15 +232,18 @@ int dstar_eval_crust_eos(dstar_ctx* c, int n, const double* rho, const double* T
     CK(d_Y.upload(Yion, (size_t)ncharged * n, s)); CK(d_Tc.upload(Tcs, (size_t)3 * n, s));
     if (chi_in) CK(d_chi.upload(chi_in, n, s));
     CK(d_res.alloc((size_t)15 * n)); CK(d_chio.alloc(n)); CK(d_ph.alloc(n)); CK(d_ie.alloc(n));
+    DevBuf<double> d_comp;
+    if (components) CK(d_comp.alloc((size_t)28 * n));
     DsEvalEosArgs a{};
     a.n = n; a.ncharged = ncharged; a.rho = d_rho.p; a.T = d_T.p; a.ionic = d_ion.p; a.Zion = d_Z.p; a.Aion = d_A.p;
     a.Yion = d_Y.p; a.Tcs = d_Tc.p; a.chi_in = chi_in ? d_chi.p : nullptr;
     a.eos = DsEosCtrl{175.0, 140.0, DS_R4(1.0e-9)};
     if (eos_ctrl) a.eos = DsEosCtrl{eos_ctrl[0], eos_ctrl[1], eos_ctrl[2]};
-    a.res = d_res.p; a.phase = d_ph.p; a.chi_out = d_chio.p; a.ierr = d_ie.p;
+    a.res = d_res.p; a.phase = d_ph.p; a.chi_out = d_chio.p; a.ierr = d_ie.p; a.comps = components ? d_comp.p : nullptr;
     ds_eval_eos_kernel<<<(n + 63) / 64, 64, 0, s>>>(a, c->helm);
     CK(cudaGetLastError());
     CK(d_res.download(res, (size_t)15 * n, s));
+    if (components) CK(d_comp.download(components, (size_t)28 * n, s));
     if (phase) CK(d_ph.download(phase, n, s));
     if (chi_out) CK(d_chio.download(chi_out, n, s));
     std::vector<int> ie(n);
@@ -248,6 +252,21 @@ int dstar_eval_crust_eos(dstar_ctx* c, int n, const double* rho, const double* T
     int worst = 0;
     for (int i = 0; i < n; ++i) { if (ierr) ierr[i] = ie[i]; if (ie[i] != 0) worst = ie[i]; }
     return worst;
+}
+
+int dstar_eval_crust_eos(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic, int ncharged,
+                         const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
+                         const double* chi_in, const double* eos_ctrl, double* res, int32_t* phase,
+                         double* chi_out, int32_t* ierr) {
+    return eval_crust_eos_impl(c, n, rho, T, ionic, ncharged, Zion, Aion, Yion, Tcs, chi_in, eos_ctrl, res, phase, chi_out,
+                               ierr, nullptr);
+}
+int dstar_eval_crust_eos_components(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic,
+                                    int ncharged, const double* Zion, const double* Aion, const double* Yion,
+                                    const double* Tcs, const double* chi_in, const double* eos_ctrl, double* res,
+                                    int32_t* phase, double* chi_out, int32_t* ierr, double* components) {
+    return eval_crust_eos_impl(c, n, rho, T, ionic, ncharged, Zion, Aion, Yion, Tcs, chi_in, eos_ctrl, res, phase, chi_out,
+                               ierr, components);
 }
 
 int dstar_crust_neutrino(dstar_ctx* c, int n, const double* rho, const double* T, const double* ionic,
@@ -312,8 +331,8 @@ int dstar_crust_composition_info(dstar_ctx* c, int nv, int nisos, const double* 
     std::vector<double> z53(nisos), z73(nisos), z52(nisos), zz1(nisos);
     for (int i = 0; i < nisos; ++i) {
         if (Ziso[i] > 0.0 && Aiso[i] > 0.0) ++nch;
-        z53[i] = std::pow(Ziso[i], 5.0 / 3.0); z73[i] = std::pow(Ziso[i], 7.0 / 3.0);
-        z52[i] = std::pow(Ziso[i], 2.5); zz1[i] = Ziso[i] * std::pow(Ziso[i] + 1.0, 1.5);
+        z53[i] = dsm::pow(Ziso[i], 5.0 / 3.0); z73[i] = dsm::pow(Ziso[i], 7.0 / 3.0);
+        z52[i] = dsm::pow(Ziso[i], 2.5); zz1[i] = Ziso[i] * dsm::pow(Ziso[i] + 1.0, 1.5);
     }
     DevBuf<double> d_tab, d_Y, d_Z, d_A, d_53, d_73, d_52, d_zz, d_lgP, d_ion, d_Yion;
     CK(d_tab.upload(lgP_tab, nv, s)); CK(d_Y.upload(Ycoef, (size_t)4 * nv * nisos, s));
@@ -654,6 +673,19 @@ int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, i
         rc = dstar_batch_download_tables(b, tab_lnT, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK, rho_bar1, status);
     dstar_batch_destroy(b);
     return rc;
+}
+
+int dstar_dsmath_eval(dstar_ctx* c, int fn, int n, const double* x, const double* y, double* out) {
+    if (!c || n <= 0 || !x || !y || !out) return fail(DSTAR_ERR_ARG, "dsmath_eval");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DevBuf<double> dx, dy, dout;
+    CK(dx.upload(x, n, s)); CK(dy.upload(y, n, s)); CK(dout.alloc(n));
+    ds_dsmath_kernel<<<(n + 127) / 128, 128, 0, s>>>(fn, n, dx.p, dy.p, dout.p);
+    CK(cudaGetLastError());
+    CK(dout.download(out, n, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
 }
 
 int dstar_fp64_peak_tflops(dstar_ctx* c, double* tflops) {

@@ -33,16 +33,16 @@ DS_D double ee_PCY(double ne, double T) {
     double mec2 = Melectron * clight * clight;
     double eefac = 1.5 * (finestructure * finestructure) * mec2 / dsd::ipow<3>(pi) / hbar;
     double befac = ds_hc.befac;
-    double kF = pow(3.0 * (pi * pi) * ne, onethird);
+    double kF = dsm::pow(3.0 * (pi * pi) * ne, onethird);
     double x = kF * hbar / Melectron / clight;
     double eF = sqrt(1.0 + x * x);
     double beta = x / eF;
     double b2 = beta * beta;
-    double be3 = befac / pow(beta, 1.5);
+    double be3 = befac / dsm::pow(beta, 1.5);
     double plasma_theta = boltzmann * T / mec2;
-    double y = yfac * pow(x, 1.5) / plasma_theta / sqrt(eF);
+    double y = yfac * dsm::pow(x, 1.5) / plasma_theta / sqrt(eF);
     double lJ = 1.0 + (DS_R4(2.810) - DS_R4(0.810) * b2) / y;
-    double llJ = log(lJ);
+    double llJ = dsm::log(lJ);
     double J0 = onethird / dsd::ipow<3>(1.0 + DS_R4(0.07414) * y);
     double J1 = J0 * llJ + onesixth * dsd::ipow<5>(pi) * y / dsd::ipow<4>(DS_R4(13.91) + y);
     double J2 = 1.0 + DS_R4(0.4) * (3.0 + 1.0 / (x * x)) / (x * x);
@@ -53,7 +53,7 @@ DS_D double ee_PCY(double ne, double T) {
 DS_D double ee_SY06(double ne, double T) {
     double nu_pre = 36.0 * (finestructure * finestructure) * (hbar * hbar) * clight / pi / boltzmann / Melectron;
     double Tp_pre = ds_hc.Tp_pre;
-    double kF = pow(threepisquare * ne, onethird);
+    double kF = dsm::pow(threepisquare * ne, onethird);
     double xF = hbar * kF / Melectron / clight;
     double eF = sqrt(1.0 + xF * xF);
     double u = xF / eF;
@@ -64,18 +64,18 @@ DS_D double ee_SY06(double ne, double T) {
     double At = 20.0 + 450.0 * u3;
     double Ct1 = DS_R4(0.05067) + DS_R4(0.03216) * u2;
     double Ct2 = DS_R4(0.0254) + DS_R4(0.04127) * u4;
-    double Ct = At * exp(Ct1 / Ct2);
+    double Ct = At * dsm::exp(Ct1 / Ct2);
     double Alt = DS_R4(12.2) + DS_R4(25.2) * u3;
     double Blt = 1.0 - 0.75 * u;
     double Clt1 = DS_R4(0.123636) + DS_R4(0.016234) * u2;
     double Clt2 = DS_R4(0.0762) + DS_R4(0.05714) * u4;
-    double Clt = Alt * exp(Clt1 / Clt2);
+    double Clt = Alt * dsm::exp(Clt1 / Clt2);
     double Il = (1.0 / u) * (DS_R4(0.1587) - DS_R4(0.02538) / (1.0 + DS_R4(0.0435) * theta)) *
-                log(1.0 + DS_R4(128.56) / theta / (DS_R4(37.1) + theta * (DS_R4(10.83) + theta)));
+                dsm::log(1.0 + DS_R4(128.56) / theta / (DS_R4(37.1) + theta * (DS_R4(10.83) + theta)));
     double It = u3 * (DS_R4(2.404) / Ct + (Ct2 - DS_R4(2.404) / Ct) / (1.0 + DS_R4(0.1) * tu)) *
-                log(1.0 + Ct / tu / (At + tu));
-    double Ilt = u * (DS_R4(18.52) * u2 / Clt + (Clt2 - DS_R4(18.2) * u2 / Clt) / (1.0 + DS_R4(0.1558) * pow(theta, Blt))) *
-                 log(1.0 + Clt / (Alt * theta + DS_R4(10.83) * (tu * tu) + pow(tu, (double)(8.0f / 3.0f))));
+                dsm::log(1.0 + Ct / tu / (At + tu));
+    double Ilt = u * (DS_R4(18.52) * u2 / Clt + (Clt2 - DS_R4(18.2) * u2 / Clt) / (1.0 + DS_R4(0.1558) * dsm::pow(theta, Blt))) *
+                 dsm::log(1.0 + Clt / (Alt * theta + DS_R4(10.83) * (tu * tu) + dsm::pow(tu, (double)(8.0f / 3.0f))));
     double I = Il + It + Ilt;
     return nu_pre * ne * I / eF / T;
 }
@@ -83,7 +83,7 @@ DS_D double ee_SY06(double ne, double T) {
 DS_D double eone(double z) {
     const double a0 = DS_R4(0.1397), a1 = DS_R4(0.5772), a2 = DS_R4(2.2757);
     double z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
-    return exp(-z4 / (z3 + a0)) * (log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
+    return dsm::exp(-z4 / (z3 + a0)) * (dsm::log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
 }
 
 DS_D double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z2, double Z53, double A) {
@@ -101,33 +101,33 @@ DS_D double eion(double kF, double Gamma_e, double eta, double Ye, double Z, dou
     double Gamma = Gamma_e * Z53;
     double s = finestructure / pi / v;
     double kTF2 = 4.0 * s * kF2;
-    double eta02 = dsd::ipow<2>(DS_R4(0.19) / pow(Z, onesixth));
+    double eta02 = dsd::ipow<2>(DS_R4(0.19) / dsm::pow(Z, onesixth));
     double aei = ds_hc.aei_fac * kF;
     double qD2 = 3.0 * Gamma_e * (aei * aei) * Z2 / Z;
     double beta = pi * finestructure * Z * v;
-    double qi2 = qD2 * (1.0 + DS_R4(0.06) * Gamma) * exp(-sqrt(Gamma));
-    double qs2 = (qi2 + kTF2) * exp(-beta);
+    double qi2 = qD2 * (1.0 + DS_R4(0.06) * Gamma) * dsm::exp(-sqrt(Gamma));
+    double qs2 = (qi2 + kTF2) * dsm::exp(-beta);
     (void)qs2;
     double Gs = eta / sqrt(eta * eta + eta02) * (1.0 + DS_R4(0.122) * (beta * beta));
-    double Gk0 = 1.0 / pow(eta * eta + DS_R4(0.0081), 1.5);
+    double Gk0 = 1.0 / dsm::pow(eta * eta + DS_R4(0.0081), 1.5);
     double Gk1 = 1.0 + beta * dsd::ipow<3>(v);
     double GkZ = 1.0 - 1.0 / Z;
     double Gk = Gs + DS_R4(0.0105) * GkZ * Gk1 * Gk0 * eta;
     double a0 = 4.0 * kF2 / qD2 / eta;
-    double D1 = exp(DS_R4(-9.1) * eta);
-    double D = exp(-a0 * um1 * D1 * 0.25);
+    double D1 = dsm::exp(DS_R4(-9.1) * eta);
+    double D = dsm::exp(-a0 * um1 * D1 * 0.25);
     double w1 = 1.0 + onethird * beta;
     double w = 4.0 * um2 * kF2 / qD2 * w1;
     double sw = s * w;
     double L1, L2;
     if (sw < sw_max) {
-        double fac = exp(sw) * (eone(sw) - eone(sw + w));
-        L1 = 0.5 * (log(1.0 + 1.0 / s) + (1.0 - exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
-        L2 = 0.5 * (1.0 - (1.0 - exp(-w)) / w +
-                    s * (s / (1.0 + s) * (1.0 - exp(-w)) - 2.0 * log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
+        double fac = dsm::exp(sw) * (eone(sw) - eone(sw + w));
+        L1 = 0.5 * (dsm::log(1.0 + 1.0 / s) + (1.0 - dsm::exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
+        L2 = 0.5 * (1.0 - (1.0 - dsm::exp(-w)) / w +
+                    s * (s / (1.0 + s) * (1.0 - dsm::exp(-w)) - 2.0 * dsm::log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
     } else {
-        L1 = 0.5 * (log((s + 1.0) / s) - 1.0 / (s + 1.0));
-        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * log((s + 1.0) / s);
+        L1 = 0.5 * (dsm::log((s + 1.0) / s) - 1.0 / (s + 1.0));
+        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * dsm::log((s + 1.0) / s);
     }
     double Lei = (Z2 / A) * (L1 - v2 * L2) * Gk * D;
     return eifac * eF * Lei * A / Z;
@@ -143,7 +143,7 @@ DS_D double eQ(double kF, double Z, double A, double Q) {
     double v2 = v * v;
     double s = finestructure / pi / v;
     double L1 = 1.0 + 4.0 * v2 * s;
-    double L = 0.5 * (L1 * log(1.0 + 1.0 / s) - v2 - 1.0 / (s + 1.0) - v2 * s / (1.0 + s));
+    double L = 0.5 * (L1 * dsm::log(1.0 + 1.0 / s) - v2 - 1.0 / (s + 1.0) - v2 * s / (1.0 + s));
     return fac * gamma * dZ2 * L * A / Z;
 }
 
@@ -155,12 +155,12 @@ DS_D double eQ_page(double kF, double Z, double A, double Q) {
     double gamma = sqrt(1.0 + x * x);
     double v = x / gamma;
     double qs = DS_R4(0.048196) / sqrt(v);
-    double L = log(1.0 / qs) - 0.5 * (1 + v * v);
+    double L = dsm::log(1.0 / qs) - 0.5 * (1 + v * v);
     return fac * gamma * dZ2 * L * A / Z;
 }
 
 DS_D double electron_scattering(double eta_e, double theta, double Ye) {
-    double xi = exp(DS_R4(0.8168) * eta_e - DS_R4(0.05522) * (eta_e * eta_e));
+    double xi = dsm::exp(DS_R4(0.8168) * eta_e - DS_R4(0.05522) * (eta_e * eta_e));
     double xi2 = xi * xi;
     double theta2 = theta * theta;
     double t1 = DS_R4(1.129) + DS_R4(0.2965) * xi - DS_R4(0.005594) * xi2;
@@ -174,22 +174,22 @@ DS_D double freefree(double rho, double T, double eta_e, const DsComp& c) {
     const double bfac = DS_R4(0.753);
     double rY = rho * c.Ye;
     double T8 = T * 1.0e-8;
-    double T8_32 = pow(T8, 1.5);
+    double T8_32 = dsm::pow(T8, 1.5);
     double xx;
     if (eta_e > dbl_max_log) xx = eta_e;
-    else xx = log(1.0 + exp(eta_e));
+    else xx = dsm::log(1.0 + dsm::exp(eta_e));
     double norm = 1.16 * 8.02e3 * xx * T8_32 / rY;
-    double x = pow(1.0 + xx, twothird);
+    double x = dsm::pow(1.0 + xx, twothird);
     double gam = sqrt(DS_R4(1.58e-3) / T8) * c.Z;
     double sxpt = sqrt(x + 10.0);
     double sx = sqrt(x);
     double tpg = 2.0 * pi * gam;
-    double expnum = exp(-tpg / sxpt);
-    double expden = exp(-tpg / sx);
+    double expnum = dsm::exp(-tpg / sxpt);
+    double expden = dsm::exp(-tpg / sx);
     double elwert = (1.0 - expnum) / (1.0 - expden);
-    double relfactor = 1.0 + pow(T8 / DS_R4(7.7), 1.5);
+    double relfactor = 1.0 + dsm::pow(T8 / DS_R4(7.7), 1.5);
     double gff = norm * elwert * relfactor;
-    return bfac * (rY / 1.0e5) / pow(T8, 3.5) * gff * c.Z2 / c.A;
+    return bfac * (rY / 1.0e5) / dsm::pow(T8, 3.5) * gff * c.Z2 / c.A;
 }
 
 DS_D double Rosseland_kappa(double rho, double T, double mu_e, const DsComp& c) {
@@ -200,7 +200,7 @@ DS_D double Rosseland_kappa(double rho, double T, double mu_e, const DsComp& c) 
     double T6 = T * 1.0e-6;
     double T_Ry = T6 / 0.15789 / c.Z2;
     double f = kap_ff / (kap_ff + kap_th);
-    double A = 1.0 + (1.097 + 0.777 * T_Ry) / (1.0 + 0.536 * T_Ry) * pow(f, 0.617) * pow(1.0 - f, 0.77);
+    double A = 1.0 + (1.097 + 0.777 * T_Ry) / (1.0 + 0.536 * T_Ry) * dsm::pow(f, 0.617) * dsm::pow(1.0 - f, 0.77);
     return (kap_th + kap_ff) * A;
 }
 
@@ -211,24 +211,24 @@ struct SfacPar {
 };
 template <bool PHONON>
 DS_D double sfac(double x, const SfacPar& p) {
-    double formfac = fabs(3.0 * (sin(x) - x * cos(x)) / dsd::ipow<3>(x));
+    double formfac = fabs(3.0 * (dsm::sin(x) - x * dsm::cos(x)) / dsd::ipow<3>(x));
     if (!PHONON) return dsd::ipow<3>(x) * (formfac * formfac);
     double nn = dsd::ipow<3>(p.kfn) / threepisquare;
     double nion = nn / p.Yn * (1.0 - p.Yn) / p.A;
-    double aion = pow(3.0 / (4.0 * pi * nion), onethird);
+    double aion = dsm::pow(3.0 / (4.0 * pi * nion), onethird);
     double mion = (p.A - p.Z) * Mneutron + p.Z * Mproton;
-    double omegaP = pow(hbar * clight * 4. * pi * (p.Z * p.Z) * finestructure * nion / mion, 0.5);
+    double omegaP = dsm::pow(hbar * clight * 4. * pi * (p.Z * p.Z) * finestructure * nion / mion, 0.5);
     double eta = boltzmann * p.T / (hbar * omegaP);
     double Gamma = hbar * clight * (p.Z * p.Z) * finestructure / (boltzmann * p.T * aion);
     double a1 = dsd::ipow<2>(x / p.R_a * aion) / (3. * Gamma * eta);
     double um1 = DS_R4(2.8);
     double um2 = 13.0;
-    double w = a1 * (um1 * exp(DS_R4(-9.1) * eta) + 2. * eta * um2) / 4.;
-    double w1 = a1 * um2 * (eta * eta) / (2. * pow(eta * eta + dsd::ipow<2>(um2 / 117.), 0.5));
-    double ssig = exp(-2. * (w - w1)) * (1.0 - exp(-2. * w1));
-    double dskappa2 = a1 * 91. * (eta * eta) * exp(-2. * w) / dsd::ipow<2>(1. + DS_R4(111.4) * (eta * eta));
+    double w = a1 * (um1 * dsm::exp(DS_R4(-9.1) * eta) + 2. * eta * um2) / 4.;
+    double w1 = a1 * um2 * (eta * eta) / (2. * dsm::pow(eta * eta + dsd::ipow<2>(um2 / 117.), 0.5));
+    double ssig = dsm::exp(-2. * (w - w1)) * (1.0 - dsm::exp(-2. * w1));
+    double dskappa2 = a1 * 91. * (eta * eta) * dsm::exp(-2. * w) / dsd::ipow<2>(1. + DS_R4(111.4) * (eta * eta));
     double dskappa4 = a1 * DS_R4(0.101) * dsd::ipow<4>(eta) /
-                      ((DS_R4(0.06408) + eta * eta) * pow(DS_R4(0.001377) + eta * eta, 1.5));
+                      ((DS_R4(0.06408) + eta * eta) * dsm::pow(DS_R4(0.001377) + eta * eta, 1.5));
     double dskappa = dskappa2 + dskappa4;
     return dsd::ipow<3>(x) * (formfac * formfac) * (ssig + (3. * dsd::ipow<2>(p.kfn * p.R_a / x) - 0.5) * dskappa);
 }
@@ -261,7 +261,7 @@ DS_D int dop853_quad(const SfacPar& par, double x, double xend, int max_steps, d
         der2 = sqrt(der2) / h;
         double der12 = fmax(fabs(der2), sqrt(dnf));
         double h1;
-        if (der12 <= 1.0e-15) h1 = fmax(1.0e-6, fabs(h) * 1.0e-3); else h1 = pow(0.01 / der12, 1.0 / 8);
+        if (der12 <= 1.0e-15) h1 = fmax(1.0e-6, fabs(h) * 1.0e-3); else h1 = dsm::pow(0.01 / der12, 1.0 / 8);
         h = fmin(fmin(100.0 * fabs(h), h1), hmax);
         h = copysign(h, posneg);
     }
@@ -287,8 +287,8 @@ DS_D int dop853_quad(const SfacPar& par, double x, double xend, int max_steps, d
         double deno = err + 0.01 * err2;
         if (deno <= 0.0) deno = 1.0;
         err = fabs(h) * err * sqrt(1.0 / (1 * deno));
-        double fac11 = pow(err, 0.125);
-        double fac = fac11 / pow(facold, 0.0);
+        double fac11 = dsm::pow(err, 0.125);
+        double fac = fac11 / dsm::pow(facold, 0.0);
         fac = fmax(facc2, fmin(facc1, fac / safe));
         double hnew = h / fac;
         if (err <= 1.0) {
@@ -322,18 +322,18 @@ DS_D DsNucleus nucleus_model(const DsComp& c) {
     double n_l = n_0 + n_2 * (isospin * isospin);
     DsNucleus r;
     r.n_in = n_l / 2.0 * (1.0 + DS_R4(0.9208) * isospin);
-    r.R_a = pow(3.0 * (c.A - c.Z) / 4.0 / pi / r.n_in, onethird);
+    r.R_a = dsm::pow(3.0 * (c.A - c.Z) / 4.0 / pi / r.n_in, onethird);
     return r;
 }
 // Lambda_n,imp: T-independent (neutron_conductivity.f:338-383, :149-153)
 DS_D int ds_lambda_imp(double nn, const DsComp& c, double& lambda) {
-    double kFn = pow(threepisquare * nn, onethird);
+    double kFn = dsm::pow(threepisquare * nn, onethird);
     DsNucleus nuc = nucleus_model(c);
     SfacPar par{0.0, c.Z, c.A, c.Yn, kFn, nuc.R_a};
     return dop853_quad<false>(par, 1.0e-10, 2.0 * kFn * nuc.R_a, 1000, DS_R4(1.0e-4), DS_R4(1.0e-5), lambda);
 }
 DS_D int ds_lambda_phonon(double nn, double T, const DsComp& c, double& lambda) {
-    double kFn = pow(threepisquare * nn, onethird);
+    double kFn = dsm::pow(threepisquare * nn, onethird);
     DsNucleus nuc = nucleus_model(c);
     SfacPar par{T, c.Z, c.A, c.Yn, kFn, nuc.R_a};
     return dop853_quad<true>(par, 1.0e-10, 2.0 * kFn * nuc.R_a, 1000, DS_R4(1.0e-4), DS_R4(1.0e-5), lambda);
@@ -343,11 +343,11 @@ DS_D double neutron_nu_prefactor(double nn, double nion, const DsComp& c) {
     const double twothird4 = (double)(2.0f / 3.0f);
     DsNucleus nuc = nucleus_model(c);
     double fac = (double)(4.0f / 27.0f) / pi / dsd::ipow<3>(hbar) / (clight * clight);
-    double V = hbar * hbar * pow(threepisquare * nuc.n_in, twothird4) / 2.0 / Mneutron *
-               (1.0 - pow(nn / nuc.n_in, twothird4));
+    double V = hbar * hbar * dsm::pow(threepisquare * nuc.n_in, twothird4) / 2.0 / Mneutron *
+               (1.0 - dsm::pow(nn / nuc.n_in, twothird4));
     double mnstar = Mneutron;
-    double EFn = DS_R4(15.1) * mev_to_ergs * pow(c.Yn, twothird4) *
-                     pow(nn * amu / c.Yn / DS_R4(1.0E14), twothird4) * (2.0 * Mneutron / mnstar) +
+    double EFn = DS_R4(15.1) * mev_to_ergs * dsm::pow(c.Yn, twothird4) *
+                     dsm::pow(nn * amu / c.Yn / DS_R4(1.0E14), twothird4) * (2.0 * Mneutron / mnstar) +
                  Mneutron * (clight * clight);
     return fac * EFn * (nion / nn) * dsd::ipow<2>(V * nuc.R_a);
 }
@@ -359,9 +359,9 @@ DS_D double sPh(double nn, double nion, double temperature, const DsComp& c) {
     double etwo = finestructure * hbarc_n;
     double Mu_n = amu * clight2 * ergs_to_mev;
     double T = temperature * boltzmann * ergs_to_mev;
-    double ai = pow(3.0 / fourpi / nion, onethird);
-    double kFn = pow(threepisquare * nn, onethird);
-    double kFe = pow(threepisquare * nion * c.Z, onethird);
+    double ai = dsm::pow(3.0 / fourpi / nion, onethird);
+    double kFn = dsm::pow(threepisquare * nn, onethird);
+    double kFe = dsm::pow(threepisquare * nion * c.Z, onethird);
     double vs = hbarc_n * kFn / Mn_n / (double)sqrtf(3.0f);
     double Cv = 2.0 * (pi * pi) * dsd::ipow<3>(T) / 15.0 / dsd::ipow<3>(vs);
     double omega_p = sqrt(fourpi * etwo * c.Z2 * nion / c.A / Mu_n);
@@ -370,9 +370,9 @@ DS_D double sPh(double nn, double nion, double temperature, const DsComp& c) {
     double alpha = cs / vs;
     double anlt = anl / (1.0 + DS_R4(0.4) * kFn * anl + 0.5 * 2.0 * anl * (kFn * kFn));
     double gmix = 2.0 * anlt * hbarc_n * sqrt(nion * kFn / c.A / (Mu_n * Mu_n));
-    double TUm = onethird * etwo * omega_p * pow(c.Z, onethird);
+    double TUm = onethird * etwo * omega_p * dsm::pow(c.Z, onethird);
     double omega = 3.0 * T / hbarc_n;
-    double fu = exp(-TUm / T);
+    double fu = dsm::exp(-TUm / T);
     double Llphn = 2.0 / pi / omega;
     double Llphu = 100.0 * ai;
     double Llph = 1.0 / (fu / Llphu + (1.0 - fu) / Llphn);
@@ -389,9 +389,9 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
                           int imp_ierr, DsCond& kap) {
     const double eQ_threshold = 1.0e-8, sf_reduction_threshold = 1.0e-10;
     kap = DsCond{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const double lgrho = log10(rho);
+    const double lgrho = dsm::log10(rho);
     const double ne = rho / amu * c.Ye;
-    const double kF = pow(threepisquare * ne, onethird);
+    const double kF = dsm::pow(threepisquare * ne, onethird);
     const double xF = hbar * kF / Melectron / clight;
     const double eF = sqrt(1.0 + xF * xF);
     const double Gamma_e = Gamma / c.Z53;
@@ -419,8 +419,8 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
             if (T < Tns) {
                 double tau = T / Tns;
                 double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / sqrt(tau) + DS_R4(1.764) / tau);
-                R = pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
-                    exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
+                R = dsm::pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
+                    dsm::exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
                 if (R < sf_reduction_threshold) R = 0.0;
             }
             const double pre = neutron_nu_prefactor(nn, nion, c);

@@ -29,8 +29,8 @@ struct DsHostConsts {
     double ctf_fac;     // (18.0/175.0)*(12.0/pi)**(2.0*onethird) ion.f:184
     double xrs;         // finestructure*(9.0*pi/4.0)**onethird  ion.f:198,303
     double atf;         // (54.0/175.0)*(12.0/pi)**onethird*finestructure ion.f:301
-    double e1;          // exp(1.0_dp) ion.f:300
-    double half_log_6_over_pi;  // 0.5*log(6.0/pi) ion.f:432
+    double e1;          // dsm::exp(1.0_dp) ion.f:300
+    double half_log_6_over_pi;  // 0.5*dsm::log(6.0/pi) ion.f:432
     double aei_fac;     // (4.0/9.0/pi)**onethird electron_conductivity.f:128
     double befac;       // (finestructure/pi)**1.5 electron_conductivity.f:27
     double yfac;        // sqrt(4.0*finestructure/pi) electron_conductivity.f:24
@@ -48,7 +48,7 @@ using namespace dsc;
 DS_D void lattice_properties(double rho, double T, const DsComp& c, double& ne, double& rs,
                         double& Gamma_e, double& Gamma, double& ionQ) {
     ne = rho * c.Ye / amu;
-    rs = pow(3.0 / fourpi / ne, onethird) / a_Bohr;
+    rs = dsm::pow(3.0 / fourpi / ne, onethird) / a_Bohr;
     Gamma_e = 2.0 * Rydberg / boltzmann / T / rs;
     Gamma = Gamma_e * c.Z53;
     ionQ = sqrt(3.0 * (Gamma_e * Gamma_e) * Melectron / rs / amu * c.Z2XoA2 * c.A / c.Z);
@@ -60,7 +60,7 @@ DS_D double nuclear_volume_fraction(double rho, const DsComp& c, double nuclear_
 
 DS_D double neutron_wavenumber(double rho, const DsComp& c, double chi) {
     double n = rho * c.Yn / amu / (1.0 - chi);
-    return pow(threepisquare * n, onethird) / cm_to_fm;
+    return dsm::pow(threepisquare * n, onethird) / cm_to_fm;
 }
 
 DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
@@ -72,8 +72,8 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta3 * theta;
     double t1, t2, t1_h, t2_h, t1_hh, t2_hh;
     if (theta > theta_low) {
-        double cht1 = cosh(1.0 / theta), sht1 = sinh(1.0 / theta);
-        double cht2 = cosh(1.0 / sqth), sht2 = sinh(1.0 / sqth);
+        double cht1 = dsm::cosh(1.0 / theta), sht1 = dsm::sinh(1.0 / theta);
+        double cht2 = dsm::cosh(1.0 / sqth), sht2 = dsm::sinh(1.0 / sqth);
         t1 = sht1 / cht1;
         t2 = sht2 / cht2;
         t1_h = -1.0 / dsd::ipow<2>(theta * cht1);
@@ -131,7 +131,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double e_hh = e_h * eh + e * (t1_hh / t1 - dsd::ipow<2>(t1_h / t1) + e0_hh / e0 - dsd::ipow<2>(e0_h / e0) -
                                   e1_hh / e1 + dsd::ipow<2>(e1_h / e1) - 1.0 / theta2);
 
-    double exp1th = exp(-1.0 / theta);
+    double exp1th = dsm::exp(-1.0 / theta);
     double c = (DS_R4(0.872496) + DS_R4(0.025248) * exp1th) * e;
     double c_h = DS_R4(0.025248) * exp1th / theta2 * e + c * e_h / e;
     double c_hh = DS_R4(0.025248) * exp1th / theta2 * (e_h + (1.0 - 2.0 * theta) / theta2 * e) +
@@ -177,7 +177,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
                     2.0 * ((d_h * b2 + d * b2_h + b3 * e_h + d_h * b2 + d * b2_h) * e_h + d * b2 * e_hh) / (e * e) +
                     6.0 * d * b2 * (e_h * e_h) / dsd::ipow<3>(e)) / e;
 
-    double s3 = c3 * log(r3);
+    double s3 = c3 * dsm::log(r3);
     double s3_h = s3 * c3_h / c3 + c3 * r3_h / r3;
     double s3_hh = (s3_h * c3_h + s3 * c3_hh) / c3 - s3 * dsd::ipow<2>(c3_h / c3) +
                    (c3_h * r3_h + c3 * r3_hh) / r3 - c3 * dsd::ipow<2>(r3_h / r3);
@@ -204,7 +204,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double s4b = d * b3 + b4 * b2;
     double s4b_h = d_h * b3 + d * b3_h + b4_h * b2 + b4 * b2_h;
     double s4b_hh = d_hh * b3 + 2.0 * d_h * b3_h + d * b3_hh + b4_hh * b2 + 2. * b4_h * b2_h + b4 * b2_hh;
-    double s4c = atan(c4 / discr) - atan(d / discr);
+    double s4c = dsm::atan(c4 / discr) - dsm::atan(d / discr);
     double up1 = c4_h * discr - c4 * di_h;
     double dn1 = discr * discr + c4 * c4;
     double up2 = d_h * discr - d * di_h;
@@ -246,18 +246,18 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
 DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
     const double s3 = (double)sqrtf(3.0f);
     const double CTFfac = ds_hc.ctf_fac;
-    double Z13 = pow(Z, onethird);
-    double cDH = (Z / s3) * (pow(1.0 + Z, 1.5) - 1.0 - pow(Z, 1.5));
+    double Z13 = dsm::pow(Z, onethird);
+    double cDH = (Z / s3) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
     double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / sqrt(Z13));
     double xrs = ds_hc.xrs;
     double xr = xrs / rs;
-    double lZ = log(Z);
+    double lZ = dsm::log(Z);
 
-    double a = DS_R4(1.11) * pow(Z, DS_R4(0.475));
+    double a = DS_R4(1.11) * dsm::pow(Z, DS_R4(0.475));
     double b = DS_R4(0.2) + DS_R4(0.078) * (lZ * lZ);
     double nu = DS_R4(1.16) + DS_R4(0.08) * lZ;
     double sGam = sqrt(Gamma_e);
-    double nuGam = pow(Gamma_e, nu);
+    double nuGam = dsm::pow(Gamma_e, nu);
     double nuGam_g = nu * nuGam / Gamma_e;
     double nuGam_gg = (nu - 1.0) * nuGam_g / Gamma_e;
     double ty1 = 1.0 / (DS_R4(0.001) * (Z * Z) + 2.0 * Gamma_e);
@@ -296,7 +296,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
     double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / (d0 * d0)) / d0;
 
     double rgam = sqrt(1.0 + xr * xr);
-    double q1 = DS_R4(0.18) / pow(Z, 0.25);
+    double q1 = DS_R4(0.18) / dsm::pow(Z, 0.25);
     double q2 = DS_R4(0.2) + DS_R4(0.37) / sqrt(Z);
     double h1u = 1.0 + DS_R4(0.2) * (xr * xr);
     double h1d = 1.0 + q1 * xr + q2 * (xr * xr);
@@ -350,16 +350,16 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     double aTF = ds_hc.atf;
     double xrs = ds_hc.xrs;
     double xr = xrs / rs;
-    double lZ = log(Z);
-    double r3 = 1.0 / (1.0 + DS_R4(0.01) * pow(lZ, 1.5) + DS_R4(0.097) / (Z * Z));
+    double lZ = dsm::log(Z);
+    double r3 = 1.0 / (1.0 + DS_R4(0.01) * dsm::pow(lZ, 1.5) + DS_R4(0.097) / (Z * Z));
     double b[4];
-    b[0] = 1.0 - a[0] / pow(Z, DS_R4(0.267)) + DS_R4(0.27) / Z;
-    b[1] = 1.0 + 2.25 / pow(Z, onethird) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
+    b[0] = 1.0 - a[0] / dsm::pow(Z, DS_R4(0.267)) + DS_R4(0.27) / Z;
+    b[1] = 1.0 + 2.25 / dsm::pow(Z, onethird) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
                      (1.0 + DS_R4(0.222) * dsd::ipow<6>(Z));
     b[2] = a[3] / (1.0 + lZ);
-    b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / pow(Z, 1.5);
+    b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / dsm::pow(Z, 1.5);
 
-    double finf = aTF * pow(Z, twothird) * b[0] * sqrt(1.0 + b[1] / (xr * xr));
+    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sqrt(1.0 + b[1] / (xr * xr));
     double finfx = -b[1] / ((b[1] + xr * xr) * xr);
     double finf_x = finf * finfx;
     double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / ((b[1] + xr * xr) * xr);
@@ -380,14 +380,14 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
         double y0_xx = 0.0;
         double y0_gg = y0_g / Gamma;
         double y0_xg = y0_g / xr;
-        double y1 = exp(y0);
+        double y1 = dsm::exp(y0);
         double y1_x = y1 * y0_x;
         double y1_g = y1 * y0_g;
         double y1_xx = y1 * (y0_x * y0_x + y0_xx);
         double y1_gg = y1 * (y0_g * y0_g + y0_gg);
         double y1_xg = y1 * (y0_x * y0_g + y0_xg);
         double sa = 1.0 + y1;
-        double supa = log(sa);
+        double supa = dsm::log(sa);
         double supa_x = y1_x / sa;
         double supa_g = y1_g / sa;
         double supa_xx = (y1_xx - y1_x * y1_x / sa) / sa;
@@ -395,7 +395,7 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
         double supa_xg = (y1_xg - y1_x * y1_g / sa) / sa;
         double em2 = e1 - 2.0;
         double sb = e1 - em2 / y1;
-        double supb = log(sb);
+        double supb = dsm::log(sb);
         double em2y1 = em2 / ((y1 * y1) * sb);
         double supb_x = em2y1 * y1_x;
         double supb_g = em2y1 * y1_g;
@@ -421,7 +421,7 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
         sup_gg = 0.0;
         sup_xg = sup_x / Gamma;
     }
-    double gr3 = pow(Gamma / sup, r3);
+    double gr3 = dsm::pow(Gamma / sup, r3);
     double gr3x = -r3 * sup_x / sup;
     double gr3_x = gr3 * gr3x;
     double gr3_xx = gr3_x * gr3x - r3 * gr3 * (sup_xx / sup - dsd::ipow<2>(sup_x / sup));
@@ -460,20 +460,20 @@ DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
     const double B1 = DS_R4(4.50e-3), B2 = DS_R4(170.0), B3 = DS_R4(-8.4e-5), B4 = DS_R4(3.70e-3);
 
     double f0 = A1 * (sqrt(Gamma * (A2 + Gamma)) -
-                      A2 * log(sqrt(Gamma / A2) + sqrt(1.0 + Gamma / A2))) +
-                2.0 * A3 * (sqrt(Gamma) - atan(sqrt(Gamma)));
+                      A2 * dsm::log(sqrt(Gamma / A2) + sqrt(1.0 + Gamma / A2))) +
+                2.0 * A3 * (sqrt(Gamma) - dsm::atan(sqrt(Gamma)));
     double G2 = Gamma * Gamma;
-    double G15 = pow(Gamma, 1.5);
-    double f = f0 + B1 * (Gamma - B2 * log(1.0 + Gamma / B2)) + 0.5 * B3 * log(1.0 + G2 / B4);
+    double G15 = dsm::pow(Gamma, 1.5);
+    double f = f0 + B1 * (Gamma - B2 * dsm::log(1.0 + Gamma / B2)) + 0.5 * B3 * dsm::log(1.0 + G2 / B4);
     double u = G15 * (A1 / sqrt(A2 + Gamma) + A3 / (1.0 + Gamma)) +
                G2 * (B1 / (B2 + Gamma) + B3 / (B4 + G2));
-    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / dsd::ipow<2>(Gamma + 1.0) - A1 * A2 / pow(Gamma + A2, 1.5)) +
+    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / dsd::ipow<2>(Gamma + 1.0) - A1 * A2 / dsm::pow(Gamma + A2, 1.5)) +
                 G2 * (B3 * (G2 - B4) / dsd::ipow<2>(G2 + B4) - B1 * B2 / dsd::ipow<2>(Gamma + B2));
     double p = onethird * u;
     double dpr = (4.0 * u - cv) / 9.0;
     double dpt = onethird * cv;
 
-    double fid = 3.0 * log(theta) - 1.5 * log(Gamma) - ds_hc.half_log_6_over_pi - 1.0;
+    double fid = 3.0 * dsm::log(theta) - 1.5 * dsm::log(Gamma) - ds_hc.half_log_6_over_pi - 1.0;
     f = f + fid;
     u = u + 1.5;
     p = p + 1.0;
@@ -512,7 +512,7 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
         fh = -uh / 3.0;
         cvh = 4.0 * uh;
     } else if (theta < theta_low) {
-        fh = 3.0 * log(theta) + clm - 1.5 * w * theta + theta * theta / 24.0;
+        fh = 3.0 * dsm::log(theta) + clm - 1.5 * w * theta + theta * theta / 24.0;
         uh = 3.0 - 1.5 * w * theta + theta * theta / 12.0;
         cvh = 3.0 - theta * theta / 12.0;
     } else {
@@ -535,9 +535,9 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
         Bc[1] = Bc[1] + 9.0 * alpha[6] * a[6] * dsd::ipow<8>(theta) + 11.0 * alpha[8] * a[8] * dsd::ipow<10>(theta);
         Bc[2] = Bc[2] + 72.0 * alpha[6] * a[6] * dsd::ipow<7>(theta) + 110.0 * alpha[8] * a[8] * dsd::ipow<9>(theta);
         for (int n = 1; n <= 3; ++n) {
-            double ea = exp(-alpha[n] * theta);
+            double ea = dsm::exp(-alpha[n] * theta);
             double omea = 1.0 - ea;
-            fh = fh + log(omea);
+            fh = fh + dsm::log(omea);
             uh = uh + alpha[n] * ea / omea;
             cvh = cvh + alpha[n] * alpha[n] * ea / (omea * omea);
         }
@@ -560,7 +560,7 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
     double theta2 = theta * theta;
     double theta4 = dsd::ipow<4>(theta);
     double c1t2 = c1 * theta2;
-    double sup = exp(-c1t2);
+    double sup = dsm::exp(-c1t2);
     double tq = b1 * theta2 / Gamma;
     double gninv = sup;
     for (int n = 1; n <= 3; ++n) {
@@ -592,8 +592,8 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
 
 DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsThermo& r) {
     const double sevensixth = (double)(7.0f / 6.0f);
-    double Gamma = Gamma_e * pow(Z, fivethird);
-    double theta = Gamma * sqrt(3.0 * Melectron / A / amu / rs) / pow(Z, sevensixth);
+    double Gamma = Gamma_e * dsm::pow(Z, fivethird);
+    double theta = Gamma * sqrt(3.0 * Melectron / A / amu / rs) / dsm::pow(Z, sevensixth);
     DsThermo ie, ii;
     if (phase == ds_liquid_phase) {
         ie_liquid(Gamma_e, rs, Z, ie);
@@ -617,14 +617,14 @@ DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r
     double D = c.Z2 / (c.Z * c.Z);
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (fabs(D - 1.0) < threshold) return;
-    double p3 = pow(D, DS_R4(-0.2));
+    double p3 = dsm::pow(D, DS_R4(-0.2));
     double d0 = (DS_R4(2.6) * difR + 14.0 * dsd::ipow<3>(difR)) / (1.0 - p3);
-    double gp = d0 * pow(Gamma, p3);
+    double gp = d0 * dsm::pow(Gamma, p3);
     double f0 = difFDH / (1.0 + gp);
     double q = (D * D) * DS_R4(0.0117);
     double rr = 1.5 / p3 - 1.0;
     double gq = q * gp;
-    double f = f0 / pow(1.0 + gq, rr);
+    double f = f0 / dsm::pow(1.0 + gq, rr);
     double g = 1.5 - p3 * gp / (1.0 + gp) - rr * p3 * gq / (1.0 + gq);
     double u = f * g;
     double s = u - f;
@@ -656,7 +656,7 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
             one_ion(Gamma_e, rs, Zion[i], Aion[i], phase, t);
             f = f + Yion[i] * t.f;
             u = u + Yion[i] * t.u;
-            s = s + Yion[i] * (t.s - log(Yion[i]));
+            s = s + Yion[i] * (t.s - dsm::log(Yion[i]));
             p = p + Yion[i] * t.p;
             cv = cv + Yion[i] * t.cv;
             dpr = dpr + Yion[i] * t.dpr;
@@ -685,27 +685,27 @@ DS_D double ratfit(const double* a, int m, const double* b, int k, double xx) {
 }
 
 DS_D double zfermim12(double x) {  // funct_fermi1.f:21-86
-    if (x < 2.0) { double xx = exp(x); return xx * ratfit(zfermim12_a1, 7, zfermim12_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermim12_a1, 7, zfermim12_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return sqrt(x) * ratfit(zfermim12_a2, 11, zfermim12_b2, 11, xx);
 }
 
 DS_D double zfermi12(double x) {  // :88-146
-    if (x < 2.0) { double xx = exp(x); return xx * ratfit(zfermi12_a1, 7, zfermi12_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermi12_a1, 7, zfermi12_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return x * sqrt(x) * ratfit(zfermi12_a2, 10, zfermi12_b2, 11, xx);
 }
 
 DS_D double zfermi32(double x) {  // :216-276
-    if (x < 2.0) { double xx = exp(x); return xx * ratfit(zfermi32_a1, 6, zfermi32_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermi32_a1, 6, zfermi32_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return x * x * sqrt(x) * ratfit(zfermi32_a2, 9, zfermi32_b2, 10, xx);
 }
 
 DS_D double ifermi12(double f) {  // :528-580
     const double an = 0.5;
-    if (f < 4.0) return log(f * ratfit(ifermi12_a1, 4, ifermi12_b1, 3, f));
-    double ff = 1.0 / pow(f, 1.0 / (1.0 + an));
+    if (f < 4.0) return dsm::log(f * ratfit(ifermi12_a1, 4, ifermi12_b1, 3, f));
+    double ff = 1.0 / dsm::pow(f, 1.0 / (1.0 + an));
     double rn = ff + ifermi12_a2[5];
     for (int i = 4; i >= 0; --i) rn = rn * ff + ifermi12_a2[i];
     double den = ifermi12_b2[5];
@@ -717,7 +717,7 @@ DS_D void MB77(double n, double T, double Tns, DsThermo& r) {
     const double c[4] = {DS_R4(1.2974), DS_R4(15.0298), DS_R4(-15.2343), DS_R4(7.4663)};
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (n == 0.0) return;
-    double k = pow(0.5 * threepisquare * n, onethird) / cm_to_fm;
+    double k = dsm::pow(0.5 * threepisquare * n, onethird) / cm_to_fm;
     double dkdn = onethird * k / n;
     double u = k * (c[0] + k * (c[1] + k * (c[2] + k * c[3])));
     u = u * mev_to_ergs;
@@ -727,7 +727,7 @@ DS_D void MB77(double n, double T, double Tns, DsThermo& r) {
     double dpr = (p / n + dpdk * dkdn) * n;
     double dpT = 0.0;
 
-    double lambda3 = pi * pi * pow(hbar * hbar / (Mneutron * boltzmann * T), 1.5) / (double)sqrtf(2.0f);
+    double lambda3 = pi * pi * dsm::pow(hbar * hbar / (Mneutron * boltzmann * T), 1.5) / (double)sqrtf(2.0f);
     double zeta = ifermi12(n * lambda3);
     double cv = 2.5 * zfermi32(zeta) / zfermi12(zeta) - 4.5 * zfermi12(zeta) / zfermim12(zeta);
     cv = cv * boltzmann;
@@ -737,8 +737,8 @@ DS_D void MB77(double n, double T, double Tns, DsThermo& r) {
     if (T < Tns) {
         double tau = T / Tns;
         double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / sqrt(tau) + DS_R4(1.764) / tau);
-        R = pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
-            exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
+        R = dsm::pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
+            dsm::exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
     } else {
         R = 1.0;
     }
@@ -769,13 +769,14 @@ struct DsEosRes {
     int phase, ierr;
 };
 
-// Sum of the five components (dStar_eos_lib.f:173-258).  `logT` is log10(T); for the coefficient
+// Sum of the five components (dStar_eos_lib.f:173-258).  `logT` is dsm::log10(T); for the coefficient
 // pass it is supplied by the host together with T so that table-cell selection is identical on
 // both sides of the ABI.  Zion/Aion/Yion: the charged species of the zone (Yion = Y/(1-Yn)).
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
                             double logT, const DsComp& c, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
-                            const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o) {
+                            const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o,
+                            double* __restrict__ comps = nullptr) {
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
     dse::lattice_properties(rho, T, c, ne, rs, Gamma_e, Gamma, ionQ);
@@ -825,9 +826,9 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     const double dpt = e.dpt + ex.dpt * pexfac + ion.dpt * pifac + nt.dpt * pnfac + rad.dpt;
     const double gamma3m1 = dpt / rho / T / cv;
     const double gamma1 = (dpr + dpt * gamma3m1) / p;
-    o.lnP = log(p);
-    o.lnE = log(u);
-    o.lnS = log(s);
+    o.lnP = dsm::log(p);
+    o.lnE = dsm::log(u);
+    o.lnS = dsm::log(s);
     o.grad_ad = gamma3m1 / gamma1;
     o.chiRho = dpr / p;
     o.chiT = dpt / p;
@@ -842,4 +843,21 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     o.Gamma3 = gamma3m1;
     o.phase = phase;
     o.ierr = (chi < 1.0) ? ierr_h : -10;
+    if (comps) {  // optional `components` argument of eval_crust_eos (dStar_eos_lib.f:260-296): (7,4) = P,E,S,F,Cv,dPdlnRho,dPdlnT
+        const double pe = e.p + ex.p * pexfac;
+        double* q = comps;
+        q[0] = pe; q[1] = e.u + ex.u * uexfac; q[2] = e.s + ex.s * sexfac; q[3] = e.f + ex.f * uexfac;
+        q[4] = e.cv + ex.cv * sexfac; q[5] = (e.dpr + ex.dpr * pexfac) / pe; q[6] = (e.dpt + ex.dpt * pexfac) / pe;
+        q += 7;
+        q[0] = ion.p * pifac; q[1] = ion.u * uifac; q[2] = ion.s * sifac; q[3] = ion.f * uifac; q[4] = ion.cv * sifac;
+        q[5] = ion.dpr / ion.p; q[6] = ion.dpt / ion.p;
+        q += 7;
+        if (c.Yn < rq.Ythresh) { for (int i = 0; i < 7; ++i) q[i] = 0.0; }
+        else {
+            q[0] = nt.p * pnfac; q[1] = nt.u * unfac; q[2] = nt.s * snfac; q[3] = nt.f * unfac; q[4] = nt.cv * snfac;
+            q[5] = nt.dpr / nt.p; q[6] = nt.dpt / nt.p;
+        }
+        q += 7;
+        q[0] = rad.p; q[1] = rad.u; q[2] = rad.s; q[3] = rad.f; q[4] = rad.cv; q[5] = rad.dpr / rad.p; q[6] = rad.dpt / rad.p;
+    }
 }

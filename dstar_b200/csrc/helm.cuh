@@ -113,14 +113,14 @@ DS_D int ds_helm_electron(const DsHelmDev& h, double T, double logT, double rho,
     double ytot1 = 1.0 / abar;
     double ye = __dmul_rn(ytot1, zbar);
     double din = __dmul_rn(ye, rho);
-    if (temp < h.templo) { temp = h.templo; logtemp = log10(temp); }
+    if (temp < h.templo) { temp = h.templo; logtemp = dsm::log10(temp); }
     if (din < h.denlo) return -3;
     if (temp > h.temphi) { temp = h.temphi; logtemp = h.logthi; }
     if (din > h.denhi) din = h.denhi;
 
     int jat = (int)((logtemp - h.logtlo) * h.logtstpi) + 1;
     jat = max(1, min(jat, h.jmax - 1));
-    int iat = (int)((log10(din) - h.logdlo) * h.logdstpi) + 1;
+    int iat = (int)((dsm::log10(din) - h.logdlo) * h.logdstpi) + 1;
     iat = max(1, min(iat, h.imax - 1));
     const int j0 = jat - 1, i0 = iat - 1;
     const double* base = h.node + (size_t)DS_HELM_REC * ((size_t)i0 + (size_t)h.imax * j0);

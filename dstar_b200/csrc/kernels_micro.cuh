@@ -65,7 +65,7 @@ struct DsMicroArgs {
     const double *Yion, *Yion_bar;                 // (ncharged, total_zones)
     const double *Zion, *Aion;                     // (ncharged)
     const double *Tc_cell, *Tc_face;               // (3, total_zones) or null -> gap tables
-    const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, exp(lnT), log10(T)
+    const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, dsm::exp(lnT), dsm::log10(T)
     DsEosCtrl eos;
     DsCondCtrl cond;
     int nu_channels[5];
@@ -150,23 +150,23 @@ __global__ void __launch_bounds__(DS_NTAB) ds_micro_kernel(DsMicroArgs a, DsHelm
                       (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
     if (r.ierr != 0) s_err = r.ierr;
     if (!FACE) {
-        s_v[0][it] = log(r.Cp);
-        s_v[1][it] = log(r.Gamma);
+        s_v[0][it] = dsm::log(r.Cp);
+        s_v[1][it] = dsm::log(r.Gamma);
         if (iz == 0 && it == 0)  // create_model.f:367-369
-            a.rho_bar1[star] = rho * pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+            a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
         DsNeutrino eps;
         dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
-        double lnenu = log(eps.total / rho);
+        double lnenu = dsm::log(eps.total / rho);
         if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
-            if (log10(a.P_bar[g]) < a.lgP_shell_Urca && log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
-                lnenu = log(exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
+            if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
+                lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
                                              dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
         }
         s_v[2][it] = lnenu;
     } else {
         DsCond K;
         dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, Tc[1], s_lam, s_lam_ierr, K);
-        s_v[0][it] = log(K.total);
+        s_v[0][it] = dsm::log(K.total);
     }
     __syncthreads();
     const size_t ob = (size_t)4 * DS_NTAB * g;
@@ -186,6 +186,7 @@ struct DsEvalEosArgs {
     const double *rho, *T, *ionic, *Zion, *Aion, *Yion, *Tcs, *chi_in;
     DsEosCtrl eos;
     double* res;  // (15, n)
+    double* comps;  // (7, 4, n) or null
     int* phase;
     double* chi_out;
     int* ierr;
@@ -198,8 +199,9 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     double chi = a.chi_in ? a.chi_in[k] : -1.0;
     if (chi == -1.0) chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
     DsEosRes r;
-    ds_eval_crust_eos(helm, a.eos, rho, T, log10(T), c, a.ncharged, a.Zion, a.Aion,
-                      a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r);
+    ds_eval_crust_eos(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
+                      a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r,
+                      a.comps ? a.comps + (size_t)28 * k : nullptr);
     double* o = a.res + (size_t)15 * k;
     o[0] = r.lnP; o[1] = r.lnE; o[2] = r.lnS; o[3] = r.grad_ad; o[4] = r.chiRho; o[5] = r.chiT; o[6] = r.Cp;
     o[7] = r.Cv; o[8] = r.Chi; o[9] = r.Gamma; o[10] = r.Theta; o[11] = r.mu_e; o[12] = r.mu_n;

@@ -1,0 +1,22 @@
+// Test-support kernel: evaluates one dsmath function on the device so the CPU-side copy of the
+// specification can be compared bit for bit (tests/test_gpu_parity.py::test_dsmath_bits).
+#pragma once
+#include "dsmath.cuh"
+
+DSM_HD double ds_dsmath_dispatch(int fn, double x, double y) {
+    switch (fn) {
+        case 0: return dsm::exp(x);
+        case 1: return dsm::log(x);
+        case 2: return dsm::log10(x);
+        case 3: return dsm::pow(x, y);
+        case 4: return dsm::sin(x);
+        case 5: return dsm::cos(x);
+        case 6: return dsm::sinh(x);
+        case 7: return dsm::cosh(x);
+        default: return dsm::atan(x);
+    }
+}
+__global__ void ds_dsmath_kernel(int fn, int n, const double* x, const double* y, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ds_dsmath_dispatch(fn, x[i], y[i]);
+}

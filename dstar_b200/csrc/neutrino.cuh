@@ -27,7 +27,7 @@ constexpr double cn_cap = 1.0 - cn_ca;
 
 DS_D double plasma(double t, double r) {
     const double cvd = cn_cv * cn_cv + cn_dn * (cn_cvp * cn_cvp);
-    double rdouble = log10(2.0 * r);
+    double rdouble = dsm::log10(2.0 * r);
     double x = (17.5 + rdouble - 3.0 * t) / 6.0;
     double y = (-24.5 + rdouble + 3.0 * t) / 6.0;
     double enum_ = fmin(0.0, y - 1.6 + 1.25 * x);
@@ -35,17 +35,17 @@ DS_D double plasma(double t, double r) {
     if (fabs(x) > 0.7 || y < 0.0) {
         fxy = 1.0;
     } else {
-        fxy = 1.05 + (0.39 - 1.25 * x - 0.35 * sin(4.5 * x) - 0.3 * exp(-dsd::ipow<2>(4.5 * x + 0.9))) *
-                         exp(-dsd::ipow<2>(enum_ / (0.57 - 0.25 * x)));
+        fxy = 1.05 + (0.39 - 1.25 * x - 0.35 * dsm::sin(4.5 * x) - 0.3 * dsm::exp(-dsd::ipow<2>(4.5 * x + 0.9))) *
+                         dsm::exp(-dsd::ipow<2>(enum_ / (0.57 - 0.25 * x)));
     }
     double lamb = 1.686e-10 * t;
-    double gamd = 1.1095e11 * r / ((t * t) * sqrt(1.0 + pow(1.019e-6 * r, two_thirds)));
+    double gamd = 1.1095e11 * r / ((t * t) * sqrt(1.0 + dsm::pow(1.019e-6 * r, two_thirds)));
     double gam = sqrt(gamd);
-    double ft = 2.4 + 0.6 * sqrt(gam) + 0.51 * gam + 1.25 * pow(gam, 1.5);
-    double fl = (8.6 * gamd + 1.35 * pow(gam, 7.0 / 2.0)) / (225.0 - 17.0 * gam + gamd);
+    double ft = 2.4 + 0.6 * sqrt(gam) + 0.51 * gam + 1.25 * dsm::pow(gam, 1.5);
+    double fl = (8.6 * gamd + 1.35 * dsm::pow(gam, 7.0 / 2.0)) / (225.0 - 17.0 * gam + gamd);
     double qap;
     if (fabs(sqrt(gamd)) > 700.0) qap = 0.0;
-    else qap = fxy * (fl + ft) * exp(-gam) * dsd::ipow<3>(gamd) * dsd::ipow<9>(lamb) * 3.0e21;
+    else qap = fxy * (fl + ft) * dsm::exp(-gam) * dsd::ipow<3>(gamd) * dsd::ipow<9>(lamb) * 3.0e21;
     return qap * cvd;
 }
 
@@ -56,21 +56,21 @@ DS_D double pair(double temp, double rhom) {
     const double coep = (cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap);
     const double coem = (cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap);
     double lam = temp / 5.9302e9;
-    double xi = pow(rhom * 1.0e-9, onethird) / lam;
+    double xi = dsm::pow(rhom * 1.0e-9, onethird) / lam;
     double qp1 = 10.74800 * (lam * lam) + 0.3967 * sqrt(lam) + 1.005;
     double qp2 = rhom / (7.692e7 * dsd::ipow<3>(lam) + 9.715e6 * sqrt(lam));
-    double qp = (1.0 / qp1) * pow(1.0 + qp2, -0.3);
+    double qp = (1.0 / qp1) * dsm::pow(1.0 + qp2, -0.3);
     double axi = a0 + a1 * xi + a2 * (xi * xi);
     double fp1, fp2;
     if (xi > 100.0) fp1 = 0.0;
-    else if (temp < 1.0e10) fp1 = axi * exp(-c * xi);
-    else fp1 = axi * exp(-ch * xi);
+    else if (temp < 1.0e10) fp1 = axi * dsm::exp(-c * xi);
+    else fp1 = axi * dsm::exp(-ch * xi);
     if (temp < 1.0e10) fp2 = dsd::ipow<3>(xi) + b1 / lam + b2 / (lam * lam) + b3 / dsd::ipow<3>(lam);
     else fp2 = dsd::ipow<3>(xi) + bh1 / lam + bh2 / (lam * lam) + bh3 / dsd::ipow<3>(lam);
     double fp = fp1 / fp2;
     double g = 1.0 - 13.04 * (lam * lam) + 133.5 * dsd::ipow<4>(lam) + 1534.0 * dsd::ipow<6>(lam) + 918.6 * dsd::ipow<8>(lam);
     if (lam < 7.0e-3) return 0.0;
-    return 0.5 * coep * (1.0 + coem / coep * qp) * g * exp(-2.0 / lam) * fp;
+    return 0.5 * coep * (1.0 + coem / coep * qp) * g * dsm::exp(-2.0 / lam) * fp;
 }
 
 DS_D double cfp(double lamb, double xi) {
@@ -79,19 +79,19 @@ DS_D double cfp(double lamb, double xi) {
     int band;
     double c, tau;
     if (temp < 1.0e7) return 0.0;
-    else if (temp < 1.0e8) { band = 0; c = 0.5654 + log10(temp / 1.0e7); tau = log10(temp / 1.0e7); }
-    else if (temp < 1.0e9) { band = 1; c = 1.5654; tau = log10(temp / 1.0e8); }
-    else { band = 2; c = 1.5654; tau = log10(temp / 1.0e9); }
+    else if (temp < 1.0e8) { band = 0; c = 0.5654 + dsm::log10(temp / 1.0e7); tau = dsm::log10(temp / 1.0e7); }
+    else if (temp < 1.0e9) { band = 1; c = 1.5654; tau = dsm::log10(temp / 1.0e8); }
+    else { band = 2; c = 1.5654; tau = dsm::log10(temp / 1.0e9); }
     double a[3];
     for (int j = 0; j < 3; ++j) {
-        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * cos(10.0 * pi * tau);
+        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * dsm::cos(10.0 * pi * tau);
         for (int k = 1; k <= 5; ++k) {
             double pjt = pi * (double)k * tau;
-            a[j] = a[j] + cfp_cc[band][j][k] * cos(5.0 / 3.0 * pjt) +
-                   cfp_dd[band][j][k - 1] * sin(5.0 / 3.0 * pjt);
+            a[j] = a[j] + cfp_cc[band][j][k] * dsm::cos(5.0 / 3.0 * pjt) +
+                   cfp_dd[band][j][k - 1] * dsm::sin(5.0 / 3.0 * pjt);
         }
     }
-    return (a[0] + a[1] * xi + a[2] * (xi * xi)) * exp(-c * xi) /
+    return (a[0] + a[1] * xi + a[2] * (xi * xi)) * dsm::exp(-c * xi) /
            (dsd::ipow<3>(xi) + b[0] / lamb + b[1] / (lamb * lamb) + b[2] / dsd::ipow<3>(lamb));
 }
 
@@ -100,8 +100,8 @@ DS_D double photo(double rhom, double lamb) {
     const double coe2 = ((cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap)) /
                         ((cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap));
     double poly = 1.875e8 * lamb + 1.653e8 * (lamb * lamb) + 8.499e8 * dsd::ipow<3>(lamb) - 1.604e8 * dsd::ipow<4>(lamb);
-    double qp = 0.666 * pow(1.0 + 2.045 * lamb, -2.066) * (1.0 / (1.0 + rhom * (1.0 / poly)));
-    double xi = pow(rhom * 1.e-9, onethird) / lamb;
+    double qp = 0.666 * dsm::pow(1.0 + 2.045 * lamb, -2.066) * (1.0 / (1.0 + rhom * (1.0 / poly)));
+    double xi = dsm::pow(rhom * 1.e-9, onethird) / lamb;
     double fp = cfp(lamb, xi);
     return coe1 * (1.0 - coe2 * qp) * rhom * dsd::ipow<5>(lamb) * fp;
 }
@@ -117,7 +117,7 @@ DS_D double pbf(double kF, double T, double Tns) {
     double v2 = v * v;
     double F1 = v2 * (0.602 + v2 * (0.5942 + 0.288 * v2));
     double F2 = sqrt(DS_R4(0.5547) + sqrt(0.4453 * 0.4453 + 0.01130 * v2));
-    double F3 = exp(-sqrt(4.0 * v2 + 2.245 * 2.245) + 2.245);
+    double F3 = dsm::exp(-sqrt(4.0 * v2 + 2.245 * 2.245) + 2.245);
     double F = F1 * F2 * F3;
     double reduct = dsd::ipow<2>(xF / eF);
     return qpbf_pre * (cn_dn + 1) * mstar * xF * dsd::ipow<7>(T / 1.0e9) * F * reduct;
@@ -127,15 +127,15 @@ DS_D double bremsstrahlung(double rho, double T, const DsComp& c) {
     const double threefourth = 3.0 / 4.0, GF = 1.436e-49, Cp2 = 1.675;
     double qbrems_pre = 8.0 * pi * (GF * GF) * (finestructure * finestructure) * Cp2 *
                         dsd::ipow<6>(boltzmann / hbar / clight) / 567.0 / hbar / amu;
-    double re = pow(threefourth / pi * amu / rho / c.Ye, onethird);
-    double kF = pow(threepisquare * rho * c.Ye / amu, onethird);
+    double re = dsm::pow(threefourth / pi * amu / rho / c.Ye, onethird);
+    double kF = dsm::pow(threepisquare * rho * c.Ye / amu, onethird);
     double tau = 0.5 * boltzmann * T / hbar / clight / kF;
-    double eta = pow(c.A / c.Z, onethird) / re / cm_to_fm;
+    double eta = dsm::pow(c.A / c.Z, onethird) / re / cm_to_fm;
     double Zbareta = c.Z * eta;
     double A = 0.269 + 20.0 * tau + 0.0168 * c.Z + 0.00121 * eta - 0.0356 * Zbareta + 0.0137 * c.Z2 * tau +
                1.54 * Zbareta * tau;
     double B = 1.0 + 180.0 * (tau * tau) + 0.483 * tau * c.Z + 20.0 * tau * Zbareta * eta + 4.31e-5 * c.Z2;
-    double L = A / pow(B, threefourth);
+    double L = A / dsm::pow(B, threefourth);
     return qbrems_pre * dsd::ipow<6>(T) * c.Z2 * rho * L * (1.0 - c.Yn) / c.A;
 }
 
@@ -151,7 +151,7 @@ DS_D void ds_crust_neutrino(double rho, double T, const DsComp& c, double chi, d
     if (ch[3]) eps.brems = bremsstrahlung(rho, T, c);
     if (ch[4]) {
         double nn = rho * c.Yn / amu / (1.0 - chi);
-        double kn = pow(DS_R4(1.5) * (pi * pi) * nn, onethird) / cm_to_fm;
+        double kn = dsm::pow(DS_R4(1.5) * (pi * pi) * nn, onethird) / cm_to_fm;
         eps.pbf = pbf(kn, T, Tcn);
     }
     eps.total = eps.pair + eps.photo + eps.plasma + eps.brems + eps.pbf;

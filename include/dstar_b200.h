@@ -57,6 +57,13 @@ int dstar_eval_crust_eos(dstar_ctx* ctx, int n, const double* rho, const double*
                          int ncharged, const double* Zion, const double* Aion, const double* Yion,
                          const double* Tcs, const double* chi_in, const double* eos_ctrl, double* res,
                          int32_t* phase, double* chi_out, int32_t* ierr);
+/* same, with the optional `components` argument (dStar_eos_lib.f:260-296): components(7,4,n) =
+ * {P,E,S,F,Cv,dPdlnRho,dPdlnT} x {electron+exchange, ion, neutron, radiation} (dStar_eos_def.f:38-56) */
+int dstar_eval_crust_eos_components(dstar_ctx* ctx, int n, const double* rho, const double* T,
+                                    const double* ionic, int ncharged, const double* Zion, const double* Aion,
+                                    const double* Yion, const double* Tcs, const double* chi_in,
+                                    const double* eos_ctrl, double* res, int32_t* phase, double* chi_out,
+                                    int32_t* ierr, double* components);
 /* get_crust_neutrino_emissivity (neutrino/public/neutrino_lib.f:16): channels[5] = pair, photo, plasma,
  * brems, pbf; eps(6,n) = total, pair, photo, plasma, brems, pbf. */
 int dstar_crust_neutrino(dstar_ctx* ctx, int n, const double* rho, const double* T, const double* ionic,
@@ -162,6 +169,11 @@ int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, i
                        const double* Zion, const double* Aion, const double* Tc_cell, const double* Tc_face,
                        const dstar_micro_ctrl* ctrl, double* tab_lnT, double* tab_lnCp, double* tab_lnGamma,
                        double* tab_lnEnu, double* tab_lnK, double* rho_bar1, int32_t* status);
+
+/* ---- test support: one dsmath function on the device (fn = 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 sin,
+ * 5 cos, 6 sinh, 7 cosh, 8 atan); dsmath is the deterministic elementary-function layer that plays the
+ * role of MESA's math_lib for this implementation (dstar_b200/csrc/dsmath.cuh) ---- */
+int dstar_dsmath_eval(dstar_ctx* ctx, int fn, int n, const double* x, const double* y, double* out);
 
 /* ---- measurement helpers ---- */
 /* FP64 DFMA-chain throughput of the device in TFLOP/s (the FP64 roofline denominator) */

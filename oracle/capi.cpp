@@ -98,10 +98,20 @@ void dso_pcy97(double grav, double Plight, int n, const double* lgTb, double* lg
 
 // batched EOS: for k in [0,n): rho[k], T[k], ionic[11*k..], Yion[ncharged*k..], Tcs[3*k..];
 // chi_in[k] (<0 => default nuclear size); out res[15*k..], phase[k], chi_out[k]
+int dso_eval_crust_eos_c(int n, const double* rho, const double* T, const double* ionic, int ncharged,
+                       const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
+                       const double* chi_in, const double* eos_ctrl, double* res, int* phase,
+                       double* chi_out, double* comps);
 int dso_eval_crust_eos(int n, const double* rho, const double* T, const double* ionic, int ncharged,
                        const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
                        const double* chi_in, const double* eos_ctrl, double* res, int* phase,
                        double* chi_out) {
+    return dso_eval_crust_eos_c(n, rho, T, ionic, ncharged, Zion, Aion, Yion, Tcs, chi_in, eos_ctrl, res, phase, chi_out, nullptr);
+}
+int dso_eval_crust_eos_c(int n, const double* rho, const double* T, const double* ionic, int ncharged,
+                       const double* Zion, const double* Aion, const double* Yion, const double* Tcs,
+                       const double* chi_in, const double* eos_ctrl, double* res, int* phase,
+                       double* chi_out, double* comps) {
     if (!g_helm_loaded) return -100;
     EosControls rq;
     if (eos_ctrl) { rq.Gamma_melt = eos_ctrl[0]; rq.rsi_melt = eos_ctrl[1]; rq.Ythresh = eos_ctrl[2]; }
@@ -110,8 +120,14 @@ int dso_eval_crust_eos(int n, const double* rho, const double* T, const double* 
         Composition c = comp_from(ionic + 11 * k);
         double chi = chi_in ? chi_in[k] : use_default_nuclear_size;
         int ph = 0;
+        Thermo cm[4];
         int ierr = eval_crust_eos(g_helm, rq, rho[k], T[k], c, ncharged, Zion, Aion,
-                                  Yion + (size_t)ncharged * k, Tcs + 3 * k, res + 15 * k, ph, chi);
+                                  Yion + (size_t)ncharged * k, Tcs + 3 * k, res + 15 * k, ph, chi, comps ? cm : nullptr);
+        if (comps)
+            for (int q = 0; q < 4; ++q) {
+                double* o = comps + 28 * (size_t)k + 7 * q;  // P,E,S,F,Cv,dPdlnRho,dPdlnT
+                o[0] = cm[q].p; o[1] = cm[q].u; o[2] = cm[q].s; o[3] = cm[q].f; o[4] = cm[q].cv; o[5] = cm[q].dpr; o[6] = cm[q].dpt;
+            }
         phase[k] = ph;
         chi_out[k] = chi;
         if (ierr != 0) worst = ierr;
@@ -173,3 +189,20 @@ int dso_rodasp_test(int problem, double tend, double rtol, double atol, double h
 }
 
 }  // extern "C"
+
+// dsmath accuracy / bit-parity probes: fn = 0 exp, 1 log, 2 log10, 3 pow, 4 sin, 5 cos, 6 sinh, 7 cosh, 8 atan
+extern "C" void dso_dsmath(int fn, int n, const double* x, const double* y, double* out) {
+    for (int i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = dsm::exp(x[i]); break;
+            case 1: out[i] = dsm::log(x[i]); break;
+            case 2: out[i] = dsm::log10(x[i]); break;
+            case 3: out[i] = dsm::pow(x[i], y[i]); break;
+            case 4: out[i] = dsm::sin(x[i]); break;
+            case 5: out[i] = dsm::cos(x[i]); break;
+            case 6: out[i] = dsm::sinh(x[i]); break;
+            case 7: out[i] = dsm::cosh(x[i]); break;
+            default: out[i] = dsm::atan(x[i]); break;
+        }
+    }
+}

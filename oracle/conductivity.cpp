@@ -40,7 +40,7 @@ double hinit853(int n, OdeRhs f, void* ctx, double x, const double* y, double po
     double der12 = std::max(std::fabs(der2), std::sqrt(dnf));
     double h1;
     if (der12 <= 1.0e-15) h1 = std::max(1.0e-6, std::fabs(h) * 1.0e-3);
-    else h1 = std::pow(0.01 / der12, 1.0 / iord);
+    else h1 = dsm::pow(0.01 / der12, 1.0 / iord);
     h = std::min(std::min(100.0 * std::fabs(h), h1), hmax);
     return std::copysign(h, posneg);
 }
@@ -106,8 +106,8 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
         double deno = err + 0.01 * err2;
         if (deno <= 0.0) deno = 1.0;
         err = std::fabs(h) * err * std::sqrt(1.0 / (n * deno));
-        double fac11 = std::pow(err, expo1);
-        double fac = fac11 / std::pow(facold, beta);
+        double fac11 = dsm::pow(err, expo1);
+        double fac = fac11 / dsm::pow(facold, beta);
         fac = std::max(facc2, std::min(facc1, fac / safe));
         double hnew = h / fac;
         if (err <= 1.0) {
@@ -141,17 +141,17 @@ double ee_PCY(double ne, double T) {
     double yfac = std::sqrt(4.0 * finestructure / pi);
     double mec2 = Melectron * clight * clight;
     double eefac = 1.5 * (finestructure * finestructure) * mec2 / ipow(pi, 3) / hbar;
-    double befac = std::pow(finestructure / pi, 1.5);
-    double kF = std::pow(3.0 * (pi * pi) * ne, onethird);
+    double befac = dsm::pow(finestructure / pi, 1.5);
+    double kF = dsm::pow(3.0 * (pi * pi) * ne, onethird);
     double x = kF * hbar / Melectron / clight;
     double eF = std::sqrt(1.0 + x * x);
     double beta = x / eF;
     double b2 = beta * beta;
-    double be3 = befac / std::pow(beta, 1.5);
+    double be3 = befac / dsm::pow(beta, 1.5);
     double plasma_theta = boltzmann * T / mec2;
-    double y = yfac * std::pow(x, 1.5) / plasma_theta / std::sqrt(eF);
+    double y = yfac * dsm::pow(x, 1.5) / plasma_theta / std::sqrt(eF);
     double lJ = 1.0 + (R4(2.810) - R4(0.810) * b2) / y;
-    double llJ = std::log(lJ);
+    double llJ = dsm::log(lJ);
     double J0 = onethird / ipow(1.0 + R4(0.07414) * y, 3);
     double J1 = J0 * llJ + onesixth * ipow(pi, 5) * y / ipow(R4(13.91) + y, 4);
     double J2 = 1.0 + R4(0.4) * (3.0 + 1.0 / (x * x)) / (x * x);
@@ -163,7 +163,7 @@ double ee_PCY(double ne, double T) {
 double ee_SY06(double ne, double T) {
     double nu_pre = 36.0 * (finestructure * finestructure) * (hbar * hbar) * clight / pi / boltzmann / Melectron;
     double Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
-    double kF = std::pow(threepisquare * ne, onethird);
+    double kF = dsm::pow(threepisquare * ne, onethird);
     double xF = hbar * kF / Melectron / clight;
     double eF = std::sqrt(1.0 + xF * xF);
     double u = xF / eF;
@@ -174,18 +174,18 @@ double ee_SY06(double ne, double T) {
     double At = 20.0 + 450.0 * u3;
     double Ct1 = R4(0.05067) + R4(0.03216) * u2;
     double Ct2 = R4(0.0254) + R4(0.04127) * u4;
-    double Ct = At * std::exp(Ct1 / Ct2);
+    double Ct = At * dsm::exp(Ct1 / Ct2);
     double Alt = R4(12.2) + R4(25.2) * u3;
     double Blt = 1.0 - 0.75 * u;
     double Clt1 = R4(0.123636) + R4(0.016234) * u2;
     double Clt2 = R4(0.0762) + R4(0.05714) * u4;
-    double Clt = Alt * std::exp(Clt1 / Clt2);
+    double Clt = Alt * dsm::exp(Clt1 / Clt2);
     double Il = (1.0 / u) * (R4(0.1587) - R4(0.02538) / (1.0 + R4(0.0435) * theta)) *
-                std::log(1.0 + R4(128.56) / theta / (R4(37.1) + theta * (R4(10.83) + theta)));
+                dsm::log(1.0 + R4(128.56) / theta / (R4(37.1) + theta * (R4(10.83) + theta)));
     double It = u3 * (R4(2.404) / Ct + (Ct2 - R4(2.404) / Ct) / (1.0 + R4(0.1) * tu)) *
-                std::log(1.0 + Ct / tu / (At + tu));
-    double Ilt = u * (R4(18.52) * u2 / Clt + (Clt2 - R4(18.2) * u2 / Clt) / (1.0 + R4(0.1558) * std::pow(theta, Blt))) *
-                 std::log(1.0 + Clt / (Alt * theta + R4(10.83) * (tu * tu) + std::pow(tu, (double)(8.0f / 3.0f))));
+                dsm::log(1.0 + Ct / tu / (At + tu));
+    double Ilt = u * (R4(18.52) * u2 / Clt + (Clt2 - R4(18.2) * u2 / Clt) / (1.0 + R4(0.1558) * dsm::pow(theta, Blt))) *
+                 dsm::log(1.0 + Clt / (Alt * theta + R4(10.83) * (tu * tu) + dsm::pow(tu, (double)(8.0f / 3.0f))));
     double I = Il + It + Ilt;
     return nu_pre * ne * I / eF / T;
 }
@@ -194,7 +194,7 @@ double ee_SY06(double ne, double T) {
 double eone(double z) {
     const double a0 = R4(0.1397), a1 = R4(0.5772), a2 = R4(2.2757);
     double z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
-    return std::exp(-z4 / (z3 + a0)) * (std::log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
+    return dsm::exp(-z4 / (z3 + a0)) * (dsm::log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
 }
 
 // electron_conductivity.f:94-161
@@ -202,7 +202,7 @@ double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z
     (void)Ye;
     const double um1 = R4(2.8), um2 = R4(12.973);
     const double onesixth = (double)(1.0f / 6.0f), fourthird = 4.0 * onethird;
-    double sw_max = std::log(std::numeric_limits<double>::max());
+    double sw_max = dsm::log(std::numeric_limits<double>::max());
     double electroncompton = hbar / Melectron / clight;
     double eifac = fourthird * clight * (finestructure * finestructure) / electroncompton / pi;
     double kF2 = kF * kF;
@@ -213,33 +213,33 @@ double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z
     double Gamma = Gamma_e * Z53;
     double s = finestructure / pi / v;
     double kTF2 = 4.0 * s * kF2;
-    double eta02 = ipow(R4(0.19) / std::pow(Z, onesixth), 2);
-    double aei = std::pow((double)(4.0f / 9.0f) / pi, onethird) * kF;
+    double eta02 = ipow(R4(0.19) / dsm::pow(Z, onesixth), 2);
+    double aei = dsm::pow((double)(4.0f / 9.0f) / pi, onethird) * kF;
     double qD2 = 3.0 * Gamma_e * (aei * aei) * Z2 / Z;
     double beta = pi * finestructure * Z * v;
-    double qi2 = qD2 * (1.0 + R4(0.06) * Gamma) * std::exp(-std::sqrt(Gamma));
-    double qs2 = (qi2 + kTF2) * std::exp(-beta);
+    double qi2 = qD2 * (1.0 + R4(0.06) * Gamma) * dsm::exp(-std::sqrt(Gamma));
+    double qs2 = (qi2 + kTF2) * dsm::exp(-beta);
     (void)qs2;
     double Gs = eta / std::sqrt(eta * eta + eta02) * (1.0 + R4(0.122) * (beta * beta));
-    double Gk0 = 1.0 / std::pow(eta * eta + R4(0.0081), 1.5);
+    double Gk0 = 1.0 / dsm::pow(eta * eta + R4(0.0081), 1.5);
     double Gk1 = 1.0 + beta * ipow(v, 3);
     double GkZ = 1.0 - 1.0 / Z;
     double Gk = Gs + R4(0.0105) * GkZ * Gk1 * Gk0 * eta;
     double a0 = 4.0 * kF2 / qD2 / eta;
-    double D1 = std::exp(R4(-9.1) * eta);
-    double D = std::exp(-a0 * um1 * D1 * 0.25);
+    double D1 = dsm::exp(R4(-9.1) * eta);
+    double D = dsm::exp(-a0 * um1 * D1 * 0.25);
     double w1 = 1.0 + onethird * beta;
     double w = 4.0 * um2 * kF2 / qD2 * w1;
     double sw = s * w;
     double L1, L2;
     if (sw < sw_max) {
-        double fac = std::exp(sw) * (eone(sw) - eone(sw + w));
-        L1 = 0.5 * (std::log(1.0 + 1.0 / s) + (1.0 - std::exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
-        L2 = 0.5 * (1.0 - (1.0 - std::exp(-w)) / w +
-                    s * (s / (1.0 + s) * (1.0 - std::exp(-w)) - 2.0 * std::log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
+        double fac = dsm::exp(sw) * (eone(sw) - eone(sw + w));
+        L1 = 0.5 * (dsm::log(1.0 + 1.0 / s) + (1.0 - dsm::exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
+        L2 = 0.5 * (1.0 - (1.0 - dsm::exp(-w)) / w +
+                    s * (s / (1.0 + s) * (1.0 - dsm::exp(-w)) - 2.0 * dsm::log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
     } else {
-        L1 = 0.5 * (std::log((s + 1.0) / s) - 1.0 / (s + 1.0));
-        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * std::log((s + 1.0) / s);
+        L1 = 0.5 * (dsm::log((s + 1.0) / s) - 1.0 / (s + 1.0));
+        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * dsm::log((s + 1.0) / s);
     }
     double Lei = (Z2 / A) * (L1 - v2 * L2) * Gk * D;
     return eifac * eF * Lei * A / Z;
@@ -256,7 +256,7 @@ double eQ(double kF, double Z, double A, double Q) {
     double v2 = v * v;
     double s = finestructure / pi / v;
     double L1 = 1.0 + 4.0 * v2 * s;
-    double L = 0.5 * (L1 * std::log(1.0 + 1.0 / s) - v2 - 1.0 / (s + 1.0) - v2 * s / (1.0 + s));
+    double L = 0.5 * (L1 * dsm::log(1.0 + 1.0 / s) - v2 - 1.0 / (s + 1.0) - v2 * s / (1.0 + s));
     return fac * gamma * dZ2 * L * A / Z;
 }
 
@@ -269,14 +269,14 @@ double eQ_page(double kF, double Z, double A, double Q) {
     double gamma = std::sqrt(1.0 + x * x);
     double v = x / gamma;
     double qs = R4(0.048196) / std::sqrt(v);
-    double L = std::log(1.0 / qs) - 0.5 * (1 + v * v);
+    double L = dsm::log(1.0 / qs) - 0.5 * (1 + v * v);
     return fac * gamma * dZ2 * L * A / Z;
 }
 
 // ------------------------------------------------------- photon opacity
 // photon_conductivity.f:7-26
 double electron_scattering(double eta_e, double theta, double Ye) {
-    double xi = std::exp(R4(0.8168) * eta_e - R4(0.05522) * (eta_e * eta_e));
+    double xi = dsm::exp(R4(0.8168) * eta_e - R4(0.05522) * (eta_e * eta_e));
     double xi2 = xi * xi;
     double theta2 = theta * theta;
     double t1 = R4(1.129) + R4(0.2965) * xi - R4(0.005594) * xi2;
@@ -291,22 +291,22 @@ double freefree(double rho, double T, double eta_e, const Composition& c) {
     const double bfac = R4(0.753);
     double rY = rho * c.Ye;
     double T8 = T * 1.0e-8;
-    double T8_32 = std::pow(T8, 1.5);
+    double T8_32 = dsm::pow(T8, 1.5);
     double xx;
-    if (eta_e > std::log(std::numeric_limits<double>::max())) xx = eta_e;
-    else xx = std::log(1.0 + std::exp(eta_e));
+    if (eta_e > dsm::log(std::numeric_limits<double>::max())) xx = eta_e;
+    else xx = dsm::log(1.0 + dsm::exp(eta_e));
     double norm = 1.16 * 8.02e3 * xx * T8_32 / rY;
-    double x = std::pow(1.0 + xx, twothird);
+    double x = dsm::pow(1.0 + xx, twothird);
     double gam = std::sqrt(R4(1.58e-3) / T8) * c.Z;
     double sxpt = std::sqrt(x + 10.0);
     double sx = std::sqrt(x);
     double tpg = 2.0 * pi * gam;
-    double expnum = std::exp(-tpg / sxpt);
-    double expden = std::exp(-tpg / sx);
+    double expnum = dsm::exp(-tpg / sxpt);
+    double expden = dsm::exp(-tpg / sx);
     double elwert = (1.0 - expnum) / (1.0 - expden);
-    double relfactor = 1.0 + std::pow(T8 / R4(7.7), 1.5);
+    double relfactor = 1.0 + dsm::pow(T8 / R4(7.7), 1.5);
     double gff = norm * elwert * relfactor;
-    return bfac * (rY / 1.0e5) / std::pow(T8, 3.5) * gff * c.Z2 / c.A;
+    return bfac * (rY / 1.0e5) / dsm::pow(T8, 3.5) * gff * c.Z2 / c.A;
 }
 
 // photon_conductivity.f:80-108
@@ -318,7 +318,7 @@ double Rosseland_kappa(double rho, double T, double mu_e, const Composition& c) 
     double T6 = T * 1.0e-6;
     double T_Ry = T6 / 0.15789 / c.Z2;
     double f = kap_ff / (kap_ff + kap_th);
-    double A = 1.0 + (1.097 + 0.777 * T_Ry) / (1.0 + 0.536 * T_Ry) * std::pow(f, 0.617) * std::pow(1.0 - f, 0.77);
+    double A = 1.0 + (1.097 + 0.777 * T_Ry) / (1.0 + 0.536 * T_Ry) * dsm::pow(f, 0.617) * dsm::pow(1.0 - f, 0.77);
     return (kap_th + kap_ff) * A;
 }
 
@@ -329,23 +329,23 @@ struct SfacPar { double T, Z, A, Yn, kfn, R_a; };
 inline void sfac_common(double x, const SfacPar& p, double& ssig, double& dskappa, double& formfac) {
     double nn = ipow(p.kfn, 3) / threepisquare;
     double nion = nn / p.Yn * (1.0 - p.Yn) / p.A;
-    double aion = std::pow(3.0 / (4.0 * pi * nion), onethird);
+    double aion = dsm::pow(3.0 / (4.0 * pi * nion), onethird);
     double mion = (p.A - p.Z) * Mneutron + p.Z * Mproton;
-    double omegaP = std::pow(hbar * clight * 4. * pi * (p.Z * p.Z) * finestructure * nion / mion, (double)(1.f / 2.f));
+    double omegaP = dsm::pow(hbar * clight * 4. * pi * (p.Z * p.Z) * finestructure * nion / mion, (double)(1.f / 2.f));
     double eta = boltzmann * p.T / (hbar * omegaP);
     double Gamma = hbar * clight * (p.Z * p.Z) * finestructure / (boltzmann * p.T * aion);
     double a1 = ipow(x / p.R_a * aion, 2) / (3. * Gamma * eta);
     double um1 = R4(2.8);
     double um2 = 13.0;
-    double w = a1 * (um1 * std::exp(R4(-9.1) * eta) + 2. * eta * um2) / 4.;
+    double w = a1 * (um1 * dsm::exp(R4(-9.1) * eta) + 2. * eta * um2) / 4.;
     double w1 = a1 * um2 * (eta * eta) /
-                (2. * std::pow(eta * eta + ipow(um2 / 117., 2), (double)(1.f / 2.f)));
-    ssig = std::exp(-2. * (w - w1)) * (1.0 - std::exp(-2. * w1));
-    double dskappa2 = a1 * 91. * (eta * eta) * std::exp(-2. * w) / ipow(1. + R4(111.4) * (eta * eta), 2);
+                (2. * dsm::pow(eta * eta + ipow(um2 / 117., 2), (double)(1.f / 2.f)));
+    ssig = dsm::exp(-2. * (w - w1)) * (1.0 - dsm::exp(-2. * w1));
+    double dskappa2 = a1 * 91. * (eta * eta) * dsm::exp(-2. * w) / ipow(1. + R4(111.4) * (eta * eta), 2);
     double dskappa4 = a1 * R4(0.101) * ipow(eta, 4) /
-                      ((R4(0.06408) + eta * eta) * std::pow(R4(0.001377) + eta * eta, 1.5));
+                      ((R4(0.06408) + eta * eta) * dsm::pow(R4(0.001377) + eta * eta, 1.5));
     dskappa = dskappa2 + dskappa4;
-    formfac = std::fabs(3.0 * (std::sin(x) - x * std::cos(x)) / ipow(x, 3));
+    formfac = std::fabs(3.0 * (dsm::sin(x) - x * dsm::cos(x)) / ipow(x, 3));
 }
 void sfac_phonon(int, double x, const double*, double* dy, void* ctx) {
     const SfacPar& p = *static_cast<const SfacPar*>(ctx);
@@ -363,8 +363,8 @@ void sfac_impurity(int, double x, const double*, double* dy, void* ctx) {
 // neutron_conductivity.f:282-289
 double neutron_potential(double nn, double n_in) {
     const double twothird4 = (double)(2.0f / 3.0f);
-    return hbar * hbar * std::pow(threepisquare * n_in, twothird4) / 2.0 / Mneutron *
-           (1.0 - std::pow(nn / n_in, twothird4));
+    return hbar * hbar * dsm::pow(threepisquare * n_in, twothird4) / 2.0 / Mneutron *
+           (1.0 - dsm::pow(nn / n_in, twothird4));
 }
 
 // shared front of n_imp (:69-174) and n_phonon (:176-280)
@@ -372,14 +372,14 @@ double neutron_scattering(double nn, double nion, double temperature, const Comp
                           bool impurity, int& ierr) {
     const double twothird4 = (double)(2.0f / 3.0f);
     ierr = 0;
-    double kFn = std::pow(threepisquare * nn, onethird);
+    double kFn = dsm::pow(threepisquare * nn, onethird);
     double rtol = R4(1.0e-4), atol = R4(1.0e-5);
     double isospin = 1.0 - 2.0 * c.Z / c.A;
     double n_0 = R4(0.1740) / ipow(fm_to_cm, 3);
     double n_2 = R4(-0.0157) / ipow(fm_to_cm, 3);
     double n_l = n_0 + n_2 * (isospin * isospin);
     double n_in = n_l / 2.0 * (1.0 + R4(0.9208) * isospin);
-    double R_a = std::pow(3.0 * (c.A - c.Z) / 4.0 / pi / n_in, onethird);
+    double R_a = dsm::pow(3.0 * (c.A - c.Z) / 4.0 / pi / n_in, onethird);
     double y = 0.0;
     double kn_start = 1.0e-10;
     double kn_end = 2.0 * kFn * R_a;
@@ -392,8 +392,8 @@ double neutron_scattering(double nn, double nion, double temperature, const Comp
     double fac = (double)(4.0f / 27.0f) / pi / ipow(hbar, 3) / (clight * clight);
     double V = neutron_potential(nn, n_in);
     double mnstar = Mneutron;
-    double EFn = R4(15.1) * mev_to_ergs * std::pow(c.Yn, twothird4) *
-                     std::pow(nn * amu / c.Yn / R4(1.0E14), twothird4) * (2.0 * Mneutron / mnstar) +
+    double EFn = R4(15.1) * mev_to_ergs * dsm::pow(c.Yn, twothird4) *
+                     dsm::pow(nn * amu / c.Yn / R4(1.0E14), twothird4) * (2.0 * Mneutron / mnstar) +
                  Mneutron * (clight * clight);
     if (impurity) return fac * EFn * (nion / nn) * ipow(V * R_a, 2) * c.Q / (c.Z * c.Z) * Lambda;
     return fac * EFn * (nion / nn) * ipow(V * R_a, 2) * Lambda;
@@ -406,9 +406,9 @@ double sPh(double nn, double nion, double temperature, const Composition& c) {
     double etwo = finestructure * hbarc_n;
     double Mu_n = amu * clight2 * ergs_to_mev;
     double T = temperature * boltzmann * ergs_to_mev;
-    double ai = std::pow(3.0 / fourpi / nion, onethird);
-    double kFn = std::pow(threepisquare * nn, onethird);
-    double kFe = std::pow(threepisquare * nion * c.Z, onethird);
+    double ai = dsm::pow(3.0 / fourpi / nion, onethird);
+    double kFn = dsm::pow(threepisquare * nn, onethird);
+    double kFe = dsm::pow(threepisquare * nion * c.Z, onethird);
     double vs = hbarc_n * kFn / Mn_n / (double)std::sqrt(3.0f);
     double Cv = 2.0 * (pi * pi) * ipow(T, 3) / 15.0 / ipow(vs, 3);
     double omega_p = std::sqrt(fourpi * etwo * c.Z2 * nion / c.A / Mu_n);
@@ -417,9 +417,9 @@ double sPh(double nn, double nion, double temperature, const Composition& c) {
     double alpha = cs / vs;
     double anlt = anl / (1.0 + R4(0.4) * kFn * anl + 0.5 * 2.0 * anl * (kFn * kFn));
     double gmix = 2.0 * anlt * hbarc_n * std::sqrt(nion * kFn / c.A / (Mu_n * Mu_n));
-    double TUm = onethird * etwo * omega_p * std::pow(c.Z, onethird);
+    double TUm = onethird * etwo * omega_p * dsm::pow(c.Z, onethird);
     double omega = 3.0 * T / hbarc_n;
-    double fu = std::exp(-TUm / T);
+    double fu = dsm::exp(-TUm / T);
     double Llphn = 2.0 / pi / omega;
     double Llphu = 100.0 * ai;
     double Llph = 1.0 / (fu / Llphu + (1.0 - fu) / Llphn);
@@ -436,9 +436,9 @@ void conductivity(const CondControls& rq, double rho, double T, double chi, doub
     const double eQ_threshold = 1.0e-8, sf_reduction_threshold = 1.0e-10;
     const double tiny = std::numeric_limits<double>::min();
     kap = CondComponents{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double lgrho = std::log10(rho);
+    double lgrho = dsm::log10(rho);
     double ne = rho / amu * c.Ye;
-    double kF = std::pow(threepisquare * ne, onethird);
+    double kF = dsm::pow(threepisquare * ne, onethird);
     double xF = hbar * kF / Melectron / clight;
     double eF = std::sqrt(1.0 + xF * xF);
     double Gamma_e = Gamma / c.Z53;
@@ -470,8 +470,8 @@ void conductivity(const CondControls& rq, double rho, double T, double chi, doub
             if (T < Tns) {
                 double tau = T / Tns;
                 double v = std::sqrt(1.0 - tau) * (R4(1.456) - R4(0.157) / std::sqrt(tau) + R4(1.764) / tau);
-                R = std::pow(R4(0.4186) + std::sqrt((double)(1.007f * 1.007f) + ipow(R4(0.5010) * v, 2)), 2.5) *
-                    std::exp(R4(1.456) - std::sqrt((double)(1.456f * 1.456f) + v * v));
+                R = dsm::pow(R4(0.4186) + std::sqrt((double)(1.007f * 1.007f) + ipow(R4(0.5010) * v, 2)), 2.5) *
+                    dsm::exp(R4(1.456) - std::sqrt((double)(1.456f * 1.456f) + v * v));
                 if (R < sf_reduction_threshold) R = 0.0;
             }
             int ierr;

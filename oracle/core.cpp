@@ -61,11 +61,11 @@ void compute_composition_moments(int n, const double* Zs, const double* As, cons
     comp.A = 1.0 / sA;
     double sZ = 0, sZ53 = 0, sZ2 = 0, sZ73 = 0, sZ52 = 0, sZZ1 = 0, sZ2XoA2 = 0;
     for (int i = 0; i < nm; ++i) sZ += Ym[i] * Zm[i];
-    for (int i = 0; i < nm; ++i) sZ53 += Ym[i] * std::pow(Zm[i], fivethird);
+    for (int i = 0; i < nm; ++i) sZ53 += Ym[i] * dsm::pow(Zm[i], fivethird);
     for (int i = 0; i < nm; ++i) sZ2 += Ym[i] * (Zm[i] * Zm[i]);
-    for (int i = 0; i < nm; ++i) sZ73 += Ym[i] * std::pow(Zm[i], seventhird);
-    for (int i = 0; i < nm; ++i) sZ52 += Ym[i] * std::pow(Zm[i], 2.5);
-    for (int i = 0; i < nm; ++i) sZZ1 += Ym[i] * (Zm[i] * std::pow(Zm[i] + 1.0, 1.5));
+    for (int i = 0; i < nm; ++i) sZ73 += Ym[i] * dsm::pow(Zm[i], seventhird);
+    for (int i = 0; i < nm; ++i) sZ52 += Ym[i] * dsm::pow(Zm[i], 2.5);
+    for (int i = 0; i < nm; ++i) sZZ1 += Ym[i] * (Zm[i] * dsm::pow(Zm[i] + 1.0, 1.5));
     for (int i = 0; i < nm; ++i) sZ2XoA2 += Zm[i] * Zm[i] * Ym[i] / Am[i];
     comp.Z = sZ * comp.A;
     comp.Z53 = sZ53 * comp.A;
@@ -179,20 +179,20 @@ void pcy97_Teff(double grav, double Plight, int n, const double* lgTb, double* l
     double eta = Plight / 1.193e34;
     double g14 = grav * 1.0e-14;
     for (int i = 0; i < n; ++i) {
-        double Tb9 = std::pow(10.0, lgTb[i]) * 1.0e-9;
+        double Tb9 = dsm::pow(10.0, lgTb[i]) * 1.0e-9;
         double Tstar = std::sqrt(7.0 * Tb9 * std::sqrt(g14));
         double zeta = Tb9 - 1.0e-3 * Tstar;
-        double Te4Fe = g14 * (std::pow(R4(7.0) * zeta, 2.25) + std::pow(cst::onethird * zeta, 1.25));
+        double Te4Fe = g14 * (dsm::pow(R4(7.0) * zeta, 2.25) + dsm::pow(cst::onethird * zeta, 1.25));
         double Teff6_4;
         if (eta > 0) {
-            double Te4a = g14 * std::pow(18.1 * Tb9, 2.42);
-            double a = std::pow(Tb9, cst::fivethird) * (1.2 + std::pow(5.3e-6 / eta, 0.38));
+            double Te4a = g14 * dsm::pow(18.1 * Tb9, 2.42);
+            double a = dsm::pow(Tb9, cst::fivethird) * (1.2 + dsm::pow(5.3e-6 / eta, 0.38));
             Teff6_4 = (a * Te4Fe + Te4a) / (a + 1.0);
         } else {
             Teff6_4 = Te4Fe;
         }
-        lgTeff[i] = std::log10(1.0e6 * std::pow(Teff6_4, 0.25));
-        lgflux[i] = std::log10(cst::sigma_SB * Teff6_4 * 1.0e24);
+        lgTeff[i] = dsm::log10(1.0e6 * dsm::pow(Teff6_4, 0.25));
+        lgflux[i] = dsm::log10(cst::sigma_SB * Teff6_4 * 1.0e24);
     }
 }
 

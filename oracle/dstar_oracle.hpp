@@ -26,6 +26,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "dsmath.hpp"
+
 namespace dso {
 
 #ifndef DSO_REAL4_LITERALS
@@ -120,7 +122,7 @@ inline double ipow(double x, int n) {
     return r;
 }
 // MESA math_lib exp10: exp(x*ln10)
-inline double dexp10(double x) { return std::exp(x * cst::ln10); }
+inline double dexp10(double x) { return dsm::exp(x * cst::ln10); }
 
 // ------------------------------------------------------------- composition
 // nucchem/public/nucchem_def.f:23-35 (same field order)

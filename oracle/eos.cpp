@@ -14,7 +14,7 @@ using namespace cst;
 void lattice_properties(double rho, double T, const Composition& c, double& ne, double& rs,
                         double& Gamma_e, double& Gamma, double& ionQ) {
     ne = rho * c.Ye / amu;
-    rs = std::pow(3.0 / fourpi / ne, onethird) / a_Bohr;
+    rs = dsm::pow(3.0 / fourpi / ne, onethird) / a_Bohr;
     Gamma_e = 2.0 * Rydberg / boltzmann / T / rs;
     Gamma = Gamma_e * c.Z53;
     ionQ = std::sqrt(3.0 * (Gamma_e * Gamma_e) * Melectron / rs / amu * c.Z2XoA2 * c.A / c.Z);
@@ -28,22 +28,22 @@ double nuclear_volume_fraction(double rho, const Composition& c, double nuclear_
 // dStar_eos_lib.f:111-121
 double neutron_wavenumber(double rho, const Composition& c, double chi) {
     double n = rho * c.Yn / amu / (1.0 - chi);
-    return std::pow(threepisquare * n, onethird) / cm_to_fm;
+    return dsm::pow(threepisquare * n, onethird) / cm_to_fm;
 }
 
 // electron.f:53-250 -- Potekhin's electron exchange fit and derivatives
 void ee_exchange(double Gamma_e, double rs, Thermo& r) {
     // theta_fac = 2.0*(4.0/9.0/pi)**(2.0/3.0): 4.0/9.0 and 2.0/3.0 are REAL(4) operations
     static const double theta_fac =
-        2.0 * std::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
+        2.0 * dsm::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
     const double theta_low = R4(0.005);
     double theta = theta_fac * rs / Gamma_e;
     double sqth = std::sqrt(theta);
     double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta3 * theta;
     double t1, t2, t1_h, t2_h, t1_hh, t2_hh;
     if (theta > theta_low) {
-        double cht1 = std::cosh(1.0 / theta), sht1 = std::sinh(1.0 / theta);
-        double cht2 = std::cosh(1.0 / sqth), sht2 = std::sinh(1.0 / sqth);
+        double cht1 = dsm::cosh(1.0 / theta), sht1 = dsm::sinh(1.0 / theta);
+        double cht2 = dsm::cosh(1.0 / sqth), sht2 = dsm::sinh(1.0 / sqth);
         t1 = sht1 / cht1;
         t2 = sht2 / cht2;
         t1_h = -1.0 / ipow(theta * cht1, 2);
@@ -101,7 +101,7 @@ void ee_exchange(double Gamma_e, double rs, Thermo& r) {
     double e_hh = e_h * eh + e * (t1_hh / t1 - ipow(t1_h / t1, 2) + e0_hh / e0 - ipow(e0_h / e0, 2) -
                                   e1_hh / e1 + ipow(e1_h / e1, 2) - 1.0 / theta2);
 
-    double exp1th = std::exp(-1.0 / theta);
+    double exp1th = dsm::exp(-1.0 / theta);
     double c = (R4(0.872496) + R4(0.025248) * exp1th) * e;
     double c_h = R4(0.025248) * exp1th / theta2 * e + c * e_h / e;
     double c_hh = R4(0.025248) * exp1th / theta2 * (e_h + (1.0 - 2.0 * theta) / theta2 * e) +
@@ -147,7 +147,7 @@ void ee_exchange(double Gamma_e, double rs, Thermo& r) {
                     2.0 * ((d_h * b2 + d * b2_h + b3 * e_h + d_h * b2 + d * b2_h) * e_h + d * b2 * e_hh) / (e * e) +
                     6.0 * d * b2 * (e_h * e_h) / ipow(e, 3)) / e;
 
-    double s3 = c3 * std::log(r3);
+    double s3 = c3 * dsm::log(r3);
     double s3_h = s3 * c3_h / c3 + c3 * r3_h / r3;
     double s3_hh = (s3_h * c3_h + s3 * c3_hh) / c3 - s3 * ipow(c3_h / c3, 2) +
                    (c3_h * r3_h + c3 * r3_hh) / r3 - c3 * ipow(r3_h / r3, 2);
@@ -174,7 +174,7 @@ void ee_exchange(double Gamma_e, double rs, Thermo& r) {
     double s4b = d * b3 + b4 * b2;
     double s4b_h = d_h * b3 + d * b3_h + b4_h * b2 + b4 * b2_h;
     double s4b_hh = d_hh * b3 + 2.0 * d_h * b3_h + d * b3_hh + b4_hh * b2 + 2. * b4_h * b2_h + b4 * b2_hh;
-    double s4c = std::atan(c4 / discr) - std::atan(d / discr);
+    double s4c = dsm::atan(c4 / discr) - dsm::atan(d / discr);
     double up1 = c4_h * discr - c4 * di_h;
     double dn1 = discr * discr + c4 * c4;
     double up2 = d_h * discr - d * di_h;
@@ -219,19 +219,19 @@ namespace {
 // ion.f:178-285
 void ie_liquid(double Gamma_e, double rs, double Z, Thermo& r) {
     static const double s3 = (double)std::sqrt(3.0f);
-    static const double CTFfac = (double)(18.0f / 175.0f) * std::pow(12.0 / pi, 2.0 * onethird);
-    double Z13 = std::pow(Z, onethird);
-    double cDH = (Z / s3) * (std::pow(1.0 + Z, 1.5) - 1.0 - std::pow(Z, 1.5));
+    static const double CTFfac = (double)(18.0f / 175.0f) * dsm::pow(12.0 / pi, 2.0 * onethird);
+    double Z13 = dsm::pow(Z, onethird);
+    double cDH = (Z / s3) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
     double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + R4(0.2) / std::sqrt(Z13));
-    double xrs = finestructure * std::pow(9.0 * pi / 4.0, onethird);
+    double xrs = finestructure * dsm::pow(9.0 * pi / 4.0, onethird);
     double xr = xrs / rs;
-    double lZ = std::log(Z);
+    double lZ = dsm::log(Z);
 
-    double a = R4(1.11) * std::pow(Z, R4(0.475));
+    double a = R4(1.11) * dsm::pow(Z, R4(0.475));
     double b = R4(0.2) + R4(0.078) * (lZ * lZ);
     double nu = R4(1.16) + R4(0.08) * lZ;
     double sGam = std::sqrt(Gamma_e);
-    double nuGam = std::pow(Gamma_e, nu);
+    double nuGam = dsm::pow(Gamma_e, nu);
     double nuGam_g = nu * nuGam / Gamma_e;
     double nuGam_gg = (nu - 1.0) * nuGam_g / Gamma_e;
     double ty1 = 1.0 / (R4(0.001) * (Z * Z) + 2.0 * Gamma_e);
@@ -270,7 +270,7 @@ void ie_liquid(double Gamma_e, double rs, double Z, Thermo& r) {
     double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / (d0 * d0)) / d0;
 
     double rgam = std::sqrt(1.0 + xr * xr);
-    double q1 = R4(0.18) / std::pow(Z, 0.25);
+    double q1 = R4(0.18) / dsm::pow(Z, 0.25);
     double q2 = R4(0.2) + R4(0.37) / std::sqrt(Z);
     double h1u = 1.0 + R4(0.2) * (xr * xr);
     double h1d = 1.0 + q1 * xr + q2 * (xr * xr);
@@ -321,20 +321,20 @@ void ie_liquid(double Gamma_e, double rs, double Z, Thermo& r) {
 void ie_lattice(double Gamma, double theta, double rs, double Z, Thermo& r) {
     const double a[4] = {R4(1.1866), R4(0.684), R4(17.9), R4(41.5)};
     const double px = R4(0.205);
-    double e1 = std::exp(1.0);
-    double aTF = (double)(54.0f / 175.0f) * std::pow(12.0 / pi, onethird) * finestructure;
-    double xrs = finestructure * std::pow(9.0 * pi / 4.0, onethird);
+    double e1 = dsm::exp(1.0);
+    double aTF = (double)(54.0f / 175.0f) * dsm::pow(12.0 / pi, onethird) * finestructure;
+    double xrs = finestructure * dsm::pow(9.0 * pi / 4.0, onethird);
     double xr = xrs / rs;
-    double lZ = std::log(Z);
-    double r3 = 1.0 / (1.0 + R4(0.01) * std::pow(lZ, 1.5) + R4(0.097) / (Z * Z));
+    double lZ = dsm::log(Z);
+    double r3 = 1.0 / (1.0 + R4(0.01) * dsm::pow(lZ, 1.5) + R4(0.097) / (Z * Z));
     double b[4];
-    b[0] = 1.0 - a[0] / std::pow(Z, R4(0.267)) + R4(0.27) / Z;
-    b[1] = 1.0 + 2.25 / std::pow(Z, onethird) * (1.0 + a[1] * ipow(Z, 5) + R4(0.222) * ipow(Z, 6)) /
+    b[0] = 1.0 - a[0] / dsm::pow(Z, R4(0.267)) + R4(0.27) / Z;
+    b[1] = 1.0 + 2.25 / dsm::pow(Z, onethird) * (1.0 + a[1] * ipow(Z, 5) + R4(0.222) * ipow(Z, 6)) /
                      (1.0 + R4(0.222) * ipow(Z, 6));
     b[2] = a[3] / (1.0 + lZ);
-    b[3] = R4(0.395) * lZ + R4(0.347) / std::pow(Z, 1.5);
+    b[3] = R4(0.395) * lZ + R4(0.347) / dsm::pow(Z, 1.5);
 
-    double finf = aTF * std::pow(Z, twothird) * b[0] * std::sqrt(1.0 + b[1] / (xr * xr));
+    double finf = aTF * dsm::pow(Z, twothird) * b[0] * std::sqrt(1.0 + b[1] / (xr * xr));
     double finfx = -b[1] / ((b[1] + xr * xr) * xr);
     double finf_x = finf * finfx;
     double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / ((b[1] + xr * xr) * xr);
@@ -355,14 +355,14 @@ void ie_lattice(double Gamma, double theta, double rs, double Z, Thermo& r) {
         double y0_xx = 0.0;
         double y0_gg = y0_g / Gamma;
         double y0_xg = y0_g / xr;
-        double y1 = std::exp(y0);
+        double y1 = dsm::exp(y0);
         double y1_x = y1 * y0_x;
         double y1_g = y1 * y0_g;
         double y1_xx = y1 * (y0_x * y0_x + y0_xx);
         double y1_gg = y1 * (y0_g * y0_g + y0_gg);
         double y1_xg = y1 * (y0_x * y0_g + y0_xg);
         double sa = 1.0 + y1;
-        double supa = std::log(sa);
+        double supa = dsm::log(sa);
         double supa_x = y1_x / sa;
         double supa_g = y1_g / sa;
         double supa_xx = (y1_xx - y1_x * y1_x / sa) / sa;
@@ -370,7 +370,7 @@ void ie_lattice(double Gamma, double theta, double rs, double Z, Thermo& r) {
         double supa_xg = (y1_xg - y1_x * y1_g / sa) / sa;
         double em2 = e1 - 2.0;
         double sb = e1 - em2 / y1;
-        double supb = std::log(sb);
+        double supb = dsm::log(sb);
         double em2y1 = em2 / ((y1 * y1) * sb);
         double supb_x = em2y1 * y1_x;
         double supb_g = em2y1 * y1_g;
@@ -396,7 +396,7 @@ void ie_lattice(double Gamma, double theta, double rs, double Z, Thermo& r) {
         sup_gg = 0.0;
         sup_xg = sup_x / Gamma;
     }
-    double gr3 = std::pow(Gamma / sup, r3);
+    double gr3 = dsm::pow(Gamma / sup, r3);
     double gr3x = -r3 * sup_x / sup;
     double gr3_x = gr3 * gr3x;
     double gr3_xx = gr3_x * gr3x - r3 * gr3 * (sup_xx / sup - ipow(sup_x / sup, 2));
@@ -436,20 +436,20 @@ void ii_liquid(double Gamma, double theta, Thermo& r) {
     const double B1 = R4(4.50e-3), B2 = R4(170.0), B3 = R4(-8.4e-5), B4 = R4(3.70e-3);
 
     double f0 = A1 * (std::sqrt(Gamma * (A2 + Gamma)) -
-                      A2 * std::log(std::sqrt(Gamma / A2) + std::sqrt(1.0 + Gamma / A2))) +
-                2.0 * A3 * (std::sqrt(Gamma) - std::atan(std::sqrt(Gamma)));
+                      A2 * dsm::log(std::sqrt(Gamma / A2) + std::sqrt(1.0 + Gamma / A2))) +
+                2.0 * A3 * (std::sqrt(Gamma) - dsm::atan(std::sqrt(Gamma)));
     double G2 = Gamma * Gamma;
-    double G15 = std::pow(Gamma, 1.5);
-    double f = f0 + B1 * (Gamma - B2 * std::log(1.0 + Gamma / B2)) + 0.5 * B3 * std::log(1.0 + G2 / B4);
+    double G15 = dsm::pow(Gamma, 1.5);
+    double f = f0 + B1 * (Gamma - B2 * dsm::log(1.0 + Gamma / B2)) + 0.5 * B3 * dsm::log(1.0 + G2 / B4);
     double u = G15 * (A1 / std::sqrt(A2 + Gamma) + A3 / (1.0 + Gamma)) +
                G2 * (B1 / (B2 + Gamma) + B3 / (B4 + G2));
-    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / ipow(Gamma + 1.0, 2) - A1 * A2 / std::pow(Gamma + A2, 1.5)) +
+    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / ipow(Gamma + 1.0, 2) - A1 * A2 / dsm::pow(Gamma + A2, 1.5)) +
                 G2 * (B3 * (G2 - B4) / ipow(G2 + B4, 2) - B1 * B2 / ipow(Gamma + B2, 2));
     double p = onethird * u;
     double dpr = (4.0 * u - cv) / 9.0;
     double dpt = onethird * cv;
 
-    double fid = 3.0 * std::log(theta) - 1.5 * std::log(Gamma) - 0.5 * std::log(6.0 / pi) - 1.0;
+    double fid = 3.0 * dsm::log(theta) - 1.5 * dsm::log(Gamma) - 0.5 * dsm::log(6.0 / pi) - 1.0;
     f = f + fid;
     u = u + 1.5;
     p = p + 1.0;
@@ -489,7 +489,7 @@ void ii_lattice(double Gamma, double theta, Thermo& tot) {
         fh = -uh / 3.0;
         cvh = 4.0 * uh;
     } else if (theta < theta_low) {
-        fh = 3.0 * std::log(theta) + clm - 1.5 * w * theta + theta * theta / 24.0;
+        fh = 3.0 * dsm::log(theta) + clm - 1.5 * w * theta + theta * theta / 24.0;
         uh = 3.0 - 1.5 * w * theta + theta * theta / 12.0;
         cvh = 3.0 - theta * theta / 12.0;
     } else {
@@ -512,9 +512,9 @@ void ii_lattice(double Gamma, double theta, Thermo& tot) {
         Bc[1] = Bc[1] + 9.0 * alpha[6] * a[6] * ipow(theta, 8) + 11.0 * alpha[8] * a[8] * ipow(theta, 10);
         Bc[2] = Bc[2] + 72.0 * alpha[6] * a[6] * ipow(theta, 7) + 110.0 * alpha[8] * a[8] * ipow(theta, 9);
         for (int n = 1; n <= 3; ++n) {
-            double ea = std::exp(-alpha[n] * theta);
+            double ea = dsm::exp(-alpha[n] * theta);
             double omea = 1.0 - ea;
-            fh = fh + std::log(omea);
+            fh = fh + dsm::log(omea);
             uh = uh + alpha[n] * ea / omea;
             cvh = cvh + alpha[n] * alpha[n] * ea / (omea * omea);
         }
@@ -537,7 +537,7 @@ void ii_lattice(double Gamma, double theta, Thermo& tot) {
     double theta2 = theta * theta;
     double theta4 = ipow(theta, 4);
     double c1t2 = c1 * theta2;
-    double sup = std::exp(-c1t2);
+    double sup = dsm::exp(-c1t2);
     double tq = b1 * theta2 / Gamma;
     double gninv = sup;
     for (int n = 1; n <= 3; ++n) {
@@ -570,8 +570,8 @@ void ii_lattice(double Gamma, double theta, Thermo& tot) {
 // ion.f:135-176
 void one_ion(double Gamma_e, double rs, double Z, double A, int phase, Thermo& r) {
     static const double sevensixth = (double)(7.0f / 6.0f);
-    double Gamma = Gamma_e * std::pow(Z, fivethird);
-    double theta = Gamma * std::sqrt(3.0 * Melectron / A / amu / rs) / std::pow(Z, sevensixth);
+    double Gamma = Gamma_e * dsm::pow(Z, fivethird);
+    double theta = Gamma * std::sqrt(3.0 * Melectron / A / amu / rs) / dsm::pow(Z, sevensixth);
     Thermo ie, ii;
     if (phase == liquid_phase) {
         ie_liquid(Gamma_e, rs, Z, ie);
@@ -596,14 +596,14 @@ void LM_corrections(double rs, double Gamma_e, const Composition& c, Thermo& r) 
     double D = c.Z2 / (c.Z * c.Z);
     r = Thermo{0, 0, 0, 0, 0, 0, 0};
     if (std::fabs(D - 1.0) < threshold) return;
-    double p3 = std::pow(D, R4(-0.2));
+    double p3 = dsm::pow(D, R4(-0.2));
     double d0 = (R4(2.6) * difR + 14.0 * ipow(difR, 3)) / (1.0 - p3);
-    double gp = d0 * std::pow(Gamma, p3);
+    double gp = d0 * dsm::pow(Gamma, p3);
     double f0 = difFDH / (1.0 + gp);
     double q = (D * D) * R4(0.0117);
     double rr = 1.5 / p3 - 1.0;
     double gq = q * gp;
-    double f = f0 / std::pow(1.0 + gq, rr);
+    double f = f0 / dsm::pow(1.0 + gq, rr);
     double g = 1.5 - p3 * gp / (1.0 + gp) - rr * p3 * gq / (1.0 + gq);
     double u = f * g;
     double s = u - f;
@@ -637,7 +637,7 @@ int ion_mixture(const EosControls& rq, double rs, double Gamma_e, const Composit
             one_ion(Gamma_e, rs, Zion[i], Aion[i], phase, t);
             f = f + Yion[i] * t.f;
             u = u + Yion[i] * t.u;
-            s = s + Yion[i] * (t.s - std::log(Yion[i]));
+            s = s + Yion[i] * (t.s - dsm::log(Yion[i]));
             p = p + Yion[i] * t.p;
             cv = cv + Yion[i] * t.cv;
             dpr = dpr + Yion[i] * t.dpr;
@@ -669,24 +669,24 @@ inline double ratfit(const double* a, int m, const double* b, int k, double xx) 
 }
 }  // namespace
 double zfermim12(double x) {  // funct_fermi1.f:21-86
-    if (x < 2.0) { double xx = std::exp(x); return xx * ratfit(zfermim12_a1, 7, zfermim12_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermim12_a1, 7, zfermim12_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return std::sqrt(x) * ratfit(zfermim12_a2, 11, zfermim12_b2, 11, xx);
 }
 double zfermi12(double x) {  // :88-146
-    if (x < 2.0) { double xx = std::exp(x); return xx * ratfit(zfermi12_a1, 7, zfermi12_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermi12_a1, 7, zfermi12_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return x * std::sqrt(x) * ratfit(zfermi12_a2, 10, zfermi12_b2, 11, xx);
 }
 double zfermi32(double x) {  // :216-276
-    if (x < 2.0) { double xx = std::exp(x); return xx * ratfit(zfermi32_a1, 6, zfermi32_b1, 7, xx); }
+    if (x < 2.0) { double xx = dsm::exp(x); return xx * ratfit(zfermi32_a1, 6, zfermi32_b1, 7, xx); }
     double xx = 1.0 / (x * x);
     return x * x * std::sqrt(x) * ratfit(zfermi32_a2, 9, zfermi32_b2, 10, xx);
 }
 double ifermi12(double f) {  // :528-580
     const double an = 0.5;
-    if (f < 4.0) return std::log(f * ratfit(ifermi12_a1, 4, ifermi12_b1, 3, f));
-    double ff = 1.0 / std::pow(f, 1.0 / (1.0 + an));
+    if (f < 4.0) return dsm::log(f * ratfit(ifermi12_a1, 4, ifermi12_b1, 3, f));
+    double ff = 1.0 / dsm::pow(f, 1.0 / (1.0 + an));
     double rn = ff + ifermi12_a2[5];
     for (int i = 4; i >= 0; --i) rn = rn * ff + ifermi12_a2[i];
     double den = ifermi12_b2[5];
@@ -699,7 +699,7 @@ void MB77(double n, double T, double Tns, Thermo& r) {
     const double c[4] = {R4(1.2974), R4(15.0298), R4(-15.2343), R4(7.4663)};
     r = Thermo{0, 0, 0, 0, 0, 0, 0};
     if (n == 0.0) return;
-    double k = std::pow(0.5 * threepisquare * n, onethird) / cm_to_fm;
+    double k = dsm::pow(0.5 * threepisquare * n, onethird) / cm_to_fm;
     double dkdn = onethird * k / n;
     double u = k * (c[0] + k * (c[1] + k * (c[2] + k * c[3])));
     u = u * mev_to_ergs;
@@ -709,7 +709,7 @@ void MB77(double n, double T, double Tns, Thermo& r) {
     double dpr = (p / n + dpdk * dkdn) * n;
     double dpT = 0.0;
 
-    double lambda3 = pi * pi * std::pow(hbar * hbar / (Mneutron * boltzmann * T), 1.5) / (double)std::sqrt(2.0f);
+    double lambda3 = pi * pi * dsm::pow(hbar * hbar / (Mneutron * boltzmann * T), 1.5) / (double)std::sqrt(2.0f);
     double zeta = ifermi12(n * lambda3);
     double cv = 2.5 * zfermi32(zeta) / zfermi12(zeta) - 4.5 * zfermi12(zeta) / zfermim12(zeta);
     cv = cv * boltzmann;
@@ -719,8 +719,8 @@ void MB77(double n, double T, double Tns, Thermo& r) {
     if (T < Tns) {
         double tau = T / Tns;
         double v = std::sqrt(1.0 - tau) * (R4(1.456) - R4(0.157) / std::sqrt(tau) + R4(1.764) / tau);
-        R = std::pow(R4(0.4186) + std::sqrt((double)(1.007f * 1.007f) + ipow(R4(0.5010) * v, 2)), 2.5) *
-            std::exp(R4(1.456) - std::sqrt((double)(1.456f * 1.456f) + v * v));
+        R = dsm::pow(R4(0.4186) + std::sqrt((double)(1.007f * 1.007f) + ipow(R4(0.5010) * v, 2)), 2.5) *
+            dsm::exp(R4(1.456) - std::sqrt((double)(1.456f * 1.456f) + v * v));
     } else {
         R = 1.0;
     }
@@ -793,9 +793,9 @@ int eval_crust_eos(const HelmTable& h, const EosControls& rq, double rho, double
     if (c.Yn < rq.Ythresh) mu_n = 0.0;
     else mu_n = (nt.u - T * nt.s + nt.p / nn) * ergs_to_mev;
 
-    res[i_lnP] = std::log(p);
-    res[i_lnE] = std::log(u);
-    res[i_lnS] = std::log(s);
+    res[i_lnP] = dsm::log(p);
+    res[i_lnE] = dsm::log(u);
+    res[i_lnS] = dsm::log(s);
     res[i_grad_ad] = grad_ad;
     res[i_chiRho] = dpr / p;
     res[i_chiT] = dpt / p;

@@ -13,10 +13,10 @@ void helm_setup(HelmTable& h, int imax, int jmax, const double* const a[21]) {
     h.imax = imax;
     h.jmax = jmax;
     h.logtlo = 3.0; h.logthi = 13.0; h.logdlo = -12.0; h.logdhi = 14.0;  // helm_alloc.f:150-153
-    h.templo = std::pow(10.0, h.logtlo);
-    h.temphi = std::pow(10.0, h.logthi);
-    h.denlo = std::pow(10.0, h.logdlo);
-    h.denhi = std::pow(10.0, h.logdhi);
+    h.templo = 1.0e3;
+    h.temphi = 1.0e13;
+    h.denlo = 1.0e-12;
+    h.denhi = 1.0e14;
     h.logtstp = (h.logthi - h.logtlo) / (double)(float)(jmax - 1);
     h.logtstpi = 1.0 / h.logtstp;
     h.logdstp = (h.logdhi - h.logdlo) / (double)(float)(imax - 1);
@@ -107,7 +107,7 @@ int helmeos2_electron(const HelmTable& h, double T, double logT, double Rho, dou
     double ye = ytot1 * zbar;
     double din = ye * den;
     // helm_core.f:345-371 clipping
-    if (temp < h.templo) { temp = h.templo; logtemp = std::log10(temp); }
+    if (temp < h.templo) { temp = h.templo; logtemp = dsm::log10(temp); }
     if (din < h.denlo) return -3;  // would switch to skip_elec_pos
     if (temp > h.temphi) { temp = h.temphi; logtemp = h.logthi; }
     if (din > h.denhi) din = h.denhi;
@@ -118,7 +118,7 @@ int helmeos2_electron(const HelmTable& h, double T, double logT, double Rho, dou
     // :21-24 hash locate (1-based in source; here 0-based)
     int jat = (int)((logtemp - h.logtlo) * h.logtstpi) + 1;
     jat = std::max(1, std::min(jat, h.jmax - 1));
-    int iat = (int)((std::log10(din) - h.logdlo) * h.logdstpi) + 1;
+    int iat = (int)((dsm::log10(din) - h.logdlo) * h.logdstpi) + 1;
     iat = std::max(1, std::min(iat, h.imax - 1));
     int j0 = jat - 1, i0 = iat - 1;
     const int im = h.imax;
@@ -222,7 +222,7 @@ int get_helm_eos_results(const HelmTable& h, double rho, double T, const Composi
     if (std::fabs(c.Yn - 1.0) <= (double)1.1920929e-07f) return 0;
     double abar = c.A / (1.0 - c.Yn);
     double zbar = c.Z;
-    double logT = std::log10(T), logRho = std::log10(rho);
+    double logT = dsm::log10(T), logRho = dsm::log10(rho);
     HelmElectron he;
     int ierr = helmeos2_electron(h, T, logT, rho, logRho, abar, zbar, he);
     if (ierr != 0) return ierr;

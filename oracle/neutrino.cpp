@@ -23,7 +23,7 @@ const double cn_cap = 1.0 - cn_ca;
 // :56-102
 double plasma(double t, double r) {
     const double cvd = cn_cv * cn_cv + cn_dn * (cn_cvp * cn_cvp);
-    double rdouble = std::log10(2.0 * r);
+    double rdouble = dsm::log10(2.0 * r);
     double x = (17.5 + rdouble - 3.0 * t) / 6.0;
     double y = (-24.5 + rdouble + 3.0 * t) / 6.0;
     double enum_ = std::min(0.0, y - 1.6 + 1.25 * x);
@@ -31,17 +31,17 @@ double plasma(double t, double r) {
     if (std::fabs(x) > 0.7 || y < 0.0) {
         fxy = 1.0;
     } else {
-        fxy = 1.05 + (0.39 - 1.25 * x - 0.35 * std::sin(4.5 * x) - 0.3 * std::exp(-ipow(4.5 * x + 0.9, 2))) *
-                         std::exp(-ipow(enum_ / (0.57 - 0.25 * x), 2));
+        fxy = 1.05 + (0.39 - 1.25 * x - 0.35 * dsm::sin(4.5 * x) - 0.3 * dsm::exp(-ipow(4.5 * x + 0.9, 2))) *
+                         dsm::exp(-ipow(enum_ / (0.57 - 0.25 * x), 2));
     }
     double lamb = 1.686e-10 * t;
-    double gamd = 1.1095e11 * r / ((t * t) * std::sqrt(1.0 + std::pow(1.019e-6 * r, two_thirds)));
+    double gamd = 1.1095e11 * r / ((t * t) * std::sqrt(1.0 + dsm::pow(1.019e-6 * r, two_thirds)));
     double gam = std::sqrt(gamd);
-    double ft = 2.4 + 0.6 * std::sqrt(gam) + 0.51 * gam + 1.25 * std::pow(gam, 1.5);
-    double fl = (8.6 * gamd + 1.35 * std::pow(gam, 7.0 / 2.0)) / (225.0 - 17.0 * gam + gamd);
+    double ft = 2.4 + 0.6 * std::sqrt(gam) + 0.51 * gam + 1.25 * dsm::pow(gam, 1.5);
+    double fl = (8.6 * gamd + 1.35 * dsm::pow(gam, 7.0 / 2.0)) / (225.0 - 17.0 * gam + gamd);
     double qap;
     if (std::fabs(std::sqrt(gamd)) > 700.0) qap = 0.0;
-    else qap = fxy * (fl + ft) * std::exp(-gam) * ipow(gamd, 3) * ipow(lamb, 9) * 3.0e21;
+    else qap = fxy * (fl + ft) * dsm::exp(-gam) * ipow(gamd, 3) * ipow(lamb, 9) * 3.0e21;
     return qap * cvd;
 }
 
@@ -53,21 +53,21 @@ double pair(double temp, double rhom) {
     const double coep = (cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap);
     const double coem = (cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap);
     double lam = temp / 5.9302e9;
-    double xi = std::pow(rhom * 1.0e-9, onethird) / lam;
+    double xi = dsm::pow(rhom * 1.0e-9, onethird) / lam;
     double qp1 = 10.74800 * (lam * lam) + 0.3967 * std::sqrt(lam) + 1.005;
     double qp2 = rhom / (7.692e7 * ipow(lam, 3) + 9.715e6 * std::sqrt(lam));
-    double qp = (1.0 / qp1) * std::pow(1.0 + qp2, -0.3);
+    double qp = (1.0 / qp1) * dsm::pow(1.0 + qp2, -0.3);
     double axi = a0 + a1 * xi + a2 * (xi * xi);
     double fp1, fp2;
     if (xi > 100.0) fp1 = 0.0;
-    else if (temp < 1.0e10) fp1 = axi * std::exp(-c * xi);
-    else fp1 = axi * std::exp(-ch * xi);
+    else if (temp < 1.0e10) fp1 = axi * dsm::exp(-c * xi);
+    else fp1 = axi * dsm::exp(-ch * xi);
     if (temp < 1.0e10) fp2 = ipow(xi, 3) + b1 / lam + b2 / (lam * lam) + b3 / ipow(lam, 3);
     else fp2 = ipow(xi, 3) + bh1 / lam + bh2 / (lam * lam) + bh3 / ipow(lam, 3);
     double fp = fp1 / fp2;
     double g = 1.0 - 13.04 * (lam * lam) + 133.5 * ipow(lam, 4) + 1534.0 * ipow(lam, 6) + 918.6 * ipow(lam, 8);
     if (lam < 7.0e-3) return 0.0;
-    return 0.5 * coep * (1.0 + coem / coep * qp) * g * std::exp(-2.0 / lam) * fp;
+    return 0.5 * coep * (1.0 + coem / coep * qp) * g * dsm::exp(-2.0 / lam) * fp;
 }
 
 #include "cfp_coef.inc"
@@ -78,19 +78,19 @@ double cfp(double lamb, double xi) {
     int band;
     double c, tau;
     if (temp < 1.0e7) return 0.0;
-    else if (temp < 1.0e8) { band = 0; c = 0.5654 + std::log10(temp / 1.0e7); tau = std::log10(temp / 1.0e7); }
-    else if (temp < 1.0e9) { band = 1; c = 1.5654; tau = std::log10(temp / 1.0e8); }
-    else { band = 2; c = 1.5654; tau = std::log10(temp / 1.0e9); }
+    else if (temp < 1.0e8) { band = 0; c = 0.5654 + dsm::log10(temp / 1.0e7); tau = dsm::log10(temp / 1.0e7); }
+    else if (temp < 1.0e9) { band = 1; c = 1.5654; tau = dsm::log10(temp / 1.0e8); }
+    else { band = 2; c = 1.5654; tau = dsm::log10(temp / 1.0e9); }
     double a[3];
     for (int j = 0; j < 3; ++j) {
-        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * std::cos(10.0 * pi * tau);
+        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * dsm::cos(10.0 * pi * tau);
         for (int k = 1; k <= 5; ++k) {
             double pjt = pi * (double)k * tau;
-            a[j] = a[j] + cfp_cc[band][j][k] * std::cos(5.0 / 3.0 * pjt) +
-                   cfp_dd[band][j][k - 1] * std::sin(5.0 / 3.0 * pjt);
+            a[j] = a[j] + cfp_cc[band][j][k] * dsm::cos(5.0 / 3.0 * pjt) +
+                   cfp_dd[band][j][k - 1] * dsm::sin(5.0 / 3.0 * pjt);
         }
     }
-    return (a[0] + a[1] * xi + a[2] * (xi * xi)) * std::exp(-c * xi) /
+    return (a[0] + a[1] * xi + a[2] * (xi * xi)) * dsm::exp(-c * xi) /
            (ipow(xi, 3) + b[0] / lamb + b[1] / (lamb * lamb) + b[2] / ipow(lamb, 3));
 }
 
@@ -100,8 +100,8 @@ double photo(double rhom, double lamb) {
     const double coe2 = ((cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap)) /
                         ((cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap));
     double poly = 1.875e8 * lamb + 1.653e8 * (lamb * lamb) + 8.499e8 * ipow(lamb, 3) - 1.604e8 * ipow(lamb, 4);
-    double qp = 0.666 * std::pow(1.0 + 2.045 * lamb, -2.066) * (1.0 / (1.0 + rhom * (1.0 / poly)));
-    double xi = std::pow(rhom * 1.e-9, onethird) / lamb;
+    double qp = 0.666 * dsm::pow(1.0 + 2.045 * lamb, -2.066) * (1.0 / (1.0 + rhom * (1.0 / poly)));
+    double xi = dsm::pow(rhom * 1.e-9, onethird) / lamb;
     double fp = cfp(lamb, xi);
     return coe1 * (1.0 - coe2 * qp) * rhom * ipow(lamb, 5) * fp;
 }
@@ -118,7 +118,7 @@ double pbf(double kF, double T, double Tns) {
     double v2 = v * v;
     double F1 = v2 * (0.602 + v2 * (0.5942 + 0.288 * v2));
     double F2 = std::sqrt(R4(0.5547) + std::sqrt(0.4453 * 0.4453 + 0.01130 * v2));
-    double F3 = std::exp(-std::sqrt(4.0 * v2 + 2.245 * 2.245) + 2.245);
+    double F3 = dsm::exp(-std::sqrt(4.0 * v2 + 2.245 * 2.245) + 2.245);
     double F = F1 * F2 * F3;
     double reduct = ipow(xF / eF, 2);
     return qpbf_pre * (cn_dn + 1) * mstar * xF * ipow(T / 1.0e9, 7) * F * reduct;
@@ -129,15 +129,15 @@ double bremsstrahlung(double rho, double T, const Composition& c) {
     const double threefourth = 3.0 / 4.0, GF = 1.436e-49, Cp2 = 1.675;
     double qbrems_pre = 8.0 * pi * (GF * GF) * (finestructure * finestructure) * Cp2 *
                         ipow(boltzmann / hbar / clight, 6) / 567.0 / hbar / amu;
-    double re = std::pow(threefourth / pi * amu / rho / c.Ye, onethird);
-    double kF = std::pow(threepisquare * rho * c.Ye / amu, onethird);
+    double re = dsm::pow(threefourth / pi * amu / rho / c.Ye, onethird);
+    double kF = dsm::pow(threepisquare * rho * c.Ye / amu, onethird);
     double tau = 0.5 * boltzmann * T / hbar / clight / kF;
-    double eta = std::pow(c.A / c.Z, onethird) / re / cm_to_fm;
+    double eta = dsm::pow(c.A / c.Z, onethird) / re / cm_to_fm;
     double Zbareta = c.Z * eta;
     double A = 0.269 + 20.0 * tau + 0.0168 * c.Z + 0.00121 * eta - 0.0356 * Zbareta + 0.0137 * c.Z2 * tau +
                1.54 * Zbareta * tau;
     double B = 1.0 + 180.0 * (tau * tau) + 0.483 * tau * c.Z + 20.0 * tau * Zbareta * eta + 4.31e-5 * c.Z2;
-    double L = A / std::pow(B, threefourth);
+    double L = A / dsm::pow(B, threefourth);
     return qbrems_pre * ipow(T, 6) * c.Z2 * rho * L * (1.0 - c.Yn) / c.A;
 }
 }  // namespace
@@ -155,7 +155,7 @@ void crust_neutrino_emissivity(double rho, double T, const Composition& c, doubl
     if (ch[3]) eps.brems = bremsstrahlung(rho, T, c);
     if (ch[4]) {
         double nn = rho * c.Yn / amu / (1.0 - chi);
-        double kn = std::pow(R4(1.5) * (pi * pi) * nn, onethird) / cm_to_fm;
+        double kn = dsm::pow(R4(1.5) * (pi * pi) * nn, onethird) / cm_to_fm;
         eps.pbf = pbf(kn, T, Tcn);
     }
     eps.total = eps.pair + eps.photo + eps.plasma + eps.brems + eps.pbf;

@@ -60,26 +60,26 @@ int micro_tables(const HelmTable& h, const MicroTablesIn& in, double* tab_lnT, d
             if (in.Tc_cell) { Tc[0] = in.Tc_cell[3 * iz]; Tc[1] = in.Tc_cell[3 * iz + 1]; Tc[2] = in.Tc_cell[3 * iz + 2]; }
             else sf_get_results(*g_micro_sf, 0.0, kn, Tc);
             for (int it = 0; it < nt; ++it) {
-                double Ttab = std::exp(tab_lnT[it]);
+                double Ttab = dsm::exp(tab_lnT[it]);
                 double res[num_eos_results];
                 int phase;
                 int ierr = eval_crust_eos(h, rq, rho, Ttab, c, nch, in.Zion, in.Aion,
                                           in.Yion + (size_t)nch * iz, Tc, res, phase, chi);
                 if (ierr != 0) status = ierr;
-                lnCp[4 * it] = std::log(res[i_Cp]);
-                lnGam[4 * it] = std::log(res[i_Gamma]);
+                lnCp[4 * it] = dsm::log(res[i_Cp]);
+                lnGam[4 * it] = dsm::log(res[i_Gamma]);
                 if (iz == 0 && it == 0)  // :367-369
-                    rb1 = rho * std::pow(in.P_bar[0] / in.P[0], 1.0 / res[i_chiRho]);
+                    rb1 = rho * dsm::pow(in.P_bar[0] / in.P[0], 1.0 / res[i_chiRho]);
                 CrustNeutrino eps;
                 crust_neutrino_emissivity(rho, Ttab, c, chi, Tc[1], ch, eps);
-                lnEnu[4 * it] = std::log(eps.total / rho);
+                lnEnu[4 * it] = dsm::log(eps.total / rho);
             }
             if (in.turn_on_shell_Urca && iz < nz - 1) {  // :379-384
-                if (std::log10(in.P_bar[iz]) < in.lgP_shell_Urca && std::log10(in.P_bar[iz + 1]) > in.lgP_shell_Urca) {
+                if (dsm::log10(in.P_bar[iz]) < in.lgP_shell_Urca && dsm::log10(in.P_bar[iz + 1]) > in.lgP_shell_Urca) {
                     for (int it = 0; it < nt; ++it)
-                        lnEnu[4 * it] = std::log(std::exp(lnEnu[4 * it]) +
+                        lnEnu[4 * it] = dsm::log(dsm::exp(lnEnu[4 * it]) +
                                                  1.0e36 * in.shell_Urca_luminosity_coeff *
-                                                     ipow(std::exp(tab_lnT[it]) / 5.0e8, 5) / in.dm[iz]);
+                                                     ipow(dsm::exp(tab_lnT[it]) / 5.0e8, 5) / in.dm[iz]);
                 }
             }
             interp_pm(tab_lnT, nt, lnEnu);
@@ -94,7 +94,7 @@ int micro_tables(const HelmTable& h, const MicroTablesIn& in, double* tab_lnT, d
             Composition c = comp_at(in.ionic_bar, iz);
             double rho = (iz == 0) ? rb1 : in.rho_bar[iz];
             for (int it = 0; it < nt; ++it) {
-                double Ttab = std::exp(tab_lnT[it]);
+                double Ttab = dsm::exp(tab_lnT[it]);
                 double chi = nuclear_volume_fraction(rho, c, default_nuclear_radius);
                 double kn = neutron_wavenumber(rho, c, chi);
                 double Tc[3];
@@ -107,7 +107,7 @@ int micro_tables(const HelmTable& h, const MicroTablesIn& in, double* tab_lnT, d
                 if (ierr != 0) status = ierr;
                 CondComponents K;
                 conductivity(cq, rho, Ttab, chi, res[i_Gamma], res[i_Theta], res[i_mu_e], c, Tc[1], K);
-                lnK[4 * it] = std::log(K.total);
+                lnK[4 * it] = dsm::log(K.total);
             }
             interp_pm(tab_lnT, nt, lnK);
         }
@@ -321,12 +321,12 @@ int rodasp(const StiffProblem& pb, double& x, double* y, double xend, double& h,
                 err += (ak6[i] / sk) * (ak6[i] / sk);
             }
             err = std::sqrt(err / n);
-            double facs = std::max(fac2, std::min(fac1, std::pow(err, 0.25) / safe));
+            double facs = std::max(fac2, std::min(fac1, dsm::pow(err, 0.25) / safe));
             double hnew = h / facs;
             if (err <= 1.0) {
                 ++naccpt;
                 if (naccpt > 1) {  // Gustafsson predictive controller
-                    double facgus = (hacc / h) * std::pow(err * err / erracc, 0.25) / safe;
+                    double facgus = (hacc / h) * dsm::pow(err * err / erracc, 0.25) / safe;
                     facgus = std::max(fac2, std::min(fac1, facgus));
                     facs = std::max(facs, facgus);
                     hnew = h / facs;
@@ -392,12 +392,12 @@ int rodasp_selftest(int problem, double tend, double rtol, double atol, double h
     } else {  // Prothero-Robinson, autonomous form: y1' = -1e6 (y1 - cos y2) - sin y2, y2' = 1 ; y1 = cos t
         pb.n = 2;
         pb.fcn = [](double, const double* yy, double* f) {
-            f[0] = -1.0e6 * (yy[0] - std::cos(yy[1])) - std::sin(yy[1]);
+            f[0] = -1.0e6 * (yy[0] - dsm::cos(yy[1])) - dsm::sin(yy[1]);
             f[1] = 1.0;
             return 0; };
         pb.jac = [](double, const double* yy, double*, double* sup, double* d, double* sub) {
             d[0] = -1.0e6; d[1] = 0.0;
-            sup[0] = 0.0; sup[1] = -1.0e6 * std::sin(yy[1]) - std::cos(yy[1]);  // df(0)/dy(1), stored at column 1
+            sup[0] = 0.0; sup[1] = -1.0e6 * dsm::sin(yy[1]) - dsm::cos(yy[1]);  // df(0)/dy(1), stored at column 1
             sub[0] = 0.0; sub[1] = 0.0;
             return 0; };
     }
@@ -438,7 +438,7 @@ struct Star {
         T_bar[0] = T[0];
         for (int k = 1; k < n; ++k)
             T_bar[k] = 0.5 * (T[k - 1] * in.dm[k] + T[k] * in.dm[k - 1]) / in.dm_bar[k];
-        for (int k = 0; k < n; ++k) lnT_bar[k] = std::log(T_bar[k]);
+        for (int k = 0; k < n; ++k) lnT_bar[k] = dsm::log(T_bar[k]);
     }
     // :461-524
     void get_coefficients() {
@@ -451,14 +451,14 @@ struct Star {
             interp_value_and_slope(in.tab_lnT, nt, in.tab_lnEnu + off, lnT[iz], lnenu[iz], dlnenu[iz]);
             if (in.reference_cost_quirks) {  // :504-507 whole-array exps inside the zone loop
                 for (int k = 0; k < n; ++k) {
-                    Kcond[k] = std::exp(lnK[k]); Cp[k] = std::exp(lnCp[k]);
-                    Gam[k] = std::exp(lnGam[k]); enu[k] = std::exp(lnenu[k]);
+                    Kcond[k] = dsm::exp(lnK[k]); Cp[k] = dsm::exp(lnCp[k]);
+                    Gam[k] = dsm::exp(lnGam[k]); enu[k] = dsm::exp(lnenu[k]);
                 }
             }
         }
         for (int k = 0; k < n; ++k) {
-            Kcond[k] = std::exp(lnK[k]); Cp[k] = std::exp(lnCp[k]);
-            Gam[k] = std::exp(lnGam[k]); enu[k] = std::exp(lnenu[k]);
+            Kcond[k] = dsm::exp(lnK[k]); Cp[k] = dsm::exp(lnCp[k]);
+            Gam[k] = dsm::exp(lnGam[k]); enu[k] = dsm::exp(lnenu[k]);
         }
         nuclear_heating();
     }
@@ -484,7 +484,7 @@ struct Star {
     bool insulating() const { return in.make_inner_boundary_insulating && !in.fix_core_temperature; }
     // :237-283
     int derivatives(const double* y, double* f) {
-        for (int k = 0; k < n; ++k) { lnT[k] = y[k]; T[k] = std::exp(lnT[k]); }
+        for (int k = 0; k < n; ++k) { lnT[k] = y[k]; T[k] = dsm::exp(lnT[k]); }
         interpolate_temps();
         get_coefficients();
         evaluate_luminosity();
@@ -536,7 +536,7 @@ int evolve_epoch(const EvolveIn& in, EvolveState& st, EvolveTrace* trace) {
     const int n = in.nz;
     Star s(in);
     std::vector<double> z(st.lnT, st.lnT + n);
-    if (s.accreting_fixed()) z[0] = std::log(in.atmosphere_temperature_when_accreting);  // :69-71
+    if (s.accreting_fixed()) z[0] = dsm::log(in.atmosphere_temperature_when_accreting);  // :69-71
     double rtol = in.integration_tolerance;
     double zminv = z[0];
     for (int k = 1; k < n; ++k) zminv = std::min(zminv, z[k]);
@@ -554,7 +554,7 @@ int evolve_epoch(const EvolveIn& in, EvolveState& st, EvolveTrace* trace) {
         st.model = nr + in.starting_number_for_profile;
         st.tsec = x + in.epoch_start_time;
         st.dt = x - xold;
-        for (int k = 0; k < n; ++k) { s.lnT[k] = y[k]; s.T[k] = std::exp(s.lnT[k]); }
+        for (int k = 0; k < n; ++k) { s.lnT[k] = y[k]; s.T[k] = dsm::exp(s.lnT[k]); }
         s.interpolate_temps();
         s.get_coefficients();
         s.evaluate_luminosity();

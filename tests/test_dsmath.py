@@ -1,0 +1,78 @@
+"""dsmath (deterministic elementary functions, the analogue of MESA's math_lib/crlibm layer):
+accuracy of the CPU copy against numpy/libm on the argument ranges the hot path uses, and -- on
+the GPU -- bit-for-bit equality of the device implementation with the CPU copy."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle_lib import _ptr, f64
+
+FN = {"exp": 0, "log": 1, "log10": 2, "pow": 3, "sin": 4, "cos": 5, "sinh": 6, "cosh": 7, "atan": 8}
+
+
+def cpu_eval(oracle, name, x, y=None):
+    x = f64(x); y = f64(np.zeros_like(x) if y is None else y)
+    out = np.zeros_like(x)
+    oracle.lib.dso_dsmath(FN[name], len(x), _ptr(x), _ptr(y), _ptr(out))
+    return out
+
+
+def ulp_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.max(np.abs(got - ref) / np.spacing(np.abs(ref)))
+
+
+def samples(rng):
+    return {
+        "exp": (rng.uniform(-700, 700, 20000), None, np.exp, 2.5),
+        "log": (10.0 ** rng.uniform(-300, 300, 20000), None, np.log, 2.5),
+        "log10": (10.0 ** rng.uniform(-30, 40, 20000), None, np.log10, 3.0),
+        "sin": (rng.uniform(-60, 60, 20000), None, np.sin, None),
+        "cos": (rng.uniform(-60, 60, 20000), None, np.cos, None),
+        "sinh": (rng.uniform(0.5, 250, 20000), None, np.sinh, 4.0),
+        "cosh": (rng.uniform(-250, 250, 20000), None, np.cosh, 4.0),
+        "atan": (10.0 ** rng.uniform(-8, 8, 20000) * rng.choice([-1, 1], 20000), None, np.arctan, 6.0),
+    }
+
+
+def test_dsmath_accuracy(oracle):
+    rng = np.random.default_rng(11)
+    for name, (x, y, ref, tol) in samples(rng).items():
+        got = cpu_eval(oracle, name, x, y)
+        if tol is None:   # sin/cos: absolute accuracy (relative accuracy is lost near zeros by design)
+            assert np.max(np.abs(got - ref(x))) < 4e-16, name
+        else:
+            assert ulp_err(got, ref(x)) < tol, (name, ulp_err(got, ref(x)))
+    # pow: exact-root fast paths are correctly rounded-ish; general path carries |y ln x| ulp
+    x = 10.0 ** rng.uniform(-40, 40, 20000)
+    for yv in (0.5, 1.5, 2.5, 3.5, 0.25):
+        assert ulp_err(cpu_eval(oracle, "pow", x, np.full_like(x, yv)), x ** yv) < 2.5
+    for yv in (1 / 3, 2 / 3, 5 / 3, 0.617, -0.3, 8 / 3):
+        got = cpu_eval(oracle, "pow", x, np.full_like(x, yv))
+        assert np.max(np.abs(got / x ** yv - 1.0)) < 6e-14, yv
+    # special values
+    assert cpu_eval(oracle, "exp", [-1000.0, 0.0])[0] == 0.0 and cpu_eval(oracle, "exp", [0.0])[0] == 1.0
+    assert cpu_eval(oracle, "log", [1.0])[0] == 0.0 and np.isinf(cpu_eval(oracle, "log", [0.0])[0])
+    assert cpu_eval(oracle, "pow", [0.0, 5.0], [2.0, 0.0]).tolist() == [0.0, 1.0]
+
+
+@pytest.mark.gpu
+def test_dsmath_bits(oracle):
+    """The device implementation returns exactly the bits of the CPU copy."""
+    import dstar_b200 as ds
+    from dstar_b200._capi import check, p
+    ctx = ds.Context(0, gaps=None)
+    rng = np.random.default_rng(12)
+    try:
+        cases = {k: (v[0], v[1]) for k, v in samples(rng).items()}
+        xx = 10.0 ** rng.uniform(-40, 40, 40000)
+        cases["pow"] = (xx, rng.choice([0.5, 1.5, 2.5, 0.25, 1 / 3, 2 / 3, 5 / 3, 0.617, -0.3, 8 / 3, 0.475, -2.066], 40000))
+        for name, (x, y) in cases.items():
+            x = f64(x); y = f64(np.zeros_like(x) if y is None else y)
+            out = np.zeros_like(x)
+            check(ctx.L.dstar_dsmath_eval(ctx.h, FN[name], len(x), p(x), p(y), p(out)), "dsmath_eval")
+            ref = cpu_eval(oracle, name, x, y)
+            assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), name
+    finally:
+        ctx.close()
