@@ -170,6 +170,9 @@ class Batch:
                                                p(atm_lgflux), p(atm_index, ip), p(heat), p(T_atm), p(lnT0),
                                                self.n_epoch, p(eb), p(em), p(en)), "upload_evolve")
 
+    def reset_state(self):
+        check(self.L.dstar_batch_reset_state(self.h), "dstar_batch_reset_state")
+
     def evolve(self, ctrl=None, trace_cap=0):
         ctrl = ctrl or EvolveCtrl.defaults()
         self.trace_cap = trace_cap
@@ -258,10 +261,20 @@ class NScool:
     def set_hooks(self, other_set_Qimp=None, other_sf_get_results=None):
         QF = C.CFUNCTYPE(None, C.c_int, ip)
         SF = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, dp)
-        q = QF(other_set_Qimp) if other_set_Qimp else C.cast(None, QF)
-        s = SF(other_sf_get_results) if other_sf_get_results else C.cast(None, SF)
-        self._hooks = (q, s)
-        _nerr(self.L.dstar_NScool_set_hooks(self.id, q, s), "set_hooks")
+        q = QF(other_set_Qimp) if other_set_Qimp else None
+        s = SF(other_sf_get_results) if other_sf_get_results else None
+        self._hooks = (q, s)   # keep the trampolines alive
+        self.L.dstar_NScool_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _nerr(self.L.dstar_NScool_set_hooks(self.id, C.cast(q, C.c_void_p) if q else None,
+                                            C.cast(s, C.c_void_p) if s else None), "set_hooks")
+
+    def use_example_hooks(self):
+        """other_set_Qimp => alt_Qimp, other_sf_get_results => alt_sf (examples/custom_Tc_Qimp/src/run.f:50-51),
+        the native versions shipped in the library."""
+        L = self.L
+        L.dstar_NScool_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _nerr(L.dstar_NScool_set_hooks(self.id, C.cast(L.dstar_example_alt_Qimp, C.c_void_p),
+                                       C.cast(L.dstar_example_alt_sf, C.c_void_p)), "set_hooks")
 
     def create_model(self):
         _nerr(self.L.dstar_NScool_create_model(self.id), "NScool_create_model")

@@ -73,7 +73,7 @@ struct dstar_batch {
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
-        lnT, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
+        lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
     DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms[3] = {0, 0, 0};
@@ -540,6 +540,7 @@ int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double
     CK(b->atm_lgflux.upload(atm_lgflux, (size_t)n_atm * 4 * atm_nv, s));
     CK(b->atm_index.upload(atm_index, ns, s)); CK(b->heat.upload(heat, 9 * ns, s)); CK(b->T_atm.upload(T_atm, ns, s));
     CK(b->lnT.upload(lnT0, n, s));
+    CK(b->lnT0.upload(lnT0, n, s));
     CK(b->epoch_boundaries.upload(epoch_boundaries, (size_t)(n_epoch + 1) * ns, s));
     CK(b->epoch_Mdots.upload(epoch_Mdots, (size_t)n_epoch * ns, s));
     b->have_enuc = enuc_per_Mdot != nullptr;
@@ -554,6 +555,19 @@ int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double
     CK(b->counters.alloc(7 * ns)); CK(b->Teff.alloc(ns)); CK(b->Lsurf.alloc(ns));
     CK(cudaStreamSynchronize(s));
     b->have_evolve = true;
+    return DSTAR_OK;
+}
+
+int dstar_batch_reset_state(dstar_batch* b) {
+    if (!b) return fail(DSTAR_ERR_ARG, "batch_reset_state");
+    if (!b->have_evolve) return fail(DSTAR_ERR_STATE, "evolve inputs missing");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t ns = b->n_star;
+    CK(cudaMemcpyAsync(b->lnT.p, b->lnT0.p, (size_t)b->total * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemsetAsync(b->dt.p, 0, ns * sizeof(double), s));
+    CK(cudaMemsetAsync(b->tsec.p, 0, ns * sizeof(double), s));
+    CK(cudaMemsetAsync(b->model.p, 0, ns * sizeof(int), s));
     return DSTAR_OK;
 }
 

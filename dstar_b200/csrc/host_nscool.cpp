@@ -954,6 +954,12 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 1);
     if (rc == 0) { g_ms[0] = dstar_batch_last_kernel_ms(b, 0); rc = dstar_batch_get_rho_bar1(b, rb1.data()); }
     if (rc == 0 && any_hook) { eval_Tc(true, rb1, Tc_face); rc = dstar_batch_set_Tc_face(b, Tc_face.data()); }
+    if (any_hook)
+        for (int i = 0; i < n; ++i) {  // keep the hook-evaluated critical temperatures with the star
+            ss[i]->z["Tc_cell"].assign(&Tc_cell[(size_t)3 * zoff[i]], &Tc_cell[(size_t)3 * zoff[i]] + 3 * ss[i]->nz);
+            if (!Tc_face.empty())
+                ss[i]->z["Tc_face"].assign(&Tc_face[(size_t)3 * zoff[i]], &Tc_face[(size_t)3 * zoff[i]] + 3 * ss[i]->nz);
+        }
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 2);
     if (rc == 0) g_ms[1] = dstar_batch_last_kernel_ms(b, 1);
     std::vector<double> tlnT(DSTAR_NTAB), tCp((size_t)4 * DSTAR_NTAB * total), tGa(tCp.size()), tEn(tCp.size()), tK(tCp.size());
@@ -1206,5 +1212,28 @@ int dstar_NScool_write_history(int id, const char* path) {
 double dstar_NScool_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? g_ms[which] : -1.0; }
 
 const char* dstar_NScool_last_error(void) { return g_err.c_str(); }
+
+// ---- the hooks of examples/custom_Tc_Qimp/src/alt_micro.f, for sweep drivers
+// alt_Qimp (:4-19): Q = extra_real_controls(2) wherever rho_bar > extra_real_controls(1)
+void dstar_example_alt_Qimp(int id, int* ierr) {
+    Star* s = get(id);
+    *ierr = s ? 0 : -1;
+    if (!s) return;
+    const double rhoC = s->c.extra_real_controls[0], Q = s->c.extra_real_controls[1];
+    auto& ib = s->z["ionic_bar"];
+    const auto& rb = s->z["rho_bar"];
+    for (int k2 = 0; k2 < s->nz; ++k2) if (rb[k2] > rhoC) ib[11 * k2 + 10] = Q;
+}
+// alt_sf (:21-44): Tc = 1e10 K everywhere, neutron 1S0 closes above the wavenumber of rho_C
+void dstar_example_alt_sf(int id, double kp, double kn, double Tc[3]) {
+    (void)kp;
+    Tc[0] = Tc[1] = Tc[2] = (double)1.0e10f;
+    Star* s = get(id);
+    if (!s) return;
+    const double rhoC = s->c.extra_real_controls[0];
+    const double n = rhoC * k::avogadro;
+    const double kC = dsm::pow(0.5 * k::threepisquare * n, k::onethird) / k::cm_to_fm;
+    if (kn > kC) Tc[1] = 0.0;
+}
 
 }  // extern "C"

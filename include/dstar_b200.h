@@ -145,6 +145,8 @@ int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double
 /* optionally take the tables from the host instead of dstar_batch_micro_tables */
 int dstar_batch_upload_tables(dstar_batch* b, const double* tab_lnT, const double* tab_lnCp,
                               const double* tab_lnGamma, const double* tab_lnEnu, const double* tab_lnK);
+/* restore the evolving state (lnT, dt, tsec, model) to what dstar_batch_upload_evolve set, device to device */
+int dstar_batch_reset_state(dstar_batch* b);
 /* seam B: every star through all its epochs in ONE launch.  trace_cap > 0 keeps that many
  * history rows per star. */
 int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap);

@@ -47,6 +47,10 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids);
 typedef void (*dstar_set_Qimp_fn)(int id, int* ierr);
 typedef void (*dstar_sf_fn)(int id, double kp, double kn, double Tc[3]);
 int dstar_NScool_set_hooks(int id, dstar_set_Qimp_fn qimp, dstar_sf_fn sf);
+/* native versions of the example hooks alt_Qimp / alt_sf (examples/custom_Tc_Qimp/src/alt_micro.f:4-44),
+ * reading extra_real_controls(1:2) = (rho_C, Q_pasta), for sweep drivers */
+void dstar_example_alt_Qimp(int id, int* ierr);
+void dstar_example_alt_sf(int id, double kp, double kn, double Tc[3]);
 /* accessors to type NScool_info (NScool_def.f:33-157) */
 int dstar_NScool_get_int(int id, const char* name, int32_t* value);     /* nz, number_epochs, ncharged, model */
 int dstar_NScool_get_real(int id, const char* name, double* value);     /* grav, Mtotal, Rtotal, Teff, Lsurf, ... */
