@@ -34,7 +34,7 @@ METRIC = "zone_microphysics_evals_per_sec"
 UNIT = "evals/s"
 # algorithmic FP64 work per evaluation: cell = EOS + neutrino, face = EOS + conductivity,
 # one ion species, neutron channels off; weighted operation counts incl. transcendentals
-FLOP_CELL, FLOP_FACE = 6.0e3, 5.0e3
+FLOP_CELL, FLOP_FACE = 6.0e3, 1.6e3
 ARRS_STRUCT = ["rho", "rho_bar", "P", "P_bar", "dm", "ionic", "ionic_bar", "Yion", "Yion_bar"]
 ARRS_GEOM = ["dm_bar", "area", "ePhi", "e2Phi", "ePhi_bar", "e2Phi_bar"]
 

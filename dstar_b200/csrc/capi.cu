@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,6 +94,10 @@ void fill_host_consts(DsHostConsts& h) {
     h.befac = dsm::pow(finestructure / pi, 1.5);
     h.yfac = std::sqrt(4.0 * finestructure / pi);
     h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
+}
+int micro_minb() {  // tuning knob (experiments): CTAs per SM the coefficient-pass kernels are compiled for
+    static int v = [] { const char* e = std::getenv("DSTAR_MICRO_MINB"); return e ? std::atoi(e) : 6; }();
+    return v;
 }
 DsEosCtrl eos_ctrl_from(const dstar_micro_ctrl* c) {
     DsEosCtrl e{175.0, 140.0, DS_R4(1.0e-9)};  // dStar_eos_def.f:58-62
@@ -467,7 +472,10 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     b->launches = 0;
     if (which & 1) {
         CK(cudaEventRecord(b->ev0, s));
-        ds_micro_kernel<false><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf);
+        switch (micro_minb()) {
+            case 4: ds_micro_kernel<false, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+            default: ds_micro_kernel<false, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));
         CK(cudaEventSynchronize(b->ev1));
@@ -476,7 +484,10 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     }
     if (which & 2) {
         CK(cudaEventRecord(b->ev0, s));
-        ds_micro_kernel<true><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf);
+        switch (micro_minb()) {
+            case 4: ds_micro_kernel<true, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+            default: ds_micro_kernel<true, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));
         CK(cudaEventSynchronize(b->ev1));

@@ -114,8 +114,9 @@ DS_D void ds_cta_interp_pm(const double* __restrict__ x, double* v, double* hh, 
     __syncthreads();
 }
 
-template <bool FACE>
-__global__ void __launch_bounds__(DS_NTAB) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
+// MINB = CTAs the register allocator must fit per SM (occupancy / spill trade-off, tuned on B200)
+template <bool FACE, int MINB>
+__global__ void __launch_bounds__(DS_NTAB, MINB) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     __shared__ double s_x[DS_NTAB], s_v[3][DS_NTAB], s_h[DS_NTAB], s_m[DS_NTAB], s_s[DS_NTAB];
     __shared__ double s_lam;
     __shared__ int s_lam_ierr, s_err;

@@ -82,14 +82,21 @@ DS_D double cfp(double lamb, double xi) {
     else if (temp < 1.0e8) { band = 0; c = 0.5654 + dsm::log10(temp / 1.0e7); tau = dsm::log10(temp / 1.0e7); }
     else if (temp < 1.0e9) { band = 1; c = 1.5654; tau = dsm::log10(temp / 1.0e8); }
     else { band = 2; c = 1.5654; tau = dsm::log10(temp / 1.0e9); }
+    // the harmonics do not depend on j: evaluate the six arguments once (one fused sincos each) and
+    // reuse them for a(0), a(1), a(2); accumulation order as eval_crust_neutrino.f:230-237
+    const double c10 = dsm::cos(10.0 * pi * tau);
+    double ck[6], sk[6];
+#pragma unroll
+    for (int k = 1; k <= 5; ++k) {
+        double pjt = pi * (double)k * tau;
+        dsm::sincos(5.0 / 3.0 * pjt, sk[k], ck[k]);
+    }
     double a[3];
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
-        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * dsm::cos(10.0 * pi * tau);
-        for (int k = 1; k <= 5; ++k) {
-            double pjt = pi * (double)k * tau;
-            a[j] = a[j] + cfp_cc[band][j][k] * dsm::cos(5.0 / 3.0 * pjt) +
-                   cfp_dd[band][j][k - 1] * dsm::sin(5.0 / 3.0 * pjt);
-        }
+        a[j] = 0.5 * cfp_cc[band][j][0] + 0.5 * cfp_cc[band][j][6] * c10;
+#pragma unroll
+        for (int k = 1; k <= 5; ++k) a[j] = a[j] + cfp_cc[band][j][k] * ck[k] + cfp_dd[band][j][k - 1] * sk[k];
     }
     return (a[0] + a[1] * xi + a[2] * (xi * xi)) * dsm::exp(-c * xi) /
            (dsd::ipow<3>(xi) + b[0] / lamb + b[1] / (lamb * lamb) + b[2] / dsd::ipow<3>(lamb));
