@@ -474,6 +474,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         switch (micro_minb()) {
             case 4: ds_micro_kernel<false, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+            case 8: ds_micro_kernel<false, 8><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
             default: ds_micro_kernel<false, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
         }
         CK(cudaGetLastError());
@@ -486,6 +487,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         switch (micro_minb()) {
             case 4: ds_micro_kernel<true, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+            case 8: ds_micro_kernel<true, 8><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
             default: ds_micro_kernel<true, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
         }
         CK(cudaGetLastError());
