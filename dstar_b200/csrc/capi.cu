@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -472,10 +473,12 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     b->launches = 0;
     if (which & 1) {
         CK(cudaEventRecord(b->ev0, s));
-        switch (micro_minb()) {
-            case 4: ds_micro_kernel<false, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
-            case 8: ds_micro_kernel<false, 8><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
-            default: ds_micro_kernel<false, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+        {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
+            const int sms = c->prop.multiProcessorCount;
+            switch (micro_minb()) {
+                case 4: ds_micro_kernel<false, 4><<<std::min(sms, (b->total + 3) / 4), DS_NTAB * 4, 0, s>>>(a, c->helm, c->sf); break;
+                default: ds_micro_kernel<false, 6><<<std::min(sms, (b->total + 5) / 6), DS_NTAB * 6, 0, s>>>(a, c->helm, c->sf); break;
+            }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));
@@ -485,10 +488,12 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     }
     if (which & 2) {
         CK(cudaEventRecord(b->ev0, s));
-        switch (micro_minb()) {
-            case 4: ds_micro_kernel<true, 4><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
-            case 8: ds_micro_kernel<true, 8><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
-            default: ds_micro_kernel<true, 6><<<b->total, DS_NTAB, 0, s>>>(a, c->helm, c->sf); break;
+        {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
+            const int sms = c->prop.multiProcessorCount;
+            switch (micro_minb()) {
+                case 4: ds_micro_kernel<true, 4><<<std::min(sms, (b->total + 3) / 4), DS_NTAB * 4, 0, s>>>(a, c->helm, c->sf); break;
+                default: ds_micro_kernel<true, 6><<<std::min(sms, (b->total + 5) / 6), DS_NTAB * 6, 0, s>>>(a, c->helm, c->sf); break;
+            }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));

@@ -76,109 +76,129 @@ struct DsMicroArgs {
     double *tab_lnCp, *tab_lnGamma, *tab_lnEnu, *tab_lnK;  // (4*128, total_zones)
 };
 
-// MESA interp_pm (Steffen 1990) on the CTA's 128 knots; v holds f(1,:) on entry.
-DS_D void ds_cta_interp_pm(const double* __restrict__ x, double* v, double* hh, double* sm, double* sl,
-                           double* __restrict__ out) {
-    const int i = threadIdx.x, n = DS_NTAB;
-    if (i < n - 1) {
+// MESA interp_pm (Steffen 1990) on one zone's 128 knots; i = knot index of this lane, v holds f(1,:) on entry.
+// Called by every thread of the CTA (the barriers are CTA-wide); `on` masks groups without a zone.
+DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ x, double* v, double* hh, double* sm,
+                             double* sl, double* __restrict__ out) {
+    const int n = DS_NTAB;
+    if (on && i < n - 1) {
         hh[i] = x[i + 1] - x[i];
         sm[i] = (v[i + 1] - v[i]) / hh[i];
     }
     __syncthreads();
-    double s;
-    if (i > 0 && i < n - 1) {
-        double p = (sm[i - 1] * hh[i] + sm[i] * hh[i - 1]) / (hh[i - 1] + hh[i]);
-        double sg = copysign(1.0, sm[i - 1]) + copysign(1.0, sm[i]);
-        s = sg * fmin(fmin(fabs(sm[i - 1]), fabs(sm[i])), 0.5 * fabs(p));
-    } else if (i == 0) {
-        double p1 = sm[0] * (1.0 + hh[0] / (hh[0] + hh[1])) - sm[1] * hh[0] / (hh[0] + hh[1]);
-        if (p1 * sm[0] <= 0.0) s = 0.0;
-        else if (fabs(p1) > 2.0 * fabs(sm[0])) s = 2.0 * sm[0];
-        else s = p1;
-    } else {
-        double pn = sm[n - 2] * (1.0 + hh[n - 2] / (hh[n - 2] + hh[n - 3])) -
-                    sm[n - 3] * hh[n - 2] / (hh[n - 2] + hh[n - 3]);
-        if (pn * sm[n - 2] <= 0.0) s = 0.0;
-        else if (fabs(pn) > 2.0 * fabs(sm[n - 2])) s = 2.0 * sm[n - 2];
-        else s = pn;
+    double s = 0.0;
+    if (on) {
+        if (i > 0 && i < n - 1) {
+            double p = (sm[i - 1] * hh[i] + sm[i] * hh[i - 1]) / (hh[i - 1] + hh[i]);
+            double sg = copysign(1.0, sm[i - 1]) + copysign(1.0, sm[i]);
+            s = sg * fmin(fmin(fabs(sm[i - 1]), fabs(sm[i])), 0.5 * fabs(p));
+        } else if (i == 0) {
+            double p1 = sm[0] * (1.0 + hh[0] / (hh[0] + hh[1])) - sm[1] * hh[0] / (hh[0] + hh[1]);
+            if (p1 * sm[0] <= 0.0) s = 0.0;
+            else if (fabs(p1) > 2.0 * fabs(sm[0])) s = 2.0 * sm[0];
+            else s = p1;
+        } else {
+            double pn = sm[n - 2] * (1.0 + hh[n - 2] / (hh[n - 2] + hh[n - 3])) -
+                        sm[n - 3] * hh[n - 2] / (hh[n - 2] + hh[n - 3]);
+            if (pn * sm[n - 2] <= 0.0) s = 0.0;
+            else if (fabs(pn) > 2.0 * fabs(sm[n - 2])) s = 2.0 * sm[n - 2];
+            else s = pn;
+        }
+        sl[i] = s;
     }
-    sl[i] = s;
     __syncthreads();
-    double c2 = 0.0, c3 = 0.0;
-    if (i < n - 1) {
-        c2 = (3.0 * sm[i] - 2.0 * sl[i] - sl[i + 1]) / hh[i];
-        c3 = (sl[i] + sl[i + 1] - 2.0 * sm[i]) / (hh[i] * hh[i]);
+    if (on) {
+        double c2 = 0.0, c3 = 0.0;
+        if (i < n - 1) {
+            c2 = (3.0 * sm[i] - 2.0 * sl[i] - sl[i + 1]) / hh[i];
+            c3 = (sl[i] + sl[i + 1] - 2.0 * sm[i]) / (hh[i] * hh[i]);
+        }
+        reinterpret_cast<double4*>(out)[i] = make_double4(v[i], s, c2, c3);
     }
-    double4 r = make_double4(v[i], s, c2, c3);
-    reinterpret_cast<double4*>(out)[i] = r;
     __syncthreads();
 }
 
-// MINB = CTAs the register allocator must fit per SM (occupancy / spill trade-off, tuned on B200)
-template <bool FACE, int MINB>
-__global__ void __launch_bounds__(DS_NTAB, MINB) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
-    __shared__ double s_x[DS_NTAB], s_v[3][DS_NTAB], s_h[DS_NTAB], s_m[DS_NTAB], s_s[DS_NTAB];
-    __shared__ double s_lam;
-    __shared__ int s_lam_ierr, s_err;
-    const int g = blockIdx.x, it = threadIdx.x;
-    const int star = a.zone_star[g];
-    const int iz = g - a.zone_offset[star];
-    const int nz = a.zone_offset[star + 1] - a.zone_offset[star];
-    if (it == 0) { s_err = 0; s_lam = nan(""); s_lam_ierr = 0; }
-    s_x[it] = a.tab_lnT[it];
-    const DsComp c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
-    const double rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
-    const double chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
-    const double kn = dse::neutron_wavenumber(rho, c, chi);
-    double Tc[3];
-    const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
-    if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
-    else ds_sf_get_results(sf, 0.0, kn, Tc);
+// Persistent form: ONE CTA per SM, G groups of 128 lanes; group k of CTA b handles zones
+// (b*G + k) + round * gridDim.x * G.  The kernel body is ~430 KB of straight-line SASS executed once per
+// evaluation, far larger than the instruction caches: with independent 128-thread CTAs the SM held six CTAs
+// at six different program counters and the warps starved on instruction fetch (ncu: stalled_no_instruction
+// 11 per issue, profiles/r01_notes.md).  Here all G groups start every round together (CTA barrier), so the
+// 4*G warps of an SM walk through the code in lockstep and every instruction line is fetched once per SM.
+template <bool FACE, int G>
+__global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
+    __shared__ double s_x[DS_NTAB], s_v[G][3][DS_NTAB], s_h[G][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
+    __shared__ double s_lam[G];
+    __shared__ int s_lam_ierr[G], s_err[G];
+    const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
+    if (threadIdx.x < DS_NTAB) s_x[it] = a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
-    __syncthreads();
-
-    if (FACE && a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
-        // impurity Coulomb logarithm: T-independent, once per zone (neutron_conductivity.f:382)
-        double nn = rho / dsc::amu * c.Yn / (1.0 - chi);
-        double lam;
-        s_lam_ierr = dsk::ds_lambda_imp(nn, c, lam);
-        s_lam = lam;
-    }
-    if (FACE) __syncthreads();
-
-    DsEosRes r;
-    ds_eval_crust_eos(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion,
-                      (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
-    if (r.ierr != 0) s_err = r.ierr;
-    if (!FACE) {
-        s_v[0][it] = dsm::log(r.Cp);
-        s_v[1][it] = dsm::log(r.Gamma);
-        if (iz == 0 && it == 0)  // create_model.f:367-369
-            a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
-        DsNeutrino eps;
-        dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
-        double lnenu = dsm::log(eps.total / rho);
-        if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
-            if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
-                lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
-                                             dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
+    for (int g0 = blockIdx.x * G; g0 < a.total_zones; g0 += gridDim.x * G) {
+        const int g = g0 + grp;
+        const bool on = g < a.total_zones;
+        if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; }
+        __syncthreads();   // start of round: all groups aligned
+        int star = 0, iz = 0, nz = 0;
+        DsComp c{};
+        double rho = 0.0, chi = 0.0, Tc[3] = {0.0, 0.0, 0.0};
+        if (on) {
+            star = a.zone_star[g];
+            iz = g - a.zone_offset[star];
+            nz = a.zone_offset[star + 1] - a.zone_offset[star];
+            c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
+            rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
+            chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
+            const double kn = dse::neutron_wavenumber(rho, c, chi);
+            const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
+            if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
+            else ds_sf_get_results(sf, 0.0, kn, Tc);
         }
-        s_v[2][it] = lnenu;
-    } else {
-        DsCond K;
-        dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, Tc[1], s_lam, s_lam_ierr, K);
-        s_v[0][it] = dsm::log(K.total);
+        if (FACE) {
+            if (on && a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
+                // impurity Coulomb logarithm: T-independent, once per zone (neutron_conductivity.f:382)
+                double nn = rho / dsc::amu * c.Yn / (1.0 - chi);
+                double lam;
+                s_lam_ierr[grp] = dsk::ds_lambda_imp(nn, c, lam);
+                s_lam[grp] = lam;
+            }
+            __syncthreads();
+        }
+        if (on) {
+            DsEosRes r;
+            ds_eval_crust_eos(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion,
+                              (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
+            if (r.ierr != 0) s_err[grp] = r.ierr;
+            if (!FACE) {
+                s_v[grp][0][it] = dsm::log(r.Cp);
+                s_v[grp][1][it] = dsm::log(r.Gamma);
+                if (iz == 0 && it == 0)  // create_model.f:367-369
+                    a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+                DsNeutrino eps;
+                dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
+                double lnenu = dsm::log(eps.total / rho);
+                if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
+                    if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
+                        lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
+                                                     dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
+                }
+                s_v[grp][2][it] = lnenu;
+            } else {
+                DsCond K;
+                dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, Tc[1], s_lam[grp],
+                                     s_lam_ierr[grp], K);
+                s_v[grp][0][it] = dsm::log(K.total);
+            }
+        }
+        __syncthreads();
+        const size_t ob = (size_t)4 * DS_NTAB * (on ? g : 0);
+        if (!FACE) {
+            ds_group_interp_pm(on, it, s_x, s_v[grp][2], s_h[grp], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
+            ds_group_interp_pm(on, it, s_x, s_v[grp][0], s_h[grp], s_m[grp], s_s[grp], a.tab_lnCp + ob);
+            ds_group_interp_pm(on, it, s_x, s_v[grp][1], s_h[grp], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
+        } else {
+            ds_group_interp_pm(on, it, s_x, s_v[grp][0], s_h[grp], s_m[grp], s_s[grp], a.tab_lnK + ob);
+        }
+        if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
     }
-    __syncthreads();
-    const size_t ob = (size_t)4 * DS_NTAB * g;
-    if (!FACE) {
-        ds_cta_interp_pm(s_x, s_v[2], s_h, s_m, s_s, a.tab_lnEnu + ob);
-        ds_cta_interp_pm(s_x, s_v[0], s_h, s_m, s_s, a.tab_lnCp + ob);
-        ds_cta_interp_pm(s_x, s_v[1], s_h, s_m, s_s, a.tab_lnGamma + ob);
-    } else {
-        ds_cta_interp_pm(s_x, s_v[0], s_h, s_m, s_s, a.tab_lnK + ob);
-    }
-    if (it == 0 && s_err != 0) a.status[star] = s_err;
 }
 
 // ---------------------------------------------------------------- batched point evaluators
