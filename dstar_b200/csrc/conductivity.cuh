@@ -398,16 +398,20 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
     const double kappa_e_pre = onethird * (pi * pi) * (boltzmann * boltzmann) * T * ne / Melectron / eF;
     double nu = 0.0, nu_c;
 
+    DS_PHASE();
     nu_c = (rq.ee_fmla == 2) ? ee_PCY(ne, T) : ee_SY06(ne, T);
     nu = nu + nu_c;
+    DS_PHASE();
     if (nu_c > dbl_tiny) kap.ee = kappa_e_pre / nu_c;
     nu_c = eion(kF, Gamma_e, eta, c.Ye, c.Z, c.Z2, c.Z53, c.A);
     nu = nu + nu_c;
     if (nu_c > dbl_tiny) kap.ei = kappa_e_pre / nu_c;
+    DS_PHASE();
     nu_c = (rq.eQ_fmla == 2) ? eQ_page(kF, c.Z, c.A, c.Q) : eQ(kF, c.Z, c.A, c.Q);
     nu = nu + nu_c;
     if (c.Q > eQ_threshold) kap.eQ = kappa_e_pre / nu_c;
     kap.electron_total = kappa_e_pre / nu;
+    DS_PHASE();
 
     if (c.Yn > 0.0) {
         const double nn = rho / amu * c.Yn / (1.0 - chi);
@@ -443,6 +447,7 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
         if (rq.include_sf_phonons && T < Tns) kap.sf = sPh(nn / density_n, nion / density_n, T, c);
     }
 
+    DS_PHASE();
     double K_opacity = 0.0;
     if (lgrho < rq.rad_full_off_lgrho) {
         kap.kap = Rosseland_kappa(rho, T, mu_e, c);

@@ -95,6 +95,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double a_hh = a_h * ah + a * (a0_hh / a0 - dsd::ipow<2>(a0_h / a0) - a1_hh / a1 + dsd::ipow<2>(a1_h / a1) +
                                   t1_hh / t1 - dsd::ipow<2>(t1_h / t1));
 
+    DS_PHASE();
     double b0 = DS_R4(0.341308) + DS_R4(12.070873) * theta2 + DS_R4(1.148889) * theta4;
     double b0_h = DS_R4(24.141746) * theta + DS_R4(4.595556) * theta3;
     double b0_hh = DS_R4(24.141746) + DS_R4(13.786668) * theta2;
@@ -119,6 +120,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double d_hh = d_h * dh + d * (-0.5 / theta2 + t2_hh / t2 - dsd::ipow<2>(t2_h / t2) + d0_hh / d0 -
                                   dsd::ipow<2>(d0_h / d0) - d1_hh / d1 + dsd::ipow<2>(d1_h / d1));
 
+    DS_PHASE();
     double e0 = DS_R4(0.539409) + DS_R4(2.522206) * theta2 + DS_R4(0.178484) * theta4;
     double e0_h = DS_R4(5.044412) * theta + DS_R4(0.713936) * theta3;
     double e0_hh = DS_R4(5.044412) + DS_R4(2.141808) * theta2;
@@ -140,12 +142,14 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double di_h = 0.5 / discr * (4.0 * e_h - 2.0 * d * d_h);
     double di_hh = (-dsd::ipow<2>((2.0 * e_h - d * d_h) / discr) + 2.0 * e_hh - d_h * d_h - d * d_hh) / discr;
 
+    DS_PHASE();
     double s1 = -c / e * Gamma_e;
     double s1h = c_h / c - e_h / e;
     double s1_h = s1 * s1h;
     double s1_hh = s1_h * s1h + s1 * (c_hh / c - dsd::ipow<2>(c_h / c) - e_hh / e + dsd::ipow<2>(e_h / e));
     double s1_g = -c / e;
     double s1_hg = s1_g * (c_h / c - e_h / e);
+    DS_PHASE();
     double b2 = b - c * d / e;
     double b2_h = b_h - (c_h * d + c * d_h) / e + c * d * e_h / (e * e);
     double b2_hh = b_hh - (c_hh * d + 2.0 * c_h * d_h + c * d_hh) / e +
@@ -167,6 +171,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double r3_gg = -0.25 * d / (Gamma_e * sqge);
     double r3_hg = e_h + 0.5 * d_h / sqge;
 
+    DS_PHASE();
     double b3 = a - c / e;
     double b3_h = a_h - c_h / e + c * e_h / (e * e);
     double b3_hh = a_hh - c_hh / e + (2.0 * c_h * e_h + c * e_hh) / (e * e) - 2.0 * c * (e_h * e_h) / dsd::ipow<3>(e);
@@ -185,6 +190,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double s3_gg = c3 * (r3_gg / r3 - dsd::ipow<2>(r3_g / r3));
     double s3_hg = (c3_h * r3_g + c3 * r3_hg) / r3 - c3 * r3_g * r3_h / (r3 * r3);
 
+    DS_PHASE();
     double b4 = 2.0 - d * d / e;
     double b4_h = e_h * dsd::ipow<2>(d / e) - 2.0 * d * d_h / e;
     double b4_hh = e_hh * dsd::ipow<2>(d / e) + 2.0 * e_h * dsd::ipow<2>(d / e) * (d_h / d - e_h / e) -
@@ -197,6 +203,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double c4_gg = -0.5 * e / (Gamma_e * sqge);
     double c4_hg = e_h / sqge;
 
+    DS_PHASE();
     double s4a = 2.0 / e / discr;
     double s4ah = e_h / e + di_h / discr;
     double s4a_h = -s4a * s4ah;
@@ -215,6 +222,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double s4c_g = c4_g * discr / dn1;
     double s4c_gg = c4_gg * discr / dn1 - 2.0 * c4 * discr * dsd::ipow<2>(c4_g / dn1);
     double s4c_hg = (c4_hg * discr + c4_g * di_h - c4_g * discr / dn1 * 2. * (discr * di_h + c4 * c4_h)) / dn1;
+    DS_PHASE();
     double s4 = s4a * s4b * s4c;
     double s4_h = s4a_h * s4b * s4c + s4a * s4b_h * s4c + s4a * s4b * s4c_h;
     double s4_hh = s4a_hh * s4b * s4c + s4a * s4b_hh * s4c + s4a * s4b * s4c_hh +
@@ -780,6 +788,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
     dse::lattice_properties(rho, T, c, ne, rs, Gamma_e, Gamma, ionQ);
+    DS_PHASE();
 
     // electrons: table + exchange (electron.f:10-51, :53-250)
     DsThermo e{0, 0, 0, 0, 0, 0, 0};
@@ -794,8 +803,10 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
             eta_e = he.etaele;
         }
     }
+    DS_PHASE();
     DsThermo ex;
     dse::ee_exchange(Gamma_e, rs, ex);
+    DS_PHASE();
     const double nek = ne * boltzmann;
     const double nekT = nek * T;
     const double uexfac = nekT / rho, pexfac = nekT, sexfac = nek / rho;
@@ -804,6 +815,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     DsThermo ion;
     int phase;
     dse::ion_mixture(rq, rs, Gamma_e, c, ncharged, Zion, Aion, Yion, Gamma, ionQ, phase, ion);
+    DS_PHASE();
     const double n_i = ne / c.Z;
     const double nik = n_i * boltzmann;
     const double nikT = nik * T;
@@ -813,6 +825,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     const double nn = rho * c.Yn / amu / (1.0 - chi);
     DsThermo nt;
     dse::MB77(nn, T, Tns, nt);
+    DS_PHASE();
     const double unfac = avogadro * c.Yn, pnfac = 1.0, snfac = unfac;
 
     DsThermo rad;
@@ -826,6 +839,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     const double dpt = e.dpt + ex.dpt * pexfac + ion.dpt * pifac + nt.dpt * pnfac + rad.dpt;
     const double gamma3m1 = dpt / rho / T / cv;
     const double gamma1 = (dpr + dpt * gamma3m1) / p;
+    DS_PHASE();
     o.lnP = dsm::log(p);
     o.lnE = dsm::log(u);
     o.lnS = dsm::log(s);

@@ -133,14 +133,17 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     if (threadIdx.x < DS_NTAB) s_x[it] = a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
     for (int g0 = blockIdx.x * G; g0 < a.total_zones; g0 += gridDim.x * G) {
-        const int g = g0 + grp;
-        const bool on = g < a.total_zones;
+        const int gq = g0 + grp;
+        const bool on = gq < a.total_zones;
         if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; }
         __syncthreads();   // start of round: all groups aligned
+        // groups past the end re-evaluate the last zone (results discarded) so that every thread of the
+        // CTA reaches the DS_PHASE alignment points inside the evaluators
+        const int g = on ? gq : a.total_zones - 1;
         int star = 0, iz = 0, nz = 0;
         DsComp c{};
         double rho = 0.0, chi = 0.0, Tc[3] = {0.0, 0.0, 0.0};
-        if (on) {
+        {
             star = a.zone_star[g];
             iz = g - a.zone_offset[star];
             nz = a.zone_offset[star + 1] - a.zone_offset[star];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             else ds_sf_get_results(sf, 0.0, kn, Tc);
         }
         if (FACE) {
-            if (on && a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
+            if (a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
                 // impurity Coulomb logarithm: T-independent, once per zone (neutron_conductivity.f:382)
                 double nn = rho / dsc::amu * c.Yn / (1.0 - chi);
                 double lam;
@@ -162,15 +165,15 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             }
             __syncthreads();
         }
-        if (on) {
+        {
             DsEosRes r;
             ds_eval_crust_eos(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion,
                               (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
-            if (r.ierr != 0) s_err[grp] = r.ierr;
+            if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
                 s_v[grp][1][it] = dsm::log(r.Gamma);
-                if (iz == 0 && it == 0)  // create_model.f:367-369
+                if (on && iz == 0 && it == 0)  // create_model.f:367-369
                     a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
                 DsNeutrino eps;
                 dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             }
         }
         __syncthreads();
-        const size_t ob = (size_t)4 * DS_NTAB * (on ? g : 0);
+        const size_t ob = (size_t)4 * DS_NTAB * g;
         if (!FACE) {
             ds_group_interp_pm(on, it, s_x, s_v[grp][2], s_h[grp], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
             ds_group_interp_pm(on, it, s_x, s_v[grp][0], s_h[grp], s_m[grp], s_s[grp], a.tab_lnCp + ob);
@@ -214,7 +217,9 @@ struct DsEvalEosArgs {
 };
 __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
+    if (a.n <= 0) return;
+    const bool live = k < a.n;  // tail threads redo the last point and discard it (DS_PHASE needs all threads)
+    if (!live) k = a.n - 1;
     DsComp c = ds_load_comp(a.ionic + (size_t)11 * k);
     double rho = a.rho[k], T = a.T[k];
     double chi = a.chi_in ? a.chi_in[k] : -1.0;
@@ -222,7 +227,8 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     DsEosRes r;
     ds_eval_crust_eos(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
                       a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r,
-                      a.comps ? a.comps + (size_t)28 * k : nullptr);
+                      (a.comps && live) ? a.comps + (size_t)28 * k : nullptr);
+    if (!live) return;
     double* o = a.res + (size_t)15 * k;
     o[0] = r.lnP; o[1] = r.lnE; o[2] = r.lnS; o[3] = r.grad_ad; o[4] = r.chiRho; o[5] = r.chiT; o[6] = r.Cp;
     o[7] = r.Cv; o[8] = r.Chi; o[9] = r.Gamma; o[10] = r.Theta; o[11] = r.mu_e; o[12] = r.mu_n;
@@ -240,10 +246,13 @@ struct DsEvalNuArgs {
 };
 __global__ void ds_eval_nu_kernel(DsEvalNuArgs a) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
+    if (a.n <= 0) return;
+    const bool live = k < a.n;
+    if (!live) k = a.n - 1;
     DsNeutrino e;
     dsn::ds_crust_neutrino(a.rho[k], a.T[k], ds_load_comp(a.ionic + (size_t)11 * k), a.chi[k], a.Tcn[k],
                            a.channels, e);
+    if (!live) return;
     double* o = a.eps + (size_t)6 * k;
     o[0] = e.total; o[1] = e.pair; o[2] = e.photo; o[3] = e.plasma; o[4] = e.brems; o[5] = e.pbf;
 }
@@ -256,10 +265,13 @@ struct DsEvalCondArgs {
 };
 __global__ void ds_eval_cond_kernel(DsEvalCondArgs a) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
+    if (a.n <= 0) return;
+    const bool live = k < a.n;
+    if (!live) k = a.n - 1;
     DsCond c;
     dsk::ds_conductivity(a.cond, a.rho[k], a.T[k], a.chi[k], a.Gamma[k], a.eta[k], a.mu_e[k],
                          ds_load_comp(a.ionic + (size_t)11 * k), a.Tns[k], nan(""), 0, c);
+    if (!live) return;
     double* o = a.K + (size_t)10 * k;
     o[0] = c.total; o[1] = c.ee; o[2] = c.ei; o[3] = c.eQ; o[4] = c.sf; o[5] = c.nQ; o[6] = c.np; o[7] = c.kap;
     o[8] = c.electron_total; o[9] = c.neutron_total;

@@ -152,15 +152,21 @@ DS_D void ds_crust_neutrino(double rho, double T, const DsComp& c, double chi, d
     double rY = rho * c.Ye;
     double lambda = T / Tme;
     eps = DsNeutrino{0, 0, 0, 0, 0, 0};
+    DS_PHASE();
     if (ch[0]) eps.pair = pair(T, rY);
+    DS_PHASE();
     if (ch[1]) eps.photo = photo(rY, lambda);
+    DS_PHASE();
     if (ch[2]) eps.plasma = plasma(T, rY);
+    DS_PHASE();
     if (ch[3]) eps.brems = bremsstrahlung(rho, T, c);
+    DS_PHASE();
     if (ch[4]) {
         double nn = rho * c.Yn / amu / (1.0 - chi);
         double kn = dsm::pow(DS_R4(1.5) * (pi * pi) * nn, onethird) / cm_to_fm;
         eps.pbf = pbf(kn, T, Tcn);
     }
+    DS_PHASE();
     eps.total = eps.pair + eps.photo + eps.plasma + eps.brems + eps.pbf;
 }
 
