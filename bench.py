@@ -42,7 +42,7 @@ ARRS_GEOM = ["dm_bar", "area", "ePhi", "e2Phi", "ePhi_bar", "e2Phi_bar"]
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="custom_Tc_Qimp")
@@ -54,23 +54,66 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    NVML in-process (a few hundred samples per second, so even a 50 ms region is covered); falls back to an
+    `nvidia-smi -lms` child process when the NVML binding is unavailable.
+    """
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            self.index = int(vis.split(",")[index]) if vis else index
+        except (ValueError, IndexError):
+            self.index = index
+        self.sm, self.reasons, self.smax = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
         self.rows = []
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in self._BITS.items():
+                    if bits & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.sm.clear()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
 
@@ -79,8 +122,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.source == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -97,7 +145,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def dist_setup(args):

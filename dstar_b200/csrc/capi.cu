@@ -96,8 +96,20 @@ void fill_host_consts(DsHostConsts& h) {
     h.yfac = std::sqrt(4.0 * finestructure / pi);
     h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
 }
-int micro_minb() {  // tuning knob (experiments): CTAs per SM the coefficient-pass kernels are compiled for
-    static int v = [] { const char* e = std::getenv("DSTAR_MICRO_MINB"); return e ? std::atoi(e) : 6; }();
+template <bool FACE, int G>
+void launch_micro_g(int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+    ds_micro_kernel<FACE, G><<<std::min(sms, (total + G - 1) / G), DS_NTAB * G, 0, s>>>(a, h, sf);
+}
+template <bool FACE>
+void launch_micro(int G, int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+    switch (G) {
+        case 6: launch_micro_g<FACE, 6>(sms, total, s, a, h, sf); break;
+        default: launch_micro_g<FACE, 7>(sms, total, s, a, h, sf); break;
+    }
+}
+int micro_minb() {  // zone groups (of 128 lanes) per persistent CTA: 7 (default, 72 regs) or 6 (80 regs).
+    // B200, 144 stars: cell pass G=3 8.8 ms, 4 6.8, 5 5.7, 6 5.4, 7 5.2, 8 5.5 (profiles/r01_notes.md)
+    static int v = [] { const char* e = std::getenv("DSTAR_MICRO_MINB"); return e ? std::atoi(e) : 7; }();
     return v;
 }
 DsEosCtrl eos_ctrl_from(const dstar_micro_ctrl* c) {
@@ -475,10 +487,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
-            switch (micro_minb()) {
-                case 4: ds_micro_kernel<false, 4><<<std::min(sms, (b->total + 3) / 4), DS_NTAB * 4, 0, s>>>(a, c->helm, c->sf); break;
-                default: ds_micro_kernel<false, 6><<<std::min(sms, (b->total + 5) / 6), DS_NTAB * 6, 0, s>>>(a, c->helm, c->sf); break;
-            }
+            launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));
@@ -490,10 +499,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
-            switch (micro_minb()) {
-                case 4: ds_micro_kernel<true, 4><<<std::min(sms, (b->total + 3) / 4), DS_NTAB * 4, 0, s>>>(a, c->helm, c->sf); break;
-                default: ds_micro_kernel<true, 6><<<std::min(sms, (b->total + 5) / 6), DS_NTAB * 6, 0, s>>>(a, c->helm, c->sf); break;
-            }
+            launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));

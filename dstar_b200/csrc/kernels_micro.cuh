@@ -77,14 +77,12 @@ struct DsMicroArgs {
 };
 
 // MESA interp_pm (Steffen 1990) on one zone's 128 knots; i = knot index of this lane, v holds f(1,:) on entry.
-// Called by every thread of the CTA (the barriers are CTA-wide); `on` masks groups without a zone.
-DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ x, double* v, double* hh, double* sm,
+// hh[i] = x[i+1] - x[i] is common to all zones.  Called by every thread of the CTA (the barriers are CTA-wide);
+// `on` masks groups without a zone.
+DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, double* v, double* sm,
                              double* sl, double* __restrict__ out) {
     const int n = DS_NTAB;
-    if (on && i < n - 1) {
-        hh[i] = x[i + 1] - x[i];
-        sm[i] = (v[i + 1] - v[i]) / hh[i];
-    }
+    if (on && i < n - 1) sm[i] = (v[i + 1] - v[i]) / hh[i];
     __syncthreads();
     double s = 0.0;
     if (on) {
@@ -126,11 +124,11 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ x, doubl
 // 4*G warps of an SM walk through the code in lockstep and every instruction line is fetched once per SM.
 template <bool FACE, int G>
 __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
-    __shared__ double s_x[DS_NTAB], s_v[G][3][DS_NTAB], s_h[G][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
+    __shared__ double s_h[DS_NTAB], s_v[G][3][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G];
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
-    if (threadIdx.x < DS_NTAB) s_x[it] = a.tab_lnT[it];
+    if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
     for (int g0 = blockIdx.x * G; g0 < a.total_zones; g0 += gridDim.x * G) {
         const int gq = g0 + grp;
@@ -194,11 +192,11 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         __syncthreads();
         const size_t ob = (size_t)4 * DS_NTAB * g;
         if (!FACE) {
-            ds_group_interp_pm(on, it, s_x, s_v[grp][2], s_h[grp], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
-            ds_group_interp_pm(on, it, s_x, s_v[grp][0], s_h[grp], s_m[grp], s_s[grp], a.tab_lnCp + ob);
-            ds_group_interp_pm(on, it, s_x, s_v[grp][1], s_h[grp], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
+            ds_group_interp_pm(on, it, s_h, s_v[grp][2], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
+            ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
+            ds_group_interp_pm(on, it, s_h, s_v[grp][1], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
         } else {
-            ds_group_interp_pm(on, it, s_x, s_v[grp][0], s_h[grp], s_m[grp], s_s[grp], a.tab_lnK + ob);
+            ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
         }
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
     }
