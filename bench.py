@@ -407,7 +407,7 @@ def cpu_baseline(stars, H, zoff, args, threads, budget_s):
         rs = list(ex.map(one, range(n)))
     wall = time.perf_counter() - t0
     evals = sum(r[2] for r in rs)
-    return {"value": evals / wall, "unit": UNIT, "cores": threads, "kind": "port",
+    return {"value": evals / wall, "unit": UNIT, "cores": min(threads, n), "kind": "port",
             "sample": "%d of %d stars of the same workload (full coefficient pass + light curve each), oracle C++ -O2, %d thread(s)"
                       % (n, len(stars), threads),
             "curves_per_sec": n / wall, "seconds": wall,
@@ -427,15 +427,18 @@ def run_reference(args):
     ds.NScool_init(device=0)          # input generation only (structure of the sample stars); untimed
     threads = os.cpu_count() or 1
     a2 = argparse.Namespace(**vars(args))
-    a2.stars = 16 if args.workload != "basic_run" else 1
+    side = int(np.ceil(np.sqrt(min(threads, 64))))        # the sweep builders want a square grid of stars
+    a2.stars = side * side if args.workload != "basic_run" else 1
     stars = build_stars(ds, a2, 0)
     nz, zoff, H = gather_host_inputs(stars)
-    n_sample = min(len(stars), threads)
+    n_sample = min(len(stars), threads)                   # one star per host thread
     a2.cpu_sample_stars = n_sample
-    for _ in range(min(args.warmup, 1)):
+    # one step = the bounded sample (<= 16 stars, at most one per host thread: ~1.3 s), so W + K steps stay
+    # within a few minutes for any reasonable K
+    for _ in range(args.warmup):
         cpu_baseline(stars, H, zoff, a2, threads=threads, budget_s=0)
     vals, secs = [], []
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(max(1, args.steps)):
         r = cpu_baseline(stars, H, zoff, a2, threads=threads, budget_s=0)
         vals.append(r["value"]); secs.append(r["seconds"])
     v = float(np.mean(vals))
