@@ -63,82 +63,91 @@ DS_D double neutron_wavenumber(double rho, const DsComp& c, double chi) {
     return dsm::pow(threepisquare * n, onethird) / cm_to_fm;
 }
 
-DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
+template <bool FAST>
+DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     // theta_fac = 2.0*(4.0/9.0/pi)**(2.0/3.0): 4.0/9.0 and 2.0/3.0 are REAL(4) operations
     const double theta_fac = ds_hc.theta_fac;
     const double theta_low = DS_R4(0.005);
-    double theta = theta_fac * rs / Gamma_e;
+    const DsDen<FAST> Gamma_eD = den(Gamma_e);
+    double theta = theta_fac * rs / Gamma_eD;
     double sqth = sqrt(theta);
     double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta3 * theta;
+    const DsDen<FAST> thetaD = den(theta), theta2D = den(theta2);
     double t1, t2, t1_h, t2_h, t1_hh, t2_hh;
     if (theta > theta_low) {
-        double cht1 = dsm::cosh(1.0 / theta), sht1 = dsm::sinh(1.0 / theta);
-        double cht2 = dsm::cosh(1.0 / sqth), sht2 = dsm::sinh(1.0 / sqth);
-        t1 = sht1 / cht1;
-        t2 = sht2 / cht2;
+        double cht1 = dsm::cosh(1.0 / thetaD), sht1 = dsm::sinh(1.0 / thetaD);
+        double cht2 = dsm::cosh(1.0 / den(sqth)), sht2 = dsm::sinh(1.0 / den(sqth));
+        t1 = sht1 / den(cht1);
+        t2 = sht2 / den(cht2);
+        // (theta cosh(1/theta))^3 reaches 1e260 just above theta_low: these four stay plain divisions
         t1_h = -1.0 / dsd::ipow<2>(theta * cht1);
-        t1_hh = 2.0 / dsd::ipow<3>(theta * cht1) * (cht1 - sht1 / theta);
+        t1_hh = 2.0 / dsd::ipow<3>(theta * cht1) * (cht1 - sht1 / thetaD);
         t2_h = -0.5 * sqth / dsd::ipow<2>(theta * cht2);
         t2_hh = (0.75 * sqth * cht2 - 0.5 * sht2) / dsd::ipow<3>(theta * cht2);
     } else {
         t1 = 1.0; t2 = 1.0; t1_h = 0.0; t2_h = 0.0; t1_hh = 0.0; t2_hh = 0.0;
     }
-    double a0 = 0.75 + DS_R4(3.04363) * theta2 - DS_R4(0.09227) * theta3 + DS_R4(1.7035) * theta4;
+    const DsDen<FAST> t1D = den(t1), t2D = den(t2);
+    const DsDen<FAST> a0 = den(0.75 + DS_R4(3.04363) * theta2 - DS_R4(0.09227) * theta3 + DS_R4(1.7035) * theta4);
     double a0_h = DS_R4(6.08726) * theta - DS_R4(0.27681) * theta2 + DS_R4(6.814) * theta3;
     double a0_hh = DS_R4(6.08726) - DS_R4(0.55362) * theta + DS_R4(20.442) * theta2;
-    double a1 = 1. + DS_R4(8.31051) * theta2 + DS_R4(5.1105) * theta4;
+    const DsDen<FAST> a1 = den(1. + DS_R4(8.31051) * theta2 + DS_R4(5.1105) * theta4);
     double a1_h = DS_R4(16.62102) * theta + DS_R4(20.442) * theta3;
     double a1_hh = DS_R4(16.62102) + DS_R4(61.326) * theta2;
     double a = DS_R4(0.610887) * a0 / a1 * t1;
-    double ah = a0_h / a0 - a1_h / a1 + t1_h / t1;
+    double ah = a0_h / a0 - a1_h / a1 + t1_h / t1D;
     double a_h = a * ah;
     double a_hh = a_h * ah + a * (a0_hh / a0 - dsd::ipow<2>(a0_h / a0) - a1_hh / a1 + dsd::ipow<2>(a1_h / a1) +
-                                  t1_hh / t1 - dsd::ipow<2>(t1_h / t1));
+                                  t1_hh / t1D - dsd::ipow<2>(t1_h / t1D));
 
     DS_PHASE();
-    double b0 = DS_R4(0.341308) + DS_R4(12.070873) * theta2 + DS_R4(1.148889) * theta4;
+    const DsDen<FAST> b0 = den(DS_R4(0.341308) + DS_R4(12.070873) * theta2 + DS_R4(1.148889) * theta4);
     double b0_h = DS_R4(24.141746) * theta + DS_R4(4.595556) * theta3;
     double b0_hh = DS_R4(24.141746) + DS_R4(13.786668) * theta2;
-    double b1 = 1.0 + DS_R4(10.495346) * theta2 + DS_R4(1.326623) * theta4;
+    const DsDen<FAST> b1 = den(1.0 + DS_R4(10.495346) * theta2 + DS_R4(1.326623) * theta4);
     double b1_h = DS_R4(20.990692) * theta + DS_R4(5.306492) * theta3;
     double b1_hh = DS_R4(20.990692) + DS_R4(15.919476) * theta2;
     double b = sqth * t2 * b0 / b1;
-    double bh = 0.5 / theta + t2_h / t2 + b0_h / b0 - b1_h / b1;
+    double bh = 0.5 / thetaD + t2_h / t2D + b0_h / b0 - b1_h / b1;
     double b_h = b * bh;
-    double b_hh = b_h * bh + b * (-0.5 / theta2 + t2_hh / t2 - dsd::ipow<2>(t2_h / t2) + b0_hh / b0 -
+    double b_hh = b_h * bh + b * (-0.5 / theta2D + t2_hh / t2D - dsd::ipow<2>(t2_h / t2D) + b0_hh / b0 -
                                   dsd::ipow<2>(b0_h / b0) - b1_hh / b1 + dsd::ipow<2>(b1_h / b1));
 
-    double d0 = DS_R4(0.614925) + DS_R4(16.996055) * theta2 + DS_R4(1.489056) * theta4;
+    const DsDen<FAST> d0 = den(DS_R4(0.614925) + DS_R4(16.996055) * theta2 + DS_R4(1.489056) * theta4);
     double d0_h = DS_R4(33.99211) * theta + DS_R4(5.956224) * theta3;
     double d0_hh = DS_R4(33.99211) + DS_R4(17.868672) * theta2;
-    double d1 = 1.0 + DS_R4(10.10935) * theta2 + DS_R4(1.22184) * theta4;
+    const DsDen<FAST> d1 = den(1.0 + DS_R4(10.10935) * theta2 + DS_R4(1.22184) * theta4);
     double d1_h = DS_R4(20.2187) * theta + DS_R4(4.88736) * theta3;
     double d1_hh = DS_R4(20.2187) + DS_R4(14.66208) * theta2;
     double d = sqth * t2 * d0 / d1;
-    double dh = 0.5 / theta + t2_h / t2 + d0_h / d0 - d1_h / d1;
+    double dh = 0.5 / thetaD + t2_h / t2D + d0_h / d0 - d1_h / d1;
     double d_h = d * dh;
-    double d_hh = d_h * dh + d * (-0.5 / theta2 + t2_hh / t2 - dsd::ipow<2>(t2_h / t2) + d0_hh / d0 -
+    double d_hh = d_h * dh + d * (-0.5 / theta2D + t2_hh / t2D - dsd::ipow<2>(t2_h / t2D) + d0_hh / d0 -
                                   dsd::ipow<2>(d0_h / d0) - d1_hh / d1 + dsd::ipow<2>(d1_h / d1));
 
     DS_PHASE();
-    double e0 = DS_R4(0.539409) + DS_R4(2.522206) * theta2 + DS_R4(0.178484) * theta4;
+    const DsDen<FAST> e0 = den(DS_R4(0.539409) + DS_R4(2.522206) * theta2 + DS_R4(0.178484) * theta4);
     double e0_h = DS_R4(5.044412) * theta + DS_R4(0.713936) * theta3;
     double e0_hh = DS_R4(5.044412) + DS_R4(2.141808) * theta2;
-    double e1 = 1.0 + DS_R4(2.555501) * theta2 + DS_R4(0.146319) * theta4;
+    const DsDen<FAST> e1 = den(1.0 + DS_R4(2.555501) * theta2 + DS_R4(0.146319) * theta4);
     double e1_h = DS_R4(5.111002) * theta + DS_R4(0.585276) * theta3;
     double e1_hh = DS_R4(5.111002) + DS_R4(1.755828) * theta2;
-    double e = theta * t1 * e0 / e1;
-    double eh = 1.0 / theta + t1_h / t1 + e0_h / e0 - e1_h / e1;
+    const DsDen<FAST> e = den(theta * t1 * e0 / e1);
+    const DsDen<FAST> e2D = den(e * e);
+    double eh = 1.0 / thetaD + t1_h / t1D + e0_h / e0 - e1_h / e1;
     double e_h = e * eh;
-    double e_hh = e_h * eh + e * (t1_hh / t1 - dsd::ipow<2>(t1_h / t1) + e0_hh / e0 - dsd::ipow<2>(e0_h / e0) -
-                                  e1_hh / e1 + dsd::ipow<2>(e1_h / e1) - 1.0 / theta2);
+    double e_hh = e_h * eh + e * (t1_hh / t1D - dsd::ipow<2>(t1_h / t1D) + e0_hh / e0 - dsd::ipow<2>(e0_h / e0) -
+                                  e1_hh / e1 + dsd::ipow<2>(e1_h / e1) - 1.0 / theta2D);
 
-    double exp1th = dsm::exp(-1.0 / theta);
-    double c = (DS_R4(0.872496) + DS_R4(0.025248) * exp1th) * e;
+    double exp1th = dsm::exp(-1.0 / thetaD);
+    const DsDen<FAST> c = den((DS_R4(0.872496) + DS_R4(0.025248) * exp1th) * e);
+    // exp(-1/theta) runs down to 1e-300 in the crust: its two quotients stay plain divisions (a branch-free one
+    // would flag every lane with theta in (0.0013, 0.0017) and send the whole CTA through the re-evaluation)
     double c_h = DS_R4(0.025248) * exp1th / theta2 * e + c * e_h / e;
-    double c_hh = DS_R4(0.025248) * exp1th / theta2 * (e_h + (1.0 - 2.0 * theta) / theta2 * e) +
+    double c_hh = DS_R4(0.025248) * exp1th / theta2 * (e_h + (1.0 - 2.0 * theta) / theta2D * e) +
                   c_h * e_h / e + c * e_hh / e - c * dsd::ipow<2>(e_h / e);
-    double discr = sqrt(4.0 * e - d * d);
+    const DsDen<FAST> discr = den(sqrt(4.0 * e - d * d));
     double di_h = 0.5 / discr * (4.0 * e_h - 2.0 * d * d_h);
     double di_hh = (-dsd::ipow<2>((2.0 * e_h - d * d_h) / discr) + 2.0 * e_hh - d_h * d_h - d * d_hh) / discr;
 
@@ -150,37 +159,37 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double s1_g = -c / e;
     double s1_hg = s1_g * (c_h / c - e_h / e);
     DS_PHASE();
-    double b2 = b - c * d / e;
-    double b2_h = b_h - (c_h * d + c * d_h) / e + c * d * e_h / (e * e);
+    const DsDen<FAST> b2 = den(b - c * d / e);
+    double b2_h = b_h - (c_h * d + c * d_h) / e + c * d * e_h / e2D;
     double b2_hh = b_hh - (c_hh * d + 2.0 * c_h * d_h + c * d_hh) / e +
-                   (2.0 * (c_h * d + c * d_h - c * d * e_h / e) * e_h + c * d * e_hh) / (e * e);
+                   (2.0 * (c_h * d + c * d_h - c * d * e_h / e) * e_h + c * d * e_hh) / e2D;
 
-    double sqge = sqrt(Gamma_e);
+    const DsDen<FAST> sqge = den(sqrt(Gamma_e));
     double s2 = -2.0 / e * b2 * sqge;
     double s2h = b2_h / b2 - e_h / e;
     double s2_h = s2 * s2h;
     double s2_hh = s2_h * s2h + s2 * (b2_hh / b2 - dsd::ipow<2>(b2_h / b2) - e_hh / e + dsd::ipow<2>(e_h / e));
-    double s2_g = 0.5 * s2 / Gamma_e;
-    double s2_gg = -0.5 * s2_g / Gamma_e;
-    double s2_hg = 0.5 * s2_h / Gamma_e;
+    double s2_g = 0.5 * s2 / Gamma_eD;
+    double s2_gg = -0.5 * s2_g / Gamma_eD;
+    double s2_hg = 0.5 * s2_h / Gamma_eD;
 
-    double r3 = e * Gamma_e + d * sqge + 1.0;
+    const DsDen<FAST> r3 = den(e * Gamma_e + d * sqge + 1.0);
     double r3_h = e_h * Gamma_e + d_h * sqge;
     double r3_hh = e_hh * Gamma_e + d_hh * sqge;
     double r3_g = e + 0.5 * d / sqge;
-    double r3_gg = -0.25 * d / (Gamma_e * sqge);
+    double r3_gg = -0.25 * d / den(Gamma_e * sqge);
     double r3_hg = e_h + 0.5 * d_h / sqge;
 
     DS_PHASE();
     double b3 = a - c / e;
-    double b3_h = a_h - c_h / e + c * e_h / (e * e);
-    double b3_hh = a_hh - c_hh / e + (2.0 * c_h * e_h + c * e_hh) / (e * e) - 2.0 * c * (e_h * e_h) / dsd::ipow<3>(e);
+    double b3_h = a_h - c_h / e + c * e_h / e2D;
+    double b3_hh = a_hh - c_hh / e + (2.0 * c_h * e_h + c * e_hh) / e2D - 2.0 * c * (e_h * e_h) / den(dsd::ipow<3>(e));
 
-    double c3 = (d / e * b2 - b3) / e;
-    double c3_h = (d_h * b2 + d * b2_h + b3 * e_h) / (e * e) - 2.0 * d * b2 * e_h / dsd::ipow<3>(e) - b3_h / e;
+    const DsDen<FAST> c3 = den((d / e * b2 - b3) / e);
+    double c3_h = (d_h * b2 + d * b2_h + b3 * e_h) / e2D - 2.0 * d * b2 * e_h / den(dsd::ipow<3>(e)) - b3_h / e;
     double c3_hh = (-b3_hh + (d_hh * b2 + 2.0 * d_h * b2_h + d * b2_hh + b3_h * e_h + b3 * e_hh + b3_h * e_h) / e -
-                    2.0 * ((d_h * b2 + d * b2_h + b3 * e_h + d_h * b2 + d * b2_h) * e_h + d * b2 * e_hh) / (e * e) +
-                    6.0 * d * b2 * (e_h * e_h) / dsd::ipow<3>(e)) / e;
+                    2.0 * ((d_h * b2 + d * b2_h + b3 * e_h + d_h * b2 + d * b2_h) * e_h + d * b2 * e_hh) / e2D +
+                    6.0 * d * b2 * (e_h * e_h) / den(dsd::ipow<3>(e))) / e;
 
     double s3 = c3 * dsm::log(r3);
     double s3_h = s3 * c3_h / c3 + c3 * r3_h / r3;
@@ -188,19 +197,19 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
                    (c3_h * r3_h + c3 * r3_hh) / r3 - c3 * dsd::ipow<2>(r3_h / r3);
     double s3_g = c3 * r3_g / r3;
     double s3_gg = c3 * (r3_gg / r3 - dsd::ipow<2>(r3_g / r3));
-    double s3_hg = (c3_h * r3_g + c3 * r3_hg) / r3 - c3 * r3_g * r3_h / (r3 * r3);
+    double s3_hg = (c3_h * r3_g + c3 * r3_hg) / r3 - c3 * r3_g * r3_h / den(r3 * r3);
 
     DS_PHASE();
     double b4 = 2.0 - d * d / e;
     double b4_h = e_h * dsd::ipow<2>(d / e) - 2.0 * d * d_h / e;
-    double b4_hh = e_hh * dsd::ipow<2>(d / e) + 2.0 * e_h * dsd::ipow<2>(d / e) * (d_h / d - e_h / e) -
-                   2.0 * (d_h * d_h + d * d_hh) / e + 2. * d * d_h * e_h / (e * e);
+    double b4_hh = e_hh * dsd::ipow<2>(d / e) + 2.0 * e_h * dsd::ipow<2>(d / e) * (d_h / den(d) - e_h / e) -
+                   2.0 * (d_h * d_h + d * d_hh) / e + 2. * d * d_h * e_h / e2D;
 
     double c4 = 2.0 * e * sqge + d;
     double c4_h = 2.0 * e_h * sqge + d_h;
     double c4_hh = 2.0 * e_hh * sqge + d_hh;
     double c4_g = e / sqge;
-    double c4_gg = -0.5 * e / (Gamma_e * sqge);
+    double c4_gg = -0.5 * e / den(Gamma_e * sqge);
     double c4_hg = e_h / sqge;
 
     DS_PHASE();
@@ -213,12 +222,12 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double s4b_hh = d_hh * b3 + 2.0 * d_h * b3_h + d * b3_hh + b4_hh * b2 + 2. * b4_h * b2_h + b4 * b2_hh;
     double s4c = dsm::atan(c4 / discr) - dsm::atan(d / discr);
     double up1 = c4_h * discr - c4 * di_h;
-    double dn1 = discr * discr + c4 * c4;
+    const DsDen<FAST> dn1 = den(discr * discr + c4 * c4);
     double up2 = d_h * discr - d * di_h;
     double dn2 = discr * discr + d * d;
-    double s4c_h = up1 / dn1 - up2 / dn2;
-    double s4c_hh = (c4_hh * discr - c4 * di_hh) / dn1 - up1 * 2.0 * (discr * di_h + c4 * c4_h) / (dn1 * dn1) -
-                    (d_hh * discr - d * di_hh) / dn2 + up2 * 2.0 * (discr * di_h + d * d_h) / (dn2 * dn2);
+    double s4c_h = up1 / dn1 - up2 / den(dn2);
+    double s4c_hh = (c4_hh * discr - c4 * di_hh) / dn1 - up1 * 2.0 * (discr * di_h + c4 * c4_h) / den(dn1 * dn1) -
+                    (d_hh * discr - d * di_hh) / den(dn2) + up2 * 2.0 * (discr * di_h + d * d_h) / den(dn2 * dn2);
     double s4c_g = c4_g * discr / dn1;
     double s4c_gg = c4_gg * discr / dn1 - 2.0 * c4 * discr * dsd::ipow<2>(c4_g / dn1);
     double s4c_hg = (c4_hg * discr + c4_g * di_h - c4_g * discr / dn1 * 2. * (discr * di_h + c4 * c4_h)) / dn1;
@@ -247,18 +256,22 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r) {
     double pdlh = onethird * theta * (Gamma_e * f_hg - 2.0 * f_h - 2.0 * theta * f_hh);
     double pdlg = onethird * Gamma_e * (f_g + Gamma_e * f_gg - 2.0 * theta * f_hg);
     double dpr = p + onethird * (pdlg - 2.0 * pdlh);
-    double dpt = Gamma_e * (theta * f_hg - onethird * Gamma_e * f_gg) - theta * (f_h / 0.75 + theta * f_hh / 1.5);
+    double dpt = Gamma_e * (theta * f_hg - onethird * Gamma_e * f_gg) - theta * (f_h / den(0.75) + theta * f_hh / den(1.5));
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
+    bad |= ds_den_bad;
 }
 
-DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
+template <bool FAST>
+DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double s3 = (double)sqrtf(3.0f);
     const double CTFfac = ds_hc.ctf_fac;
     double Z13 = dsm::pow(Z, onethird);
-    double cDH = (Z / s3) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
-    double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / sqrt(Z13));
+    double cDH = (Z / den(s3)) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
+    double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / den(sqrt(Z13)));
     double xrs = ds_hc.xrs;
-    double xr = xrs / rs;
+    const DsDen<FAST> rsD = den(rs), Gamma_eD = den(Gamma_e);
+    const DsDen<FAST> xr = den(xrs / rsD);
     double lZ = dsm::log(Z);
 
     double a = DS_R4(1.11) * dsm::pow(Z, DS_R4(0.475));
@@ -266,48 +279,48 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
     double nu = DS_R4(1.16) + DS_R4(0.08) * lZ;
     double sGam = sqrt(Gamma_e);
     double nuGam = dsm::pow(Gamma_e, nu);
-    double nuGam_g = nu * nuGam / Gamma_e;
-    double nuGam_gg = (nu - 1.0) * nuGam_g / Gamma_e;
-    double ty1 = 1.0 / (DS_R4(0.001) * (Z * Z) + 2.0 * Gamma_e);
+    double nuGam_g = nu * nuGam / Gamma_eD;
+    double nuGam_gg = (nu - 1.0) * nuGam_g / Gamma_eD;
+    double ty1 = 1.0 / den(DS_R4(0.001) * (Z * Z) + 2.0 * Gamma_e);
     double ty1_g = -2.0 * (ty1 * ty1);
     double ty1_gg = -4.0 * ty1 * ty1_g;
     double rs2 = rs * rs, rs3 = rs * rs * rs;
-    double ty2 = 1.0 + 6.0 * rs2;
+    const DsDen<FAST> ty2 = den(1.0 + 6.0 * rs2);
     double ty2_x = -12.0 * rs2 / xr;
     double ty2_xx = -3.0 * ty2_x / xr;
     double ty = rs3 / ty2 * (1.0 + ty1);
     double tyx = 3.0 / xr + ty2_x / ty2;
     double ty_x = -ty * tyx;
     double ty_g = rs3 * ty1_g / ty2;
-    double p1 = (Z - 1.0) / 9.0;
+    double p1 = (Z - 1.0) / den(9.0);
     double cor1 = 1.0 + p1 * ty;
     double cor1_x = p1 * ty_x;
     double cor1_g = p1 * ty_g;
-    double cor1_xx = p1 * (ty * (3.0 / (xr * xr) + dsd::ipow<2>(ty2_x / ty2) - ty2_xx / ty2) - ty_x * tyx);
+    double cor1_xx = p1 * (ty * (3.0 / den(xr * xr) + dsd::ipow<2>(ty2_x / ty2) - ty2_xx / ty2) - ty_x * tyx);
     double cor1_gg = p1 * rs3 * ty1_gg / ty2;
     double cor1_xg = -p1 * ty_g * tyx;
-    double u0 = DS_R4(0.78) * sqrt(Gamma_e / Z) * rs3;
+    double u0 = DS_R4(0.78) * sqrt(Gamma_e / den(Z)) * rs3;
     double u0_x = -3.0 * u0 / xr;
-    double u0_g = 0.5 * u0 / Gamma_e;
+    double u0_g = 0.5 * u0 / Gamma_eD;
     double u0_xx = -4.0 * u0_x / xr;
-    double u0_gg = -0.5 * u0_g / Gamma_e;
+    double u0_gg = -0.5 * u0_g / Gamma_eD;
     double u0_xg = -3.0 * u0_g / xr;
     double d0_g = Z * Z * Z;
-    double d0 = Gamma_e * d0_g + 21.0 * rs3;
+    const DsDen<FAST> d0 = den(Gamma_e * d0_g + 21.0 * rs3);
     double d0_x = -63.0 * rs3 / xr;
-    double d0_xx = 252.0 * rs3 / (xr * xr);
+    double d0_xx = 252.0 * rs3 / den(xr * xr);
     double cor0 = 1.0 + u0 / d0;
     double cor0_x = (u0_x - u0 * d0_x / d0) / d0;
     double cor0_g = (u0_g - u0 * d0_g / d0) / d0;
     double cor0_xx = (u0_xx - (2.0 * u0_x * d0_x + u0 * d0_xx) / d0 + 2.0 * dsd::ipow<2>(d0_x / d0)) / d0;
     double cor0_gg = (u0_gg - 2.0 * u0_g * d0_g / d0 + 2.0 * u0 * dsd::ipow<2>(d0_g / d0)) / d0;
-    double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / (d0 * d0)) / d0;
+    double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / den(d0 * d0)) / d0;
 
-    double rgam = sqrt(1.0 + xr * xr);
-    double q1 = DS_R4(0.18) / dsm::pow(Z, 0.25);
-    double q2 = DS_R4(0.2) + DS_R4(0.37) / sqrt(Z);
-    double h1u = 1.0 + DS_R4(0.2) * (xr * xr);
-    double h1d = 1.0 + q1 * xr + q2 * (xr * xr);
+    const DsDen<FAST> rgam = den(sqrt(1.0 + xr * xr));
+    double q1 = DS_R4(0.18) / den(dsm::pow(Z, 0.25));
+    double q2 = DS_R4(0.2) + DS_R4(0.37) / den(sqrt(Z));
+    const DsDen<FAST> h1u = den(1.0 + DS_R4(0.2) * (xr * xr));
+    const DsDen<FAST> h1d = den(1.0 + q1 * xr + q2 * (xr * xr));
     double h1 = h1u / h1d;
     double h1x = DS_R4(0.4) * xr / h1u - (q1 + 2. * q2 * xr) / h1d;
     double h1_x = h1 * h1x;
@@ -315,24 +328,24 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
                                       dsd::ipow<2>((q1 + 2. * q2 * xr) / h1d));
     double up = cDH * sGam + a * cTF * nuGam * cor0 * h1;
     double up_x = a * cTF * nuGam * (cor0_x * h1 + cor0 * h1_x);
-    double up_g = 0.5 * cDH / sGam + a * cTF * (nuGam_g * cor0 + nuGam * cor0_g) * h1;
+    double up_g = 0.5 * cDH / den(sGam) + a * cTF * (nuGam_g * cor0 + nuGam * cor0_g) * h1;
     double up_xx = a * cTF * nuGam * (cor0_xx * h1 + 2. * cor0_x * h1_x + cor0 * h1_xx);
-    double up_gg = -0.25 * cDH / (sGam * Gamma_e) +
+    double up_gg = -0.25 * cDH / den(sGam * Gamma_e) +
                    a * cTF * (nuGam_gg * cor0 + 2.0 * nuGam_g * cor0_g + nuGam * cor0_gg) * h1;
     double up_xg = a * cTF * (nuGam_g * (cor0_x * h1 + cor0 * h1_x) + nuGam * (cor0_xg * h1 + cor0_g * h1_x));
-    double dn1 = b * sGam + a / rs * nuGam * cor1;
-    double dn1_x = a * nuGam * (cor1 / xrs + cor1_x / rs);
-    double dn1_g = 0.5 * b / sGam + a / rs * (nuGam_g * cor1 + nuGam * cor1_g);
-    double dn1_xx = a * nuGam / xrs * (2. * cor1_x + xr * cor1_xx);
-    double dn1_gg = -0.25 * b / (Gamma_e * sGam) +
-                    a / rs * (nuGam_gg * cor1 + 2. * nuGam_g * cor1_g + nuGam * cor1_gg);
-    double dn1_xg = a * (nuGam_g * (cor1 / xrs + cor1_x / rs) + nuGam * (cor1_g / xrs + cor1_xg / rs));
-    double dn = 1.0 + dn1 / rgam;
-    double dn_x = dn1_x / rgam - xr * dn1 / dsd::ipow<3>(rgam);
-    double dn_xx = (dn1_xx - ((2. * xr * dn1_x + dn1) - 3. * (xr * xr) * dn1 / (rgam * rgam)) / (rgam * rgam)) / rgam;
+    double dn1 = b * sGam + a / rsD * nuGam * cor1;
+    double dn1_x = a * nuGam * (cor1 / den(xrs) + cor1_x / rsD);
+    double dn1_g = 0.5 * b / den(sGam) + a / rsD * (nuGam_g * cor1 + nuGam * cor1_g);
+    double dn1_xx = a * nuGam / den(xrs) * (2. * cor1_x + xr * cor1_xx);
+    double dn1_gg = -0.25 * b / den(Gamma_e * sGam) +
+                    a / rsD * (nuGam_gg * cor1 + 2. * nuGam_g * cor1_g + nuGam * cor1_gg);
+    double dn1_xg = a * (nuGam_g * (cor1 / den(xrs) + cor1_x / rsD) + nuGam * (cor1_g / den(xrs) + cor1_xg / rsD));
+    const DsDen<FAST> dn = den(1.0 + dn1 / rgam);
+    double dn_x = dn1_x / rgam - xr * dn1 / den(dsd::ipow<3>(rgam));
+    double dn_xx = (dn1_xx - ((2. * xr * dn1_x + dn1) - 3. * (xr * xr) * dn1 / den(rgam * rgam)) / den(rgam * rgam)) / rgam;
     double dn_g = dn1_g / rgam;
     double dn_gg = dn1_gg / rgam;
-    double dn_xg = dn1_xg / rgam - xr * dn1_g / dsd::ipow<3>(rgam);
+    double dn_xg = dn1_xg / rgam - xr * dn1_g / den(dsd::ipow<3>(rgam));
     double f = -up / dn * Gamma_e;
     double fx = (up * dn_x / dn - up_x) / dn;
     double fx_g = ((up_g * dn_x + up_x * dn_g + up * dn_xg - 2.0 * up * dn_x * dn_g / dn) / dn - up_xg) / dn;
@@ -347,55 +360,58 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r) {
     double cv = -(Gamma_e * Gamma_e) * f_gg;
     double p = onethird * (xr * f_x + Gamma_e * f_g);
     double dpt = -(Gamma_e * Gamma_e) * (xr * fx_g + f_gg) * onethird;
-    double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma_e * f_xg + (Gamma_e * Gamma_e) * f_gg) / 9.0;
+    double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma_e * f_xg + (Gamma_e * Gamma_e) * f_gg) / den(9.0);
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
+    bad |= ds_den_bad;
 }
 
-DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& r) {
+template <bool FAST>
+DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double a[4] = {DS_R4(1.1866), DS_R4(0.684), DS_R4(17.9), DS_R4(41.5)};
     const double px = DS_R4(0.205);
     double e1 = ds_hc.e1;
     double aTF = ds_hc.atf;
     double xrs = ds_hc.xrs;
-    double xr = xrs / rs;
+    const DsDen<FAST> xr = den(xrs / den(rs));
     double lZ = dsm::log(Z);
-    double r3 = 1.0 / (1.0 + DS_R4(0.01) * dsm::pow(lZ, 1.5) + DS_R4(0.097) / (Z * Z));
+    double r3 = 1.0 / den(1.0 + DS_R4(0.01) * dsm::pow(lZ, 1.5) + DS_R4(0.097) / (Z * Z));
     double b[4];
-    b[0] = 1.0 - a[0] / dsm::pow(Z, DS_R4(0.267)) + DS_R4(0.27) / Z;
-    b[1] = 1.0 + 2.25 / dsm::pow(Z, onethird) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
+    b[0] = 1.0 - a[0] / den(dsm::pow(Z, DS_R4(0.267))) + DS_R4(0.27) / den(Z);
+    b[1] = 1.0 + 2.25 / den(dsm::pow(Z, onethird)) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
                      (1.0 + DS_R4(0.222) * dsd::ipow<6>(Z));
-    b[2] = a[3] / (1.0 + lZ);
-    b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / dsm::pow(Z, 1.5);
+    b[2] = a[3] / den(1.0 + lZ);
+    b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / den(dsm::pow(Z, 1.5));
 
-    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sqrt(1.0 + b[1] / (xr * xr));
-    double finfx = -b[1] / ((b[1] + xr * xr) * xr);
+    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sqrt(1.0 + b[1] / den(xr * xr));
+    double finfx = -b[1] / den((b[1] + xr * xr) * xr);
     double finf_x = finf * finfx;
-    double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / ((b[1] + xr * xr) * xr);
+    double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / den((b[1] + xr * xr) * xr);
 
     double q1u = b[2] + a[2] * (xr * xr);
-    double q1d = 1.0 + b[3] * (xr * xr);
+    const DsDen<FAST> q1d = den(1.0 + b[3] * (xr * xr));
     double q1 = q1u / q1d;
-    double q1x = 2.0 * xr * (a[2] / q1u - b[3] / q1d);
-    double q1x_x = q1x / xr + 4.0 * (xr * xr) * (dsd::ipow<2>(b[3] / q1d) - dsd::ipow<2>(a[2] / q1u));
+    double q1x = 2.0 * xr * (a[2] / den(q1u) - b[3] / q1d);
+    double q1x_x = q1x / xr + 4.0 * (xr * xr) * (dsd::ipow<2>(b[3] / q1d) - dsd::ipow<2>(a[2] / den(q1u)));
     double q1_x = q1 * q1x;
     double q1_xx = q1_x * q1x + q1 * q1x_x;
 
     double sup, sup_x, sup_g, sup_xx, sup_gg, sup_xg;
-    if (theta < 6.0 / px) {
+    if (theta < 6.0 / den(px)) {
         double y0 = dsd::ipow<2>(px * theta);
         double y0_x = y0 / xr;
-        double y0_g = 2.0 * y0 / Gamma;
+        double y0_g = 2.0 * y0 / den(Gamma);
         double y0_xx = 0.0;
-        double y0_gg = y0_g / Gamma;
+        double y0_gg = y0_g / den(Gamma);
         double y0_xg = y0_g / xr;
-        double y1 = dsm::exp(y0);
+        const DsDen<FAST> y1 = den(dsm::exp(y0));
         double y1_x = y1 * y0_x;
         double y1_g = y1 * y0_g;
         double y1_xx = y1 * (y0_x * y0_x + y0_xx);
         double y1_gg = y1 * (y0_g * y0_g + y0_gg);
         double y1_xg = y1 * (y0_x * y0_g + y0_xg);
-        double sa = 1.0 + y1;
-        double supa = dsm::log(sa);
+        const DsDen<FAST> sa = den(1.0 + y1);
+        const DsDen<FAST> supa = den(dsm::log(sa));
         double supa_x = y1_x / sa;
         double supa_g = y1_g / sa;
         double supa_xx = (y1_xx - y1_x * y1_x / sa) / sa;
@@ -403,8 +419,8 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
         double supa_xg = (y1_xg - y1_x * y1_g / sa) / sa;
         double em2 = e1 - 2.0;
         double sb = e1 - em2 / y1;
-        double supb = dsm::log(sb);
-        double em2y1 = em2 / ((y1 * y1) * sb);
+        const DsDen<FAST> supb = den(dsm::log(sb));
+        double em2y1 = em2 / den((y1 * y1) * sb);
         double supb_x = em2y1 * y1_x;
         double supb_g = em2y1 * y1_g;
         double supb_xx = em2y1 * (y1_xx - 2.0 * (y1_x * y1_x) / y1 - y1_x * supb_x);
@@ -424,25 +440,27 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     } else {
         sup = px * theta;
         sup_x = 0.5 * px * theta / xr;
-        sup_g = px * theta / Gamma;
+        sup_g = px * theta / den(Gamma);
         sup_xx = -0.5 * sup_x / xr;
         sup_gg = 0.0;
-        sup_xg = sup_x / Gamma;
+        sup_xg = sup_x / den(Gamma);
     }
-    double gr3 = dsm::pow(Gamma / sup, r3);
-    double gr3x = -r3 * sup_x / sup;
+    const DsDen<FAST> supD = den(sup), GammaD = den(Gamma);
+    const DsDen<FAST> gr3 = den(dsm::pow(Gamma / supD, r3));
+    const DsDen<FAST> gr32D = den(gr3 * gr3);
+    double gr3x = -r3 * sup_x / supD;
     double gr3_x = gr3 * gr3x;
-    double gr3_xx = gr3_x * gr3x - r3 * gr3 * (sup_xx / sup - dsd::ipow<2>(sup_x / sup));
-    double gr3g = r3 * (1.0 / Gamma - sup_g / sup);
+    double gr3_xx = gr3_x * gr3x - r3 * gr3 * (sup_xx / supD - dsd::ipow<2>(sup_x / supD));
+    double gr3g = r3 * (1.0 / GammaD - sup_g / supD);
     double gr3_g = gr3 * gr3g;
-    double gr3_gg = gr3_g * gr3g + gr3 * r3 * (dsd::ipow<2>(sup_g / sup) - sup_gg / sup - 1.0 / (Gamma * Gamma));
-    double gr3_xg = gr3_g * gr3x + gr3 * r3 * (sup_x * sup_g / (sup * sup) - sup_xg / sup);
+    double gr3_gg = gr3_g * gr3g + gr3 * r3 * (dsd::ipow<2>(sup_g / supD) - sup_gg / supD - 1.0 / den(Gamma * Gamma));
+    double gr3_xg = gr3_g * gr3x + gr3 * r3 * (sup_x * sup_g / den(sup * sup) - sup_xg / supD);
     double w = 1.0 + q1 / gr3;
-    double w_x = q1_x / gr3 - q1 * gr3_x / (gr3 * gr3);
-    double w_g = -q1 * gr3_g / (gr3 * gr3);
-    double w_xx = q1_xx / gr3 - (2.0 * q1_x * gr3_x + q1 * (gr3_xx - 2.0 * (gr3_x * gr3_x) / gr3)) / (gr3 * gr3);
-    double w_gg = q1 * (2.0 * (gr3_g * gr3_g) / gr3 - gr3_gg) / (gr3 * gr3);
-    double w_xg = -(q1_x * gr3_g + q1 * (gr3_xg - 2.0 * gr3_x * gr3_g / gr3)) / (gr3 * gr3);
+    double w_x = q1_x / gr3 - q1 * gr3_x / gr32D;
+    double w_g = -q1 * gr3_g / gr32D;
+    double w_xx = q1_xx / gr3 - (2.0 * q1_x * gr3_x + q1 * (gr3_xx - 2.0 * (gr3_x * gr3_x) / gr3)) / gr32D;
+    double w_gg = q1 * (2.0 * (gr3_g * gr3_g) / gr3 - gr3_gg) / gr32D;
+    double w_xg = -(q1_x * gr3_g + q1 * (gr3_xg - 2.0 * gr3_x * gr3_g / gr3)) / gr32D;
 
     double f = -Gamma * finf * w;
     double f_x = -Gamma * (finf_x * w + finf * w_x);
@@ -456,8 +474,9 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     double cv = -(Gamma * Gamma) * f_gg;
     double p = onethird * (xr * f_x + Gamma * f_g);
     double dpt = onethird * (Gamma * Gamma) * (xr * finf * (finfx * w_g + w_xg) - f_gg);
-    double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma * f_xg + (Gamma * Gamma) * f_gg) / 9.0;
+    double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma * f_xg + (Gamma * Gamma) * f_gg) / den(9.0);
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
+    bad |= ds_den_bad;
 }
 
 DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
@@ -598,16 +617,17 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
     tot.dpr = dprh + dpra + madelung / 2.25;
 }
 
-DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsThermo& r) {
+template <bool FAST>
+DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsThermo& r, bool& bad) {
     const double sevensixth = (double)(7.0f / 6.0f);
     double Gamma = Gamma_e * dsm::pow(Z, fivethird);
     double theta = Gamma * sqrt(3.0 * Melectron / A / amu / rs) / dsm::pow(Z, sevensixth);
     DsThermo ie, ii;
     if (phase == ds_liquid_phase) {
-        ie_liquid(Gamma_e, rs, Z, ie);
+        ie_liquid<FAST>(Gamma_e, rs, Z, ie, bad);
         ii_liquid(Gamma, theta, ii);
     } else {
-        ie_lattice(Gamma, theta, rs, Z, ie);
+        ie_lattice<FAST>(Gamma, theta, rs, Z, ie, bad);
         ii_lattice(Gamma, theta, ii);
     }
     r.f = ie.f + ii.f; r.u = ie.u + ii.u; r.p = ie.p + ii.p; r.s = ie.s + ii.s;
@@ -645,9 +665,10 @@ DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
 }
 
+template <bool FAST>
 DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsComp& c,
                 int ncharged, const double* Zion, const double* Aion, const double* Yion,
-                double& Gamma, double& ionQ, int& phase, DsThermo& r) {
+                double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad) {
     const double Q2_threshold = 18.0;
     int err = 0;
     double Mu = amu / Melectron;
@@ -661,7 +682,7 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
     for (int i = 0; i < ncharged; ++i) {
         if (Yion[i] > rq.Ythresh) {
             DsThermo t;
-            one_ion(Gamma_e, rs, Zion[i], Aion[i], phase, t);
+            one_ion<FAST>(Gamma_e, rs, Zion[i], Aion[i], phase, t, bad);
             f = f + Yion[i] * t.f;
             u = u + Yion[i] * t.u;
             s = s + Yion[i] * (t.s - dsm::log(Yion[i]));
@@ -780,10 +801,14 @@ struct DsEosRes {
 // Sum of the five components (dStar_eos_lib.f:173-258).  `logT` is dsm::log10(T); for the coefficient
 // pass it is supplied by the host together with T so that table-cell selection is identical on
 // both sides of the ABI.  Zion/Aion/Yion: the charged species of the zone (Yion = Y/(1-Yn)).
+// FAST selects the branch-free divisions (DsDen, dconst.cuh); `bad` is raised when an operand left their
+// safe range, and the caller then repeats the evaluation with FAST = false (all lanes of the CTA together,
+// because of the DS_PHASE barriers inside).
+template <bool FAST>
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
                             double logT, const DsComp& c, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
-                            const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o,
+                            const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o, bool& bad,
                             double* __restrict__ comps = nullptr) {
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
@@ -805,7 +830,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     }
     DS_PHASE();
     DsThermo ex;
-    dse::ee_exchange(Gamma_e, rs, ex);
+    dse::ee_exchange<FAST>(Gamma_e, rs, ex, bad);
     DS_PHASE();
     const double nek = ne * boltzmann;
     const double nekT = nek * T;
@@ -814,7 +839,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     // ions (ion.f:20-92)
     DsThermo ion;
     int phase;
-    dse::ion_mixture(rq, rs, Gamma_e, c, ncharged, Zion, Aion, Yion, Gamma, ionQ, phase, ion);
+    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, Yion, Gamma, ionQ, phase, ion, bad);
     DS_PHASE();
     const double n_i = ne / c.Z;
     const double nik = n_i * boltzmann;

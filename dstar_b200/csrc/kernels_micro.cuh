@@ -74,6 +74,8 @@ struct DsMicroArgs {
     double* rho_bar1;  // (n_star) in/out
     int* status;       // (n_star) sticky error word
     double *tab_lnCp, *tab_lnGamma, *tab_lnEnu, *tab_lnK;  // (4*128, total_zones)
+    int* redo;  // (total_zones) or null: zones whose branch-free divisions left the safe range (see below)
+    int force_redo;  // test hook: flag every zone, so the plain pass recomputes everything
 };
 
 // MESA interp_pm (Steffen 1990) on one zone's 128 knots; i = knot index of this lane, v holds f(1,:) on entry.
@@ -122,18 +124,29 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, doub
 // at six different program counters and the warps starved on instruction fetch (ncu: stalled_no_instruction
 // 11 per issue, profiles/r01_notes.md).  Here all G groups start every round together (CTA barrier), so the
 // 4*G warps of an SM walk through the code in lockstep and every instruction line is fetched once per SM.
-template <bool FACE, int G>
+//
+// FAST = true evaluates the EOS with the branch-free divisions of dconst.cuh and records in a.redo[zone] whether
+// any lane's operands left their safe range; a second launch with FAST = false (plain IEEE divisions) then
+// re-evaluates exactly those zones and skips every other round.  Keeping the re-evaluation in a separate
+// launch keeps it out of the hot loop's register allocation (a conditional call inside the loop cost 10 %).
+// With FAST = false and a.redo == null the kernel is the single plain pass (used for the faces, whose EOS is
+// mostly dead code: only Gamma, Theta and mu_e feed the conductivity).
+template <bool FACE, int G, bool FAST>
 __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     __shared__ double s_h[DS_NTAB], s_v[G][3][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
     __shared__ double s_lam[G];
-    __shared__ int s_lam_ierr[G], s_err[G];
+    __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
     for (int g0 = blockIdx.x * G; g0 < a.total_zones; g0 += gridDim.x * G) {
         const int gq = g0 + grp;
-        const bool on = gq < a.total_zones;
-        if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; }
+        bool on = gq < a.total_zones;
+        if (!FAST && a.redo) {  // second pass: only the flagged zones; rounds without any are skipped by the whole CTA
+            on = on && a.redo[gq] != 0;
+            if (!__syncthreads_or(on)) continue;
+        }
+        if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; s_bad[grp] = 0; }
         __syncthreads();   // start of round: all groups aligned
         // groups past the end re-evaluate the last zone (results discarded) so that every thread of the
         // CTA reaches the DS_PHASE alignment points inside the evaluators
@@ -165,8 +178,10 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         }
         {
             DsEosRes r;
-            ds_eval_crust_eos(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion,
-                              (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g, Tc[1], chi, r);
+            const double* Yz = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
+            bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, Yz, Tc[1], chi, r, bad);
+            if (FAST && bad) s_bad[grp] = 1;
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
@@ -199,6 +214,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
         }
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
+        if (FAST && on && it == 0) a.redo[g] = s_bad[grp] | a.force_redo;
     }
 }
 
@@ -223,9 +239,15 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     double chi = a.chi_in ? a.chi_in[k] : -1.0;
     if (chi == -1.0) chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
     DsEosRes r;
-    ds_eval_crust_eos(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
-                      a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r,
-                      (a.comps && live) ? a.comps + (size_t)28 * k : nullptr);
+    bool bad = false;
+    double* cp = (a.comps && live) ? a.comps + (size_t)28 * k : nullptr;
+    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
+                            a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, bad, cp);
+    if (__syncthreads_or(bad)) {
+        bool unused = false;
+        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
+                                 a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, unused, cp);
+    }
     if (!live) return;
     double* o = a.res + (size_t)15 * k;
     o[0] = r.lnP; o[1] = r.lnE; o[2] = r.lnS; o[3] = r.grad_ad; o[4] = r.chiRho; o[5] = r.chiT; o[6] = r.Cp;

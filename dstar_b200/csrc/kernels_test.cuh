@@ -1,7 +1,7 @@
 // Test-support kernel: evaluates one dsmath function on the device so the CPU-side copy of the
 // specification can be compared bit for bit (tests/test_gpu_parity.py::test_dsmath_bits).
 #pragma once
-#include "dsmath.cuh"
+#include "dconst.cuh"
 
 DSM_HD double ds_dsmath_dispatch(int fn, double x, double y) {
     switch (fn) {
@@ -18,5 +18,18 @@ DSM_HD double ds_dsmath_dispatch(int fn, double x, double y) {
 }
 __global__ void ds_dsmath_kernel(int fn, int n, const double* x, const double* y, double* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = ds_dsmath_dispatch(fn, x[i], y[i]);
+    if (i >= n) return;
+    if (fn == 9) out[i] = x[i] / y[i];                       // IEEE division as the compiler emits it
+    else if (fn == 10) {                                      // branch-free form (dconst.cuh) + its fallback
+        DS_DEN_SCOPE(true);
+        const DsDen<true> d = den(y[i]);
+        const double q = x[i] / d;
+        out[i] = ds_den_bad ? x[i] / DsDen<false>(y[i], nullptr) : q;
+    } else if (fn == 11) {                                    // fast path only: NaN marks a raised flag
+        DS_DEN_SCOPE(true);
+        const DsDen<true> d = den(y[i]);
+        const double q = x[i] / d;
+        out[i] = ds_den_bad ? nan("") : q;
+    }
+    else out[i] = ds_dsmath_dispatch(fn, x[i], y[i]);
 }

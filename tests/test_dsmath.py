@@ -76,3 +76,49 @@ def test_dsmath_bits(oracle):
             assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), name
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_shared_denominator_division_bits():
+    """DsDen (dstar_b200/csrc/dconst.cuh): the branch-free division returns exactly the bits of the IEEE quotient
+    x / y -- moderate operands (fast path), extreme exponents, subnormals, zeros, infinities and NaN (flag raised,
+    plain division)."""
+    import dstar_b200 as ds
+    from dstar_b200._capi import check, p
+    ctx = ds.Context(0, gaps=None)
+    rng = np.random.default_rng(77)
+    try:
+        def rnd(n, lo, hi):
+            return rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(lo, hi, n) * rng.uniform(1.0, 2.0, n)
+        n = 1 << 22
+        sets = [(rnd(n, -30, 30), rnd(n, -30, 30)), (rnd(n, -300, 300), rnd(n, -300, 300)),
+                (rnd(n, -3, 3), rnd(n, -3, 3))]
+        # same significands, dense exponents near 1: half-way cases of the final rounding
+        m = rng.integers(1 << 52, 1 << 53, n).astype(np.float64)
+        sets.append((m * 2.0 ** -52, rng.integers(1 << 52, 1 << 53, n).astype(np.float64) * 2.0 ** -52))
+        sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                       1e-300, 1e300, 3.0, 1 / 3, 2.0 ** -967, 2.0 ** 977, 2.0 ** -900, 2.0 ** 900])
+        A, B = np.meshgrid(sp, sp)
+        sets.append((A.ravel().copy(), B.ravel().copy()))
+        for x, y in sets:
+            x = f64(x); y = f64(y)
+            q_plain = np.zeros_like(x); q_den = np.zeros_like(x)
+            check(ctx.L.dstar_dsmath_eval(ctx.h, 9, len(x), p(x), p(y), p(q_plain)), "dsmath_eval")
+            check(ctx.L.dstar_dsmath_eval(ctx.h, 10, len(x), p(x), p(y), p(q_den)), "dsmath_eval")
+            with np.errstate(all="ignore"):
+                host = x / y
+            nan = np.isnan(host)
+            assert np.array_equal(q_plain.view(np.uint64)[~nan], host.view(np.uint64)[~nan])
+            assert np.array_equal(np.isnan(q_den), nan)
+            assert np.array_equal(q_den.view(np.uint64)[~nan], host.view(np.uint64)[~nan])
+            # fast path alone: wherever the validity flag stays down the bits are the IEEE quotient's
+            q_fast = np.zeros_like(x)
+            check(ctx.L.dstar_dsmath_eval(ctx.h, 11, len(x), p(x), p(y), p(q_fast)), "dsmath_eval")
+            took = ~np.isnan(q_fast)
+            assert np.array_equal(q_fast.view(np.uint64)[took], host.view(np.uint64)[took])
+            with np.errstate(all="ignore"):
+                moderate = ((np.abs(np.log2(np.abs(y))) < 299) & (np.log2(np.abs(x)) > -959) & (np.log2(np.abs(host)) > -999)
+                            & (np.log2(np.abs(host)) < 699) & ~nan)
+            assert np.all(took[moderate])          # ... and the flag stays down for every moderate operand pair
+    finally:
+        ctx.close()

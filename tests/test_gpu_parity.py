@@ -278,3 +278,20 @@ def test_call_order_errors(ctx):
     b.close()
     with pytest.raises(ds.DStarError):
         ds.Batch(ctx, [0, 2], 2)  # fewer than 3 zones
+
+
+@pytest.mark.gpu
+def test_micro_tables_redo_pass_matches(nscool, monkeypatch):
+    """The coefficient pass evaluates the cell EOS with branch-free divisions and re-evaluates flagged zones
+    with plain IEEE divisions in a second launch; forcing every zone through that second pass must reproduce
+    the tables bit for bit (the two division forms are the same arithmetic)."""
+    s = _make_star(nscool)
+    s.create_model()
+    ref = {k: s.array(k).copy() for k in ("tab_lnCp", "tab_lnGamma", "tab_lnEnu", "tab_lnK")}
+    s.free()
+    monkeypatch.setenv("DSTAR_FORCE_REDO", "1")
+    s2 = _make_star(nscool)
+    s2.create_model()
+    for k, v in ref.items():
+        assert np.array_equal(s2.array(k).view(np.uint64), v.view(np.uint64)), k
+    s2.free()
