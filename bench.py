@@ -349,7 +349,8 @@ def run_b200(args):
             "curves_per_sec": n_star * world / (ms_step * 1e-3),
             "e2e": {"value": evals * world / e2e_s, "unit": UNIT, "curves_per_sec": n_star * world / e2e_s,
                     "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": 4 * args.steps,   # per step: cell pass (branch-free) + cell redo pass + face pass + evolve "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            # launches per step: cell pass (branch-free) + cell redo pass + face pass + evolve
+            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "all_stars_converged": ok, "wall_s_resident_loop": wall_res}
     if dist is not None:
         # final gather of the light curves (the only collective of the job)
