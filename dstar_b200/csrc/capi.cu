@@ -71,7 +71,7 @@ struct dstar_batch {
     int max_nz = 0;
     bool have_structure = false, have_tables = false, have_evolve = false, have_Tc_cell = false, have_Tc_face = false,
          have_enuc = false;
-    DevBuf<int> zone_offset, zone_star, status, redo, atm_index, idid, counters, model, trace_count, trace_model;
+    DevBuf<int> zone_offset, zone_star, status, redo, redo_count, atm_index, idid, counters, model, trace_count, trace_model;
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
@@ -393,7 +393,7 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(b->zone_offset.upload(b->h_zone_offset.data(), n_star + 1, st));
     CK(b->zone_star.upload(zs.data(), b->total, st));
     CK(b->status.alloc(n_star)); CK(cudaMemsetAsync(b->status.p, 0, n_star * sizeof(int), st));
-    CK(b->redo.alloc(b->total)); CK(cudaMemsetAsync(b->redo.p, 0, (size_t)b->total * sizeof(int), st));
+    CK(b->redo.alloc(b->total)); CK(b->redo_count.alloc(1));
     CK(b->rho_bar1.alloc(n_star));
     CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
     CK(cudaStreamSynchronize(st));
@@ -494,7 +494,8 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
-            a.redo = b->redo.p;
+            a.redo = b->redo.p; a.redo_count = b->redo_count.p;
+            CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
             { const char* e = std::getenv("DSTAR_FORCE_REDO"); a.force_redo = (e && e[0] == '1') ? 1 : 0; }  // test hook
             launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
             ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
@@ -509,7 +510,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev0, s));
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
-            a.redo = nullptr;
+            a.redo = nullptr; a.redo_count = nullptr;
             launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());

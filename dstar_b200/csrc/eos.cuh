@@ -45,13 +45,15 @@ namespace dse {
 using namespace dsc;
 
 
+template <bool FAST>
 DS_D void lattice_properties(double rho, double T, const DsComp& c, double& ne, double& rs,
-                        double& Gamma_e, double& Gamma, double& ionQ) {
-    ne = rho * c.Ye / amu;
-    rs = dsm::pow(3.0 / fourpi / ne, onethird) / a_Bohr;
-    Gamma_e = 2.0 * Rydberg / boltzmann / T / rs;
+                        double& Gamma_e, double& Gamma, double& ionQ, bool& bad) {
+    DS_DEN_SCOPE(FAST);
+    ne = rho * c.Ye / den_c(amu);
+    rs = dsm::pow(3.0 / den_c(fourpi) / den(ne), onethird) / den_c(a_Bohr);
+    Gamma_e = 2.0 * Rydberg / den_c(boltzmann) / den(T) / den(rs);
     Gamma = Gamma_e * c.Z53;
-    ionQ = sqrt(3.0 * (Gamma_e * Gamma_e) * Melectron / rs / amu * c.Z2XoA2 * c.A / c.Z);
+    ionQ = sqrt(3.0 * (Gamma_e * Gamma_e) * Melectron / den(rs) / den_c(amu) * c.Z2XoA2 * c.A / den(c.Z));
 }
 
 DS_D double nuclear_volume_fraction(double rho, const DsComp& c, double nuclear_radius) {
@@ -258,7 +260,6 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double dpr = p + onethird * (pdlg - 2.0 * pdlh);
     double dpt = Gamma_e * (theta * f_hg - onethird * Gamma_e * f_gg) - theta * (f_h / den(0.75) + theta * f_hh / den(1.5));
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
-    bad |= ds_den_bad;
 }
 
 template <bool FAST>
@@ -362,7 +363,6 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     double dpt = -(Gamma_e * Gamma_e) * (xr * fx_g + f_gg) * onethird;
     double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma_e * f_xg + (Gamma_e * Gamma_e) * f_gg) / den(9.0);
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
-    bad |= ds_den_bad;
 }
 
 template <bool FAST>
@@ -476,10 +476,11 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     double dpt = onethird * (Gamma * Gamma) * (xr * finf * (finfx * w_g + w_xg) - f_gg);
     double dpr = (12.0 * p + (xr * xr) * f_xx + 2.0 * xr * Gamma * f_xg + (Gamma * Gamma) * f_gg) / den(9.0);
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
-    bad |= ds_den_bad;
 }
 
-DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
+template <bool FAST>
+DS_D void ii_liquid(double Gamma, double theta, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     // array constructor of REAL(4): A(3) is evaluated entirely in single precision
     const float A1f = -0.907347f, A2f = 0.62849f;
     const float A3f = -0.5f * sqrtf(3.0f) + 0.907347f / sqrtf(0.62849f);
@@ -487,17 +488,17 @@ DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
     const double B1 = DS_R4(4.50e-3), B2 = DS_R4(170.0), B3 = DS_R4(-8.4e-5), B4 = DS_R4(3.70e-3);
 
     double f0 = A1 * (sqrt(Gamma * (A2 + Gamma)) -
-                      A2 * dsm::log(sqrt(Gamma / A2) + sqrt(1.0 + Gamma / A2))) +
+                      A2 * dsm::log(sqrt(Gamma / den(A2)) + sqrt(1.0 + Gamma / den(A2)))) +
                 2.0 * A3 * (sqrt(Gamma) - dsm::atan(sqrt(Gamma)));
     double G2 = Gamma * Gamma;
     double G15 = dsm::pow(Gamma, 1.5);
-    double f = f0 + B1 * (Gamma - B2 * dsm::log(1.0 + Gamma / B2)) + 0.5 * B3 * dsm::log(1.0 + G2 / B4);
-    double u = G15 * (A1 / sqrt(A2 + Gamma) + A3 / (1.0 + Gamma)) +
-               G2 * (B1 / (B2 + Gamma) + B3 / (B4 + G2));
-    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / dsd::ipow<2>(Gamma + 1.0) - A1 * A2 / dsm::pow(Gamma + A2, 1.5)) +
-                G2 * (B3 * (G2 - B4) / dsd::ipow<2>(G2 + B4) - B1 * B2 / dsd::ipow<2>(Gamma + B2));
+    double f = f0 + B1 * (Gamma - B2 * dsm::log(1.0 + Gamma / den(B2))) + 0.5 * B3 * dsm::log(1.0 + G2 / den(B4));
+    double u = G15 * (A1 / den(sqrt(A2 + Gamma)) + A3 / den(1.0 + Gamma)) +
+               G2 * (B1 / den(B2 + Gamma) + B3 / den(B4 + G2));
+    double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / den(dsd::ipow<2>(Gamma + 1.0)) - A1 * A2 / den(dsm::pow(Gamma + A2, 1.5))) +
+                G2 * (B3 * (G2 - B4) / den(dsd::ipow<2>(G2 + B4)) - B1 * B2 / den(dsd::ipow<2>(Gamma + B2)));
     double p = onethird * u;
-    double dpr = (4.0 * u - cv) / 9.0;
+    double dpr = (4.0 * u - cv) / den_c(9.0);
     double dpt = onethird * cv;
 
     double fid = 3.0 * dsm::log(theta) - 1.5 * dsm::log(Gamma) - ds_hc.half_log_6_over_pi - 1.0;
@@ -509,7 +510,7 @@ DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
     dpt = dpt + 1.0;
     dpr = dpr + 1.0;
 
-    double fq = theta * theta / 24.0;
+    double fq = theta * theta / den_c(24.0);
     f = f + fq;
     u = u + 2.0 * fq;
     s = s + fq;
@@ -520,7 +521,9 @@ DS_D void ii_liquid(double Gamma, double theta, DsThermo& r) {
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
 }
 
-DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
+template <bool FAST>
+DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double KM = DS_R4(-0.895929255682), w = DS_R4(0.5113875), clm = DS_R4(-2.49389);
     const double alpha[9] = {DS_R4(0.0), DS_R4(0.932446), DS_R4(0.334547), DS_R4(0.265764), DS_R4(0.0),
                              DS_R4(0.0), DS_R4(4.757014e-3), DS_R4(0.0), DS_R4(4.7770935e-3)};
@@ -530,18 +533,18 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
                          DS_R4(3.97355e-4), DS_R4(5.11148e-5), DS_R4(2.19749e-6)};
     const double afh[4] = {0.0, DS_R4(10.9), DS_R4(247.0), DS_R4(1.765e5)};  // 1-based
     const double b1 = DS_R4(0.12);
-    const double c1 = b1 / afh[1];
+    const double c1 = b1 / den(afh[1]);
     const double theta_low = DS_R4(1.0e-5), theta_high = DS_R4(1.0e5);
 
     double fh = 0, uh = 0, cvh = 0;
     if (theta > theta_high) {
-        uh = 3.0 / (alpha[6] * dsd::ipow<3>(theta));
-        fh = -uh / 3.0;
+        uh = 3.0 / den(alpha[6] * dsd::ipow<3>(theta));
+        fh = -uh / den_c(3.0);
         cvh = 4.0 * uh;
     } else if (theta < theta_low) {
-        fh = 3.0 * dsm::log(theta) + clm - 1.5 * w * theta + theta * theta / 24.0;
-        uh = 3.0 - 1.5 * w * theta + theta * theta / 12.0;
-        cvh = 3.0 - theta * theta / 12.0;
+        fh = 3.0 * dsm::log(theta) + clm - 1.5 * w * theta + theta * theta / den_c(24.0);
+        uh = 3.0 - 1.5 * w * theta + theta * theta / den_c(12.0);
+        cvh = 3.0 - theta * theta / den_c(12.0);
     } else {
         // Ath / Bth : value, first and second derivative by Horner (:545-575)
         double Ac[3] = {a[8], 0.0, 0.0};
@@ -565,11 +568,11 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
             double ea = dsm::exp(-alpha[n] * theta);
             double omea = 1.0 - ea;
             fh = fh + dsm::log(omea);
-            uh = uh + alpha[n] * ea / omea;
+            uh = uh + alpha[n] * ea / omea;  // ea = exp(-alpha theta) reaches the subnormals: plain divisions
             cvh = cvh + alpha[n] * alpha[n] * ea / (omea * omea);
         }
-        fh = fh - Ac[0] / Bc[0];
-        uh = (uh - (Ac[1] * Bc[0] - Ac[0] * Bc[1]) / (Bc[0] * Bc[0])) * theta;
+        fh = fh - Ac[0] / den(Bc[0]);
+        uh = (uh - (Ac[1] * Bc[0] - Ac[0] * Bc[1]) / den(Bc[0] * Bc[0])) * theta;
         cvh = cvh + ((Ac[2] * Bc[0] - Bc[2] * Ac[0]) * Bc[0] - 2.0 * (Ac[1] * Bc[0] - Bc[1] * Ac[0]) * Bc[1]) /
                         dsd::ipow<3>(Bc[0]);
         cvh = cvh * (theta * theta);
@@ -588,10 +591,10 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
     double theta4 = dsd::ipow<4>(theta);
     double c1t2 = c1 * theta2;
     double sup = dsm::exp(-c1t2);
-    double tq = b1 * theta2 / Gamma;
+    double tq = b1 * theta2 / den(Gamma);
     double gninv = sup;
     for (int n = 1; n <= 3; ++n) {
-        gninv = gninv / Gamma;
+        gninv = gninv / Gamma;  // exp(-c1 theta^2) / Gamma^n underflows gracefully: plain division
         double ninv = (double)(1.0f / (float)n);  // REAL(4) 1.0/n
         fa = fa - ninv * afh[n] * gninv;
         ua = ua + gninv * afh[n] * (1.0 + 2.0 * ninv * c1t2);
@@ -605,7 +608,7 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
     fa = fa - tq;
     ua = ua - tq;
     pa = pa - 2.0 * onethird * tq;
-    dpra = dpra - tq / 4.5;
+    dpra = dpra - tq / den_c(4.5);
 
     double madelung = KM * Gamma;
     tot.f = fh + fa + madelung;
@@ -614,53 +617,56 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot) {
     tot.s = sh;
     tot.cv = cvh + cva;
     tot.dpt = dpth + dpta;
-    tot.dpr = dprh + dpra + madelung / 2.25;
+    tot.dpr = dprh + dpra + madelung / den_c(2.25);
 }
 
 template <bool FAST>
 DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double sevensixth = (double)(7.0f / 6.0f);
     double Gamma = Gamma_e * dsm::pow(Z, fivethird);
-    double theta = Gamma * sqrt(3.0 * Melectron / A / amu / rs) / dsm::pow(Z, sevensixth);
+    double theta = Gamma * sqrt(3.0 * Melectron / den(A) / den_c(amu) / den(rs)) / den(dsm::pow(Z, sevensixth));
     DsThermo ie, ii;
     if (phase == ds_liquid_phase) {
         ie_liquid<FAST>(Gamma_e, rs, Z, ie, bad);
-        ii_liquid(Gamma, theta, ii);
+        ii_liquid<FAST>(Gamma, theta, ii, bad);
     } else {
         ie_lattice<FAST>(Gamma, theta, rs, Z, ie, bad);
-        ii_lattice(Gamma, theta, ii);
+        ii_lattice<FAST>(Gamma, theta, ii, bad);
     }
     r.f = ie.f + ii.f; r.u = ie.u + ii.u; r.p = ie.p + ii.p; r.s = ie.s + ii.s;
     r.cv = ie.cv + ii.cv; r.dpr = ie.dpr + ii.dpr; r.dpt = ie.dpt + ii.dpt;
 }
 
-DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r) {
+template <bool FAST>
+DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double threshold = DS_R4(1.0e-9);
     double Gamma = Gamma_e * c.Z53;
     double dif0;
-    if (rs < threshold) dif0 = c.Z52 - sqrt(dsd::ipow<3>(c.Z2) / c.Z);
-    else dif0 = c.ZZ1_32 - sqrt(dsd::ipow<3>(c.Z2 + c.Z) / c.Z);
-    double difR = dif0 / c.Z52;
+    if (rs < threshold) dif0 = c.Z52 - sqrt(dsd::ipow<3>(c.Z2) / den(c.Z));
+    else dif0 = c.ZZ1_32 - sqrt(dsd::ipow<3>(c.Z2 + c.Z) / den(c.Z));
+    double difR = dif0 / den(c.Z52);
     double difFDH = dif0 * Gamma_e * sqrt(onethird * Gamma_e);
-    double D = c.Z2 / (c.Z * c.Z);
+    double D = c.Z2 / den(c.Z * c.Z);
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (fabs(D - 1.0) < threshold) return;
     double p3 = dsm::pow(D, DS_R4(-0.2));
-    double d0 = (DS_R4(2.6) * difR + 14.0 * dsd::ipow<3>(difR)) / (1.0 - p3);
+    double d0 = (DS_R4(2.6) * difR + 14.0 * dsd::ipow<3>(difR)) / den(1.0 - p3);
     double gp = d0 * dsm::pow(Gamma, p3);
-    double f0 = difFDH / (1.0 + gp);
+    double f0 = difFDH / den(1.0 + gp);
     double q = (D * D) * DS_R4(0.0117);
-    double rr = 1.5 / p3 - 1.0;
+    double rr = 1.5 / den(p3) - 1.0;
     double gq = q * gp;
-    double f = f0 / dsm::pow(1.0 + gq, rr);
-    double g = 1.5 - p3 * gp / (1.0 + gp) - rr * p3 * gq / (1.0 + gq);
+    double f = f0 / den(dsm::pow(1.0 + gq, rr));
+    double g = 1.5 - p3 * gp / den(1.0 + gp) - rr * p3 * gq / den(1.0 + gq);
     double u = f * g;
     double s = u - f;
     double p = onethird * u;
-    double g_dg = -(p3 * p3) * (gp / dsd::ipow<2>(1.0 + gp) + rr * gq / dsd::ipow<2>(1.0 + gq));
+    double g_dg = -(p3 * p3) * (gp / den(dsd::ipow<2>(1.0 + gp)) + rr * gq / den(dsd::ipow<2>(1.0 + gq)));
     double u_dg = u * g + f * g_dg;
     double cv = u - u_dg;
-    double dpr = p + u_dg / 9.0;
+    double dpr = p + u_dg / den_c(9.0);
     double dpt = p - onethird * u_dg;
     r = DsThermo{f, u, p, s, cv, dpr, dpt};
 }
@@ -669,12 +675,13 @@ template <bool FAST>
 DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsComp& c,
                 int ncharged, const double* Zion, const double* Aion, const double* Yion,
                 double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double Q2_threshold = 18.0;
     int err = 0;
-    double Mu = amu / Melectron;
+    double Mu = amu / den_c(Melectron);
     Gamma = Gamma_e * c.Z53;
     phase = (Gamma < rq.Gamma_melt) ? ds_liquid_phase : ds_solid_phase;
-    double ionQ2 = 3.0 * (Gamma_e * Gamma_e) / rs / Mu * c.Z2XoA2 * c.A / c.Z;
+    double ionQ2 = 3.0 * (Gamma_e * Gamma_e) / den(rs) / den(Mu) * c.Z2XoA2 * c.A / den(c.Z);
     ionQ = sqrt(ionQ2);
     if (phase == ds_liquid_phase && ionQ2 > Q2_threshold) err = 1;
 
@@ -693,7 +700,7 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
         }
     }
     DsThermo m;
-    LM_corrections(rs, Gamma_e, c, m);
+    LM_corrections<FAST>(rs, Gamma_e, c, m, bad);
     r.f = f * c.A + m.f;
     r.u = u * c.A + m.u;
     r.s = s * c.A + m.s;
@@ -742,30 +749,32 @@ DS_D double ifermi12(double f) {  // :528-580
     return rn / (den * ff);
 }
 
-DS_D void MB77(double n, double T, double Tns, DsThermo& r) {
+template <bool FAST>
+DS_D void MB77(double n, double T, double Tns, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double c[4] = {DS_R4(1.2974), DS_R4(15.0298), DS_R4(-15.2343), DS_R4(7.4663)};
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (n == 0.0) return;
-    double k = dsm::pow(0.5 * threepisquare * n, onethird) / cm_to_fm;
-    double dkdn = onethird * k / n;
+    double k = dsm::pow(0.5 * threepisquare * n, onethird) / den_c(cm_to_fm);
+    double dkdn = onethird * k / den(n);
     double u = k * (c[0] + k * (c[1] + k * (c[2] + k * c[3])));
     u = u * mev_to_ergs;
     double p = onethird * n * k * (c[0] + k * (2.0 * c[1] + k * (3.0 * c[2] + k * 4.0 * c[3])));
     p = p * mev_to_ergs;
     double dpdk = onethird * n * k * (c[0] + k * (4.0 * c[1] + k * (9.0 * c[2] + 16.0 * c[3] * k))) * mev_to_ergs;
-    double dpr = (p / n + dpdk * dkdn) * n;
+    double dpr = (p / den(n) + dpdk * dkdn) * n;
     double dpT = 0.0;
 
-    double lambda3 = pi * pi * dsm::pow(hbar * hbar / (Mneutron * boltzmann * T), 1.5) / (double)sqrtf(2.0f);
+    double lambda3 = pi * pi * dsm::pow(hbar * hbar / den(Mneutron * boltzmann * T), 1.5) / den_c((double)sqrtf(2.0f));
     double zeta = ifermi12(n * lambda3);
-    double cv = 2.5 * zfermi32(zeta) / zfermi12(zeta) - 4.5 * zfermi12(zeta) / zfermim12(zeta);
+    double cv = 2.5 * zfermi32(zeta) / den(zfermi12(zeta)) - 4.5 * zfermi12(zeta) / den(zfermim12(zeta));
     cv = cv * boltzmann;
-    double s = fivethird * zfermi32(zeta) / zfermi12(zeta) - zeta;
+    double s = fivethird * zfermi32(zeta) / den(zfermi12(zeta)) - zeta;
     s = s * boltzmann;
     double R;
     if (T < Tns) {
-        double tau = T / Tns;
-        double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / sqrt(tau) + DS_R4(1.764) / tau);
+        double tau = T / den(Tns);
+        double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / den(sqrt(tau)) + DS_R4(1.764) / den(tau));
         R = dsm::pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
             dsm::exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
     } else {
@@ -777,17 +786,19 @@ DS_D void MB77(double n, double T, double Tns, DsThermo& r) {
     r = DsThermo{f, u, p, s, cv, dpr, dpT};
 }
 
-DS_D void get_radiation_eos(double rho, double T, DsThermo& r) {
+template <bool FAST>
+DS_D void get_radiation_eos(double rho, double T, DsThermo& r, bool& bad) {
+    DS_DEN_SCOPE(FAST);
     const double fourthird = 4.0 * onethird;
     double aT3 = arad * dsd::ipow<3>(T);
     double aT4 = arad * dsd::ipow<4>(T);
-    r.u = aT4 / rho;
+    r.u = aT4 / den(rho);
     r.p = onethird * aT4;
-    r.f = -onethird * aT4 / rho;
-    r.s = fourthird * aT3 / rho;
+    r.f = -onethird * aT4 / den(rho);
+    r.s = fourthird * aT3 / den(rho);
     r.dpr = 0.0;
     r.dpt = fourthird * aT4;
-    r.cv = 4.0 * aT3 / rho;
+    r.cv = 4.0 * aT3 / den(rho);
 }
 
 }  // namespace dse
@@ -810,9 +821,10 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
                             const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o, bool& bad,
                             double* __restrict__ comps = nullptr) {
+    DS_DEN_SCOPE(FAST);
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
-    dse::lattice_properties(rho, T, c, ne, rs, Gamma_e, Gamma, ionQ);
+    dse::lattice_properties<FAST>(rho, T, c, ne, rs, Gamma_e, Gamma, ionQ, bad);
     DS_PHASE();
 
     // electrons: table + exchange (electron.f:10-51, :53-250)
@@ -821,7 +833,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     int ierr_h = 0;
     if (!(fabs(c.Yn - 1.0) <= (double)1.1920929e-07f)) {
         DsHelmOut he;
-        ierr_h = ds_helm_electron(helm, T, logT, rho, c.A / (1.0 - c.Yn), c.Z, he);
+        ierr_h = ds_helm_electron(helm, T, logT, rho, c.A / den(1.0 - c.Yn), c.Z, he);
         if (ierr_h == 0) {
             e.u = he.eele; e.p = he.pele; e.s = he.sele; e.f = e.u - T * e.s;
             e.cv = he.deept; e.dpr = rho * he.dpepd; e.dpt = T * he.dpept;
@@ -834,27 +846,27 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     DS_PHASE();
     const double nek = ne * boltzmann;
     const double nekT = nek * T;
-    const double uexfac = nekT / rho, pexfac = nekT, sexfac = nek / rho;
+    const double uexfac = nekT / den(rho), pexfac = nekT, sexfac = nek / den(rho);
 
     // ions (ion.f:20-92)
     DsThermo ion;
     int phase;
     dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, Yion, Gamma, ionQ, phase, ion, bad);
     DS_PHASE();
-    const double n_i = ne / c.Z;
+    const double n_i = ne / den(c.Z);
     const double nik = n_i * boltzmann;
     const double nikT = nik * T;
-    const double uifac = nikT / rho, pifac = nikT, sifac = nik / rho;
+    const double uifac = nikT / den(rho), pifac = nikT, sifac = nik / den(rho);
 
     // dripped neutrons (neutron.f:15-69)
-    const double nn = rho * c.Yn / amu / (1.0 - chi);
+    const double nn = rho * c.Yn / den_c(amu) / den(1.0 - chi);
     DsThermo nt;
-    dse::MB77(nn, T, Tns, nt);
+    dse::MB77<FAST>(nn, T, Tns, nt, bad);
     DS_PHASE();
     const double unfac = avogadro * c.Yn, pnfac = 1.0, snfac = unfac;
 
     DsThermo rad;
-    dse::get_radiation_eos(rho, T, rad);
+    dse::get_radiation_eos<FAST>(rho, T, rad, bad);
 
     const double p = e.p + ex.p * pexfac + ion.p * pifac + nt.p * pnfac + rad.p;
     const double u = e.u + ex.u * uexfac + ion.u * uifac + nt.u * unfac + rad.u;
@@ -862,20 +874,20 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     const double cv = e.cv + ex.cv * sexfac + ion.cv * sifac + nt.cv * snfac + rad.cv;
     const double dpr = e.dpr + ex.dpr * pexfac + ion.dpr * pifac + nt.dpr * pnfac + rad.dpr;
     const double dpt = e.dpt + ex.dpt * pexfac + ion.dpt * pifac + nt.dpt * pnfac + rad.dpt;
-    const double gamma3m1 = dpt / rho / T / cv;
-    const double gamma1 = (dpr + dpt * gamma3m1) / p;
+    const double gamma3m1 = dpt / den(rho) / den(T) / den(cv);
+    const double gamma1 = (dpr + dpt * gamma3m1) / den(p);
     DS_PHASE();
     o.lnP = dsm::log(p);
     o.lnE = dsm::log(u);
     o.lnS = dsm::log(s);
-    o.grad_ad = gamma3m1 / gamma1;
-    o.chiRho = dpr / p;
-    o.chiT = dpt / p;
-    o.Cp = gamma1 * p * cv / dpr;
+    o.grad_ad = gamma3m1 / den(gamma1);
+    o.chiRho = dpr / den(p);
+    o.chiT = dpt / den(p);
+    o.Cp = gamma1 * p * cv / den(dpr);
     o.Cv = cv;
     o.Chi = chi;
     o.Gamma = Gamma;
-    o.Theta = 1.0 / ionQ;
+    o.Theta = 1.0 / den(ionQ);
     o.mu_e = (eta_e * boltzmann * T) * ergs_to_mev;
     o.mu_n = (c.Yn < rq.Ythresh) ? 0.0 : (nt.u - T * nt.s + nt.p / nn) * ergs_to_mev;
     o.Gamma1 = gamma1;
@@ -886,17 +898,17 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
         const double pe = e.p + ex.p * pexfac;
         double* q = comps;
         q[0] = pe; q[1] = e.u + ex.u * uexfac; q[2] = e.s + ex.s * sexfac; q[3] = e.f + ex.f * uexfac;
-        q[4] = e.cv + ex.cv * sexfac; q[5] = (e.dpr + ex.dpr * pexfac) / pe; q[6] = (e.dpt + ex.dpt * pexfac) / pe;
+        q[4] = e.cv + ex.cv * sexfac; q[5] = (e.dpr + ex.dpr * pexfac) / den(pe); q[6] = (e.dpt + ex.dpt * pexfac) / den(pe);
         q += 7;
         q[0] = ion.p * pifac; q[1] = ion.u * uifac; q[2] = ion.s * sifac; q[3] = ion.f * uifac; q[4] = ion.cv * sifac;
-        q[5] = ion.dpr / ion.p; q[6] = ion.dpt / ion.p;
+        q[5] = ion.dpr / den(ion.p); q[6] = ion.dpt / den(ion.p);
         q += 7;
         if (c.Yn < rq.Ythresh) { for (int i = 0; i < 7; ++i) q[i] = 0.0; }
         else {
             q[0] = nt.p * pnfac; q[1] = nt.u * unfac; q[2] = nt.s * snfac; q[3] = nt.f * unfac; q[4] = nt.cv * snfac;
-            q[5] = nt.dpr / nt.p; q[6] = nt.dpt / nt.p;
+            q[5] = nt.dpr / den(nt.p); q[6] = nt.dpt / den(nt.p);
         }
         q += 7;
-        q[0] = rad.p; q[1] = rad.u; q[2] = rad.s; q[3] = rad.f; q[4] = rad.cv; q[5] = rad.dpr / rad.p; q[6] = rad.dpt / rad.p;
+        q[0] = rad.p; q[1] = rad.u; q[2] = rad.s; q[3] = rad.f; q[4] = rad.cv; q[5] = rad.dpr / den(rad.p); q[6] = rad.dpt / den(rad.p);
     }
 }

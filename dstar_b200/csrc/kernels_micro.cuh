@@ -74,7 +74,8 @@ struct DsMicroArgs {
     double* rho_bar1;  // (n_star) in/out
     int* status;       // (n_star) sticky error word
     double *tab_lnCp, *tab_lnGamma, *tab_lnEnu, *tab_lnK;  // (4*128, total_zones)
-    int* redo;  // (total_zones) or null: zones whose branch-free divisions left the safe range (see below)
+    int* redo;        // (total_zones) or null: compact list of the zones whose branch-free divisions left the safe range
+    int* redo_count;  // (1) length of that list (zeroed before the branch-free pass)
     int force_redo;  // test hook: flag every zone, so the plain pass recomputes everything
 };
 
@@ -125,9 +126,9 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, doub
 // 11 per issue, profiles/r01_notes.md).  Here all G groups start every round together (CTA barrier), so the
 // 4*G warps of an SM walk through the code in lockstep and every instruction line is fetched once per SM.
 //
-// FAST = true evaluates the EOS with the branch-free divisions of dconst.cuh and records in a.redo[zone] whether
-// any lane's operands left their safe range; a second launch with FAST = false (plain IEEE divisions) then
-// re-evaluates exactly those zones and skips every other round.  Keeping the re-evaluation in a separate
+// FAST = true evaluates the EOS and the neutrino emissivities with the branch-free divisions of dconst.cuh and
+// appends to the list a.redo every zone in which some lane's operands left their safe range; a second launch
+// with FAST = false (plain IEEE divisions) then re-evaluates exactly the listed zones (normally none).  Keeping the re-evaluation in a separate
 // launch keeps it out of the hot loop's register allocation (a conditional call inside the loop cost 10 %).
 // With FAST = false and a.redo == null the kernel is the single plain pass (used for the faces, whose EOS is
 // mostly dead code: only Gamma, Theta and mu_e feed the conductivity).
@@ -139,13 +140,12 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
-    for (int g0 = blockIdx.x * G; g0 < a.total_zones; g0 += gridDim.x * G) {
-        const int gq = g0 + grp;
-        bool on = gq < a.total_zones;
-        if (!FAST && a.redo) {  // second pass: only the flagged zones; rounds without any are skipped by the whole CTA
-            on = on && a.redo[gq] != 0;
-            if (!__syncthreads_or(on)) continue;
-        }
+    // second pass (FAST = false with a redo list): the work items are the list entries, densely packed
+    const bool redo_pass = !FAST && a.redo != nullptr;
+    const int n_items = redo_pass ? *a.redo_count : a.total_zones;
+    for (int g0 = blockIdx.x * G; g0 < n_items; g0 += gridDim.x * G) {
+        const bool on = g0 + grp < n_items;
+        const int gq = redo_pass ? (on ? a.redo[g0 + grp] : 0) : g0 + grp;
         if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; s_bad[grp] = 0; }
         __syncthreads();   // start of round: all groups aligned
         // groups past the end re-evaluate the last zone (results discarded) so that every thread of the
@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             const double* Yz = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
             ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, Yz, Tc[1], chi, r, bad);
-            if (FAST && bad) s_bad[grp] = 1;
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
@@ -189,7 +188,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                 if (on && iz == 0 && it == 0)  // create_model.f:367-369
                     a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
                 DsNeutrino eps;
-                dsn::ds_crust_neutrino(rho, T, c, chi, Tc[1], a.nu_channels, eps);
+                dsn::ds_crust_neutrino<FAST>(rho, T, c, chi, Tc[1], a.nu_channels, eps, bad);
                 double lnenu = dsm::log(eps.total / rho);
                 if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
                     if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
@@ -203,6 +202,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                                      s_lam_ierr[grp], K);
                 s_v[grp][0][it] = dsm::log(K.total);
             }
+            if (FAST && bad) s_bad[grp] = 1;
         }
         __syncthreads();
         const size_t ob = (size_t)4 * DS_NTAB * g;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
         }
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
-        if (FAST && on && it == 0) a.redo[g] = s_bad[grp] | a.force_redo;
+        if (FAST && on && it == 0 && (s_bad[grp] | a.force_redo)) a.redo[atomicAdd(a.redo_count, 1)] = g;
     }
 }
 
@@ -270,8 +270,9 @@ __global__ void ds_eval_nu_kernel(DsEvalNuArgs a) {
     const bool live = k < a.n;
     if (!live) k = a.n - 1;
     DsNeutrino e;
-    dsn::ds_crust_neutrino(a.rho[k], a.T[k], ds_load_comp(a.ionic + (size_t)11 * k), a.chi[k], a.Tcn[k],
-                           a.channels, e);
+    bool unused = false;
+    dsn::ds_crust_neutrino<false>(a.rho[k], a.T[k], ds_load_comp(a.ionic + (size_t)11 * k), a.chi[k], a.Tcn[k],
+                                  a.channels, e, unused);
     if (!live) return;
     double* o = a.eps + (size_t)6 * k;
     o[0] = e.total; o[1] = e.pair; o[2] = e.photo; o[3] = e.plasma; o[4] = e.brems; o[5] = e.pbf;

@@ -21,15 +21,17 @@ __global__ void ds_dsmath_kernel(int fn, int n, const double* x, const double* y
     if (i >= n) return;
     if (fn == 9) out[i] = x[i] / y[i];                       // IEEE division as the compiler emits it
     else if (fn == 10) {                                      // branch-free form (dconst.cuh) + its fallback
+        bool bad = false;
         DS_DEN_SCOPE(true);
         const DsDen<true> d = den(y[i]);
         const double q = x[i] / d;
-        out[i] = ds_den_bad ? x[i] / DsDen<false>(y[i], nullptr) : q;
+        out[i] = bad ? x[i] / DsDen<false>(y[i], nullptr) : q;
     } else if (fn == 11) {                                    // fast path only: NaN marks a raised flag
+        bool bad = false;
         DS_DEN_SCOPE(true);
         const DsDen<true> d = den(y[i]);
         const double q = x[i] / d;
-        out[i] = ds_den_bad ? nan("") : q;
+        out[i] = bad ? nan("") : q;
     }
     else out[i] = ds_dsmath_dispatch(fn, x[i], y[i]);
 }
