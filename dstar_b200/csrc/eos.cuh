@@ -53,7 +53,7 @@ DS_D void lattice_properties(double rho, double T, const DsComp& c, double& ne, 
     rs = dsm::pow(3.0 / den_c(fourpi) / den(ne), onethird) / den_c(a_Bohr);
     Gamma_e = 2.0 * Rydberg / den_c(boltzmann) / den(T) / den(rs);
     Gamma = Gamma_e * c.Z53;
-    ionQ = sqrt(3.0 * (Gamma_e * Gamma_e) * Melectron / den(rs) / den_c(amu) * c.Z2XoA2 * c.A / den(c.Z));
+    ionQ = sq(3.0 * (Gamma_e * Gamma_e) * Melectron / den(rs) / den_c(amu) * c.Z2XoA2 * c.A / den(c.Z));
 }
 
 DS_D double nuclear_volume_fraction(double rho, const DsComp& c, double nuclear_radius) {
@@ -73,7 +73,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     const double theta_low = DS_R4(0.005);
     const DsDen<FAST> Gamma_eD = den(Gamma_e);
     double theta = theta_fac * rs / Gamma_eD;
-    double sqth = sqrt(theta);
+    double sqth = sq(theta);
     double theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta3 * theta;
     const DsDen<FAST> thetaD = den(theta), theta2D = den(theta2);
     double t1, t2, t1_h, t2_h, t1_hh, t2_hh;
@@ -149,7 +149,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double c_h = DS_R4(0.025248) * exp1th / theta2 * e + c * e_h / e;
     double c_hh = DS_R4(0.025248) * exp1th / theta2 * (e_h + (1.0 - 2.0 * theta) / theta2D * e) +
                   c_h * e_h / e + c * e_hh / e - c * dsd::ipow<2>(e_h / e);
-    const DsDen<FAST> discr = den(sqrt(4.0 * e - d * d));
+    const DsDen<FAST> discr = den(sq(4.0 * e - d * d));
     double di_h = 0.5 / discr * (4.0 * e_h - 2.0 * d * d_h);
     double di_hh = (-dsd::ipow<2>((2.0 * e_h - d * d_h) / discr) + 2.0 * e_hh - d_h * d_h - d * d_hh) / discr;
 
@@ -166,7 +166,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double b2_hh = b_hh - (c_hh * d + 2.0 * c_h * d_h + c * d_hh) / e +
                    (2.0 * (c_h * d + c * d_h - c * d * e_h / e) * e_h + c * d * e_hh) / e2D;
 
-    const DsDen<FAST> sqge = den(sqrt(Gamma_e));
+    const DsDen<FAST> sqge = den(sq(Gamma_e));
     double s2 = -2.0 / e * b2 * sqge;
     double s2h = b2_h / b2 - e_h / e;
     double s2_h = s2 * s2h;
@@ -269,7 +269,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     const double CTFfac = ds_hc.ctf_fac;
     double Z13 = dsm::pow(Z, onethird);
     double cDH = (Z / den(s3)) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
-    double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / den(sqrt(Z13)));
+    double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / den(sq(Z13)));
     double xrs = ds_hc.xrs;
     const DsDen<FAST> rsD = den(rs), Gamma_eD = den(Gamma_e);
     const DsDen<FAST> xr = den(xrs / rsD);
@@ -278,7 +278,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     double a = DS_R4(1.11) * dsm::pow(Z, DS_R4(0.475));
     double b = DS_R4(0.2) + DS_R4(0.078) * (lZ * lZ);
     double nu = DS_R4(1.16) + DS_R4(0.08) * lZ;
-    double sGam = sqrt(Gamma_e);
+    double sGam = sq(Gamma_e);
     double nuGam = dsm::pow(Gamma_e, nu);
     double nuGam_g = nu * nuGam / Gamma_eD;
     double nuGam_gg = (nu - 1.0) * nuGam_g / Gamma_eD;
@@ -300,7 +300,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     double cor1_xx = p1 * (ty * (3.0 / den(xr * xr) + dsd::ipow<2>(ty2_x / ty2) - ty2_xx / ty2) - ty_x * tyx);
     double cor1_gg = p1 * rs3 * ty1_gg / ty2;
     double cor1_xg = -p1 * ty_g * tyx;
-    double u0 = DS_R4(0.78) * sqrt(Gamma_e / den(Z)) * rs3;
+    double u0 = DS_R4(0.78) * sq(Gamma_e / den(Z)) * rs3;
     double u0_x = -3.0 * u0 / xr;
     double u0_g = 0.5 * u0 / Gamma_eD;
     double u0_xx = -4.0 * u0_x / xr;
@@ -317,9 +317,9 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     double cor0_gg = (u0_gg - 2.0 * u0_g * d0_g / d0 + 2.0 * u0 * dsd::ipow<2>(d0_g / d0)) / d0;
     double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / den(d0 * d0)) / d0;
 
-    const DsDen<FAST> rgam = den(sqrt(1.0 + xr * xr));
+    const DsDen<FAST> rgam = den(sq(1.0 + xr * xr));
     double q1 = DS_R4(0.18) / den(dsm::pow(Z, 0.25));
-    double q2 = DS_R4(0.2) + DS_R4(0.37) / den(sqrt(Z));
+    double q2 = DS_R4(0.2) + DS_R4(0.37) / den(sq(Z));
     const DsDen<FAST> h1u = den(1.0 + DS_R4(0.2) * (xr * xr));
     const DsDen<FAST> h1d = den(1.0 + q1 * xr + q2 * (xr * xr));
     double h1 = h1u / h1d;
@@ -383,7 +383,7 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     b[2] = a[3] / den(1.0 + lZ);
     b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / den(dsm::pow(Z, 1.5));
 
-    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sqrt(1.0 + b[1] / den(xr * xr));
+    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sq(1.0 + b[1] / den(xr * xr));
     double finfx = -b[1] / den((b[1] + xr * xr) * xr);
     double finf_x = finf * finfx;
     double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / den((b[1] + xr * xr) * xr);
@@ -426,7 +426,7 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
         double supb_xx = em2y1 * (y1_xx - 2.0 * (y1_x * y1_x) / y1 - y1_x * supb_x);
         double supb_gg = em2y1 * (y1_gg - 2.0 * (y1_g * y1_g) / y1 - y1_g * supb_g);
         double supb_xg = em2y1 * (y1_xg - 2.0 * y1_x * y1_g / y1 - y1_g * supb_x);
-        sup = sqrt(supa / supb);
+        sup = sq(supa / supb);
         double supx = 0.5 * (supa_x / supa - supb_x / supb);
         sup_x = sup * supx;
         double supg = 0.5 * (supa_g / supa - supb_g / supb);
@@ -487,13 +487,13 @@ DS_D void ii_liquid(double Gamma, double theta, DsThermo& r, bool& bad) {
     const double A1 = (double)A1f, A2 = (double)A2f, A3 = (double)A3f;
     const double B1 = DS_R4(4.50e-3), B2 = DS_R4(170.0), B3 = DS_R4(-8.4e-5), B4 = DS_R4(3.70e-3);
 
-    double f0 = A1 * (sqrt(Gamma * (A2 + Gamma)) -
-                      A2 * dsm::log(sqrt(Gamma / den(A2)) + sqrt(1.0 + Gamma / den(A2)))) +
-                2.0 * A3 * (sqrt(Gamma) - dsm::atan(sqrt(Gamma)));
+    double f0 = A1 * (sq(Gamma * (A2 + Gamma)) -
+                      A2 * dsm::log(sq(Gamma / den(A2)) + sq(1.0 + Gamma / den(A2)))) +
+                2.0 * A3 * (sq(Gamma) - dsm::atan(sq(Gamma)));
     double G2 = Gamma * Gamma;
     double G15 = dsm::pow(Gamma, 1.5);
     double f = f0 + B1 * (Gamma - B2 * dsm::log(1.0 + Gamma / den(B2))) + 0.5 * B3 * dsm::log(1.0 + G2 / den(B4));
-    double u = G15 * (A1 / den(sqrt(A2 + Gamma)) + A3 / den(1.0 + Gamma)) +
+    double u = G15 * (A1 / den(sq(A2 + Gamma)) + A3 / den(1.0 + Gamma)) +
                G2 * (B1 / den(B2 + Gamma) + B3 / den(B4 + G2));
     double cv = 0.5 * G15 * (A3 * (Gamma - 1.0) / den(dsd::ipow<2>(Gamma + 1.0)) - A1 * A2 / den(dsm::pow(Gamma + A2, 1.5))) +
                 G2 * (B3 * (G2 - B4) / den(dsd::ipow<2>(G2 + B4)) - B1 * B2 / den(dsd::ipow<2>(Gamma + B2)));
@@ -625,7 +625,7 @@ DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsTh
     DS_DEN_SCOPE(FAST);
     const double sevensixth = (double)(7.0f / 6.0f);
     double Gamma = Gamma_e * dsm::pow(Z, fivethird);
-    double theta = Gamma * sqrt(3.0 * Melectron / den(A) / den_c(amu) / den(rs)) / den(dsm::pow(Z, sevensixth));
+    double theta = Gamma * sq(3.0 * Melectron / den(A) / den_c(amu) / den(rs)) / den(dsm::pow(Z, sevensixth));
     DsThermo ie, ii;
     if (phase == ds_liquid_phase) {
         ie_liquid<FAST>(Gamma_e, rs, Z, ie, bad);
@@ -644,10 +644,10 @@ DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r
     const double threshold = DS_R4(1.0e-9);
     double Gamma = Gamma_e * c.Z53;
     double dif0;
-    if (rs < threshold) dif0 = c.Z52 - sqrt(dsd::ipow<3>(c.Z2) / den(c.Z));
-    else dif0 = c.ZZ1_32 - sqrt(dsd::ipow<3>(c.Z2 + c.Z) / den(c.Z));
+    if (rs < threshold) dif0 = c.Z52 - sq(dsd::ipow<3>(c.Z2) / den(c.Z));
+    else dif0 = c.ZZ1_32 - sq(dsd::ipow<3>(c.Z2 + c.Z) / den(c.Z));
     double difR = dif0 / den(c.Z52);
-    double difFDH = dif0 * Gamma_e * sqrt(onethird * Gamma_e);
+    double difFDH = dif0 * Gamma_e * sq(onethird * Gamma_e);
     double D = c.Z2 / den(c.Z * c.Z);
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (fabs(D - 1.0) < threshold) return;
@@ -682,7 +682,7 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
     Gamma = Gamma_e * c.Z53;
     phase = (Gamma < rq.Gamma_melt) ? ds_liquid_phase : ds_solid_phase;
     double ionQ2 = 3.0 * (Gamma_e * Gamma_e) / den(rs) / den(Mu) * c.Z2XoA2 * c.A / den(c.Z);
-    ionQ = sqrt(ionQ2);
+    ionQ = sq(ionQ2);
     if (phase == ds_liquid_phase && ionQ2 > Q2_threshold) err = 1;
 
     double f = 0, u = 0, p = 0, s = 0, cv = 0, dpr = 0, dpt = 0;
@@ -774,9 +774,9 @@ DS_D void MB77(double n, double T, double Tns, DsThermo& r, bool& bad) {
     double R;
     if (T < Tns) {
         double tau = T / den(Tns);
-        double v = sqrt(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / den(sqrt(tau)) + DS_R4(1.764) / den(tau));
-        R = dsm::pow(DS_R4(0.4186) + sqrt((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
-            dsm::exp(DS_R4(1.456) - sqrt((double)(1.456f * 1.456f) + v * v));
+        double v = sq(1.0 - tau) * (DS_R4(1.456) - DS_R4(0.157) / den(sq(tau)) + DS_R4(1.764) / den(tau));
+        R = dsm::pow(DS_R4(0.4186) + sq((double)(1.007f * 1.007f) + dsd::ipow<2>(DS_R4(0.5010) * v)), 2.5) *
+            dsm::exp(DS_R4(1.456) - sq((double)(1.456f * 1.456f) + v * v));
     } else {
         R = 1.0;
     }

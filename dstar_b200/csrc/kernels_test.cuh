@@ -33,5 +33,11 @@ __global__ void ds_dsmath_kernel(int fn, int n, const double* x, const double* y
         const double q = x[i] / d;
         out[i] = bad ? nan("") : q;
     }
+    else if (fn == 12) out[i] = sqrt(x[i]);                   // IEEE square root as the compiler emits it
+    else if (fn == 13) {                                      // branch-free form; NaN payload 0x7ff8..01 marks a raised flag
+        bool bad = false;
+        const double r = ds_sqrt<true>(x[i], &bad);
+        out[i] = bad ? __longlong_as_double(0x7ff8000000000001ll) : r;
+    }
     else out[i] = ds_dsmath_dispatch(fn, x[i], y[i]);
 }

@@ -41,12 +41,12 @@ DS_D double plasma(double t, double r, bool& bad) {
                          dsm::exp(-dsd::ipow<2>(enum_ / den(0.57 - 0.25 * x)));
     }
     double lamb = 1.686e-10 * t;
-    double gamd = 1.1095e11 * r / den((t * t) * sqrt(1.0 + dsm::pow(1.019e-6 * r, two_thirds)));
-    double gam = sqrt(gamd);
-    double ft = 2.4 + 0.6 * sqrt(gam) + 0.51 * gam + 1.25 * dsm::pow(gam, 1.5);
+    double gamd = 1.1095e11 * r / den((t * t) * sq(1.0 + dsm::pow(1.019e-6 * r, two_thirds)));
+    double gam = sq(gamd);
+    double ft = 2.4 + 0.6 * sq(gam) + 0.51 * gam + 1.25 * dsm::pow(gam, 1.5);
     double fl = (8.6 * gamd + 1.35 * dsm::pow(gam, 7.0 / den_c(2.0))) / den(225.0 - 17.0 * gam + gamd);
     double qap;
-    if (fabs(sqrt(gamd)) > 700.0) qap = 0.0;
+    if (fabs(sq(gamd)) > 700.0) qap = 0.0;
     else qap = fxy * (fl + ft) * dsm::exp(-gam) * dsd::ipow<3>(gamd) * dsd::ipow<9>(lamb) * 3.0e21;
     return qap * cvd;
 }
@@ -61,8 +61,8 @@ DS_D double pair(double temp, double rhom, bool& bad) {
     const double coem = (cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap);
     double lam = temp / den_c(5.9302e9);
     double xi = dsm::pow(rhom * 1.0e-9, onethird) / den(lam);
-    double qp1 = 10.74800 * (lam * lam) + 0.3967 * sqrt(lam) + 1.005;
-    double qp2 = rhom / den(7.692e7 * dsd::ipow<3>(lam) + 9.715e6 * sqrt(lam));
+    double qp1 = 10.74800 * (lam * lam) + 0.3967 * sq(lam) + 1.005;
+    double qp2 = rhom / den(7.692e7 * dsd::ipow<3>(lam) + 9.715e6 * sq(lam));
     double qp = (1.0 / den(qp1)) * dsm::pow(1.0 + qp2, -0.3);
     double axi = a0 + a1 * xi + a2 * (xi * xi);
     double fp1, fp2;
@@ -128,13 +128,13 @@ DS_D double pbf(double kF, double T, double Tns, bool& bad) {
     double tau = T / Tns;  // Tns = 0 without a gap: plain division (T/0 = inf takes the early return)
     if (kF == 0.0 || tau > 1.0 || tau < 0.01) return 0.0;
     double xF = kF * hbarc_n / den_c(Mn_n);
-    double eF = sqrt(1.0 + xF * xF);
+    double eF = sq(1.0 + xF * xF);
     double mstar = eF;
-    double v = sqrt(1.0 - tau) * (1.456 - 0.157 / den(sqrt(tau)) + 1.764 / den(tau));
+    double v = sq(1.0 - tau) * (1.456 - 0.157 / den(sq(tau)) + 1.764 / den(tau));
     double v2 = v * v;
     double F1 = v2 * (0.602 + v2 * (0.5942 + 0.288 * v2));
-    double F2 = sqrt(DS_R4(0.5547) + sqrt(0.4453 * 0.4453 + 0.01130 * v2));
-    double F3 = dsm::exp(-sqrt(4.0 * v2 + 2.245 * 2.245) + 2.245);
+    double F2 = sq(DS_R4(0.5547) + sq(0.4453 * 0.4453 + 0.01130 * v2));
+    double F3 = dsm::exp(-sq(4.0 * v2 + 2.245 * 2.245) + 2.245);
     double F = F1 * F2 * F3;
     double reduct = dsd::ipow<2>(xF / den(eF));
     return qpbf_pre * (cn_dn + 1) * mstar * xF * dsd::ipow<7>(T / den_c(1.0e9)) * F * reduct;

@@ -173,7 +173,7 @@ int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, i
                        double* tab_lnEnu, double* tab_lnK, double* rho_bar1, int32_t* status);
 
 /* ---- test support: one dsmath function on the device (fn = 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 sin,
- * 5 cos, 6 sinh, 7 cosh, 8 atan, 9 x/y, 10 x/y through the shared-denominator division DsDen); dsmath is the deterministic elementary-function layer that plays the
+ * 5 cos, 6 sinh, 7 cosh, 8 atan; 9-13 exercise the branch-free division and square root of dconst.cuh); dsmath is the deterministic elementary-function layer that plays the
  * role of MESA's math_lib for this implementation (dstar_b200/csrc/dsmath.cuh) ---- */
 int dstar_dsmath_eval(dstar_ctx* ctx, int fn, int n, const double* x, const double* y, double* out);
 

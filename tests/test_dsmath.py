@@ -152,3 +152,34 @@ def test_shared_denominator_division_bits():
             assert np.all(took[moderate])          # ... and the flag stays down for every moderate operand pair
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_branch_free_sqrt_bits():
+    """ds_sqrt<true> (dconst.cuh) returns the bits of the IEEE square root for every finite x >= 2^-970 and for
+    zero, and raises its flag (marked by NaN here) for everything else."""
+    import dstar_b200 as ds
+    from dstar_b200._capi import check, p
+    ctx = ds.Context(0, gaps=None)
+    rng = np.random.default_rng(78)
+    try:
+        n = 1 << 22
+        sets = [10.0 ** rng.uniform(-30, 30, n), 10.0 ** rng.uniform(-291, 308, n), rng.uniform(1.0, 4.0, n),
+                (rng.integers(1 << 52, 1 << 53, n).astype(np.float64)) * 2.0 ** -52,
+                np.array([0.0, -0.0, 1.0, 4.0, 2.0 ** -970, 2.0 ** -971, 5e-324, 2.2250738585072014e-308,
+                          1.7976931348623157e308, np.inf, -1.0, np.nan, 2.0, 3.0, 1e-300, 1e300])]
+        for x in sets:
+            x = f64(x); y = np.zeros_like(x)
+            r_plain = np.zeros_like(x); r_fast = np.zeros_like(x)
+            check(ctx.L.dstar_dsmath_eval(ctx.h, 12, len(x), p(x), p(y), p(r_plain)), "dsmath_eval")
+            check(ctx.L.dstar_dsmath_eval(ctx.h, 13, len(x), p(x), p(y), p(r_fast)), "dsmath_eval")
+            with np.errstate(all="ignore"):
+                host = np.sqrt(x)
+            ok = ~np.isnan(host)
+            assert np.array_equal(r_plain.view(np.uint64)[ok], host.view(np.uint64)[ok])
+            took = ~np.isnan(r_fast)
+            assert np.array_equal(r_fast.view(np.uint64)[took], host.view(np.uint64)[took])
+            safe = ((x >= 2.0 ** -970) & np.isfinite(x)) | (x == 0.0)
+            assert np.array_equal(took, safe)
+    finally:
+        ctx.close()
