@@ -1,0 +1,192 @@
+"""The synthetic workloads of BASELINE.json's configs (dstar_b200/workloads.py) at test sizes: parity against the
+CPU oracle, and size-independent properties (batch invariance, idempotence, ragged batches, extreme zone counts)."""
+import numpy as np
+import pytest
+
+from parity_helpers import oracle_evolve_star, oracle_micro_tables
+
+pytestmark = pytest.mark.gpu
+
+TABS = ("tab_lnCp", "tab_lnGamma", "tab_lnEnu", "tab_lnK")
+
+
+@pytest.fixture(scope="module")
+def nscool():
+    import dstar_b200 as ds
+    ds.NScool_init()
+    yield ds
+    ds.NScool_shutdown()
+
+
+def rel(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def check_tables(s, ref, tol=1e-10):
+    for name in TABS:
+        g = s.array(name).reshape(-1, 4); r = ref[name].reshape(-1, 4)
+        assert np.max(np.abs(g[:, 0] - r[:, 0])) < tol, name
+
+
+def test_hooks_sweep_parity(nscool, oracle):
+    """configs[1] (custom_Tc_Qimp): 2 x 2 grid with the example's alt_Qimp / alt_sf hooks -- tables (Tc and Q as
+    the hooks set them per zone) and light curves against the oracle."""
+    from dstar_b200 import workloads
+    stars = workloads.custom_Tc_Qimp(4, resolution=0.4)
+    nscool.create_models(stars)
+    y0 = [s.array("lnT").copy() for s in stars]
+    nscool.evolve_models(stars)
+    for s, lnT0 in zip(stars, y0):
+        ref = oracle_micro_tables(oracle, s, gaps=("ns", "sfb03", "t72"), Tc_cell=s.array("Tc_cell"),
+                                  Tc_face=s.array("Tc_face"))
+        check_tables(s, ref)
+        ev = oracle_evolve_star(oracle, s, lnT0, heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, 1.7],
+                                ctrl=dict(turn_on_extra_heating=1, fix_atmosphere_temperature_when_accreting=0))
+        t, Teff, Qb = s.monitors()
+        assert len(Teff) == 9 and rel(Teff, ev["Teff_monitor"]) < 1e-6
+    # the hooks matter: pasta Qimp (second control) changes the face tables, not the cell tables
+    a, b = stars[0], stars[1]           # same Tc, different pasta Qimp
+    assert np.array_equal(bits(a.array("tab_lnCp")), bits(b.array("tab_lnCp")))
+    assert not np.array_equal(bits(a.array("tab_lnK")), bits(b.array("tab_lnK")))
+    for s in stars:
+        s.free()
+
+
+def test_fit_lightcurve_walkers(nscool, oracle):
+    """configs[2]: MCMC walkers over (Mdot, Q_heating_shallow, Qimp), 7 monitor epochs; two of them against the oracle."""
+    from dstar_b200 import workloads
+    stars = workloads.fit_lightcurve(8, resolution=0.3)
+    nscool.create_models(stars)
+    y0 = [s.array("lnT").copy() for s in stars]
+    nscool.evolve_models(stars)
+    rng = np.random.default_rng(workloads.SEED + 2)
+    rng.uniform(0, 1, 8)
+    Qh = rng.uniform(0.0, 3.0, 8)
+    curves = []
+    for k, s in enumerate(stars):
+        t, Teff, Qb = s.monitors()
+        assert len(Teff) == 7 and np.all(np.isfinite(Teff)) and np.all(Teff > 0)
+        curves.append(Teff)
+        if k in (0, 5):
+            check_tables(s, oracle_micro_tables(oracle, s, gaps=("ns", "sfb03", "t72")))
+            ev = oracle_evolve_star(oracle, s, y0[k], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, float(Qh[k])],
+                                    ctrl=dict(turn_on_extra_heating=1, fix_atmosphere_temperature_when_accreting=0))
+            assert rel(Teff, ev["Teff_monitor"]) < 1e-6
+    assert len({tuple(np.round(c, 3)) for c in curves}) == 8      # eight different walkers, eight different curves
+    for s in stars:
+        s.free()
+
+
+def test_accretion_history_neutron_channels(nscool, oracle):
+    """configs[3]: two accretion cycles (10 epochs) with neutron + superfluid-phonon conductivity and shell Urca."""
+    from dstar_b200 import workloads
+    stars = workloads.accretion(2, resolution=0.6)
+    nscool.create_models(stars)
+    y0 = [s.array("lnT").copy() for s in stars]
+    nscool.evolve_models(stars)
+    s = stars[0]
+    ref = oracle_micro_tables(oracle, s, gaps=("ns", "gc", "t72"), cond_ctrl=(1, 1, 1, 1, 10.0, 9.0),
+                              shell_Urca=(1, 1.0, 28.5))
+    check_tables(s, ref)
+    ev = oracle_evolve_star(oracle, s, y0[0], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, 1.0], T_atm=5.0e8,
+                            ctrl=dict(turn_on_extra_heating=1))
+    t, Teff, Qb = s.monitors()
+    assert len(Teff) == 10 and rel(Teff, ev["Teff_monitor"]) < 1e-6
+    for s in stars:
+        s.free()
+
+
+def _star(ds, res, **kw):
+    base = dict(atm_model="pcy97", target_resolution_lnP=res, number_epochs=2, basic_epoch_Mdots=[1.0e17, 0.0],
+                basic_epoch_boundaries=[0.0, 50.0, 1050.0], core_temperature=1.4e8,
+                atmosphere_temperature_when_accreting=2.4e8, turn_on_extra_heating=True, Q_heating_shallow=0.1,
+                lgP_min_heating_shallow=27.5, lgP_max_heating_shallow=28.5, which_neutron_1S0_gap="sfb03",
+                fix_Qimp=True, Qimp=1.0)
+    base.update(kw)
+    return ds.NScool(None, **base)
+
+
+def test_ragged_batch_is_bitwise_batch_invariant(nscool):
+    """Stars with different zone counts in ONE batch: every table entry, monitor and solver counter equals the
+    star's own single-star run bit for bit (no cross-star coupling, no dependence on the launch geometry)."""
+    ds = nscool
+    res = (0.6, 0.17, 0.31, 0.17)
+    batch = [_star(ds, r, core_temperature=1.0e8 * (1 + i)) for i, r in enumerate(res)]
+    ds.create_models(batch)
+    ds.evolve_models(batch)
+    assert len({s.get_int("nz") for s in batch}) == 3
+    for i, r in enumerate(res):
+        solo = _star(ds, r, core_temperature=1.0e8 * (1 + i))
+        solo.create_model()
+        solo.evolve_model()
+        for name in TABS + ("lnT",):
+            assert np.array_equal(bits(batch[i].array(name)), bits(solo.array(name))), (i, name)
+        for a, b in zip(batch[i].monitors(), solo.monitors()):
+            assert np.array_equal(bits(a), bits(b))
+        np.testing.assert_array_equal(batch[i].counters(), solo.counters())
+        solo.free()
+    for s in batch:
+        s.free()
+
+
+@pytest.mark.parametrize("res", [0.0252, 3.0])
+def test_extreme_zone_counts(nscool, oracle, res):
+    """Largest grid the kernels accept (nz ~ 500 of 512: the 512-thread evolve kernel) and a crust of a handful of zones."""
+    s = _star(nscool, res)
+    s.create_model()
+    nz = s.get_int("nz")
+    assert (nz > 480 and nz <= 512) if res < 1 else (3 <= nz <= 6)
+    lnT0 = s.array("lnT").copy()
+    s.evolve_model()
+    check_tables(s, oracle_micro_tables(oracle, s, gaps=("ns", "sfb03", "t72")))
+    ev = oracle_evolve_star(oracle, s, lnT0, heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.5, 28.5, 0.1], T_atm=2.4e8,
+                            ctrl=dict(turn_on_extra_heating=1))
+    assert rel(s.monitors()[1], ev["Teff_monitor"]) < 1e-6
+    s.free()
+
+
+def test_too_many_zones_is_refused(nscool):
+    import dstar_b200 as ds
+    s = _star(nscool, 0.02)      # ~633 zones > 512
+    with pytest.raises(ds.DStarError):
+        s.create_model()
+    s.free()
+
+
+def test_full_size_sweep_properties(nscool):
+    """configs[1] at BASELINE size (256 stars x 253 zones): everything converges, the coefficient pass is idempotent,
+    cell tables depend on the core Tc only through ... nothing (same crust), face tables only on pasta Qimp, and a
+    star pulled out of the batch reproduces its in-batch result bit for bit."""
+    from dstar_b200 import workloads
+    ds = nscool
+    stars = workloads.custom_Tc_Qimp(256, resolution=0.05)
+    ds.create_models(stars)
+    first = {n: stars[37].array(n).copy() for n in TABS}
+    ds.create_models(stars)                                    # idempotence of the coefficient pass
+    for n in TABS:
+        assert np.array_equal(bits(stars[37].array(n)), bits(first[n])), n
+    ds.evolve_models(stars)
+    Teff = np.array([s.monitors()[1] for s in stars])
+    assert Teff.shape == (256, 9) and np.all(np.isfinite(Teff)) and np.all(Teff > 1e5) and np.all(Teff < 1e7)
+    nz = stars[0].get_int("nz")
+    assert 250 <= nz <= 256
+    # grid structure: star index = 16 * i_Tc + j_Q
+    for j in (1, 9):
+        assert np.array_equal(bits(stars[j].array("tab_lnCp")), bits(stars[0].array("tab_lnCp")))
+        assert np.array_equal(bits(stars[16 * 3 + j].array("tab_lnK")), bits(stars[j].array("tab_lnK")))
+    # hotter core => hotter surface at the last (longest-cooled) epoch, for every Qimp column
+    last = Teff[:, -1].reshape(16, 16)
+    assert np.all(np.diff(last, axis=0) > 0)
+    # batch invariance at full size
+    solo = workloads.custom_Tc_Qimp(256, resolution=0.05)[200]
+    solo.create_model(); solo.evolve_model()
+    for a, b in zip(stars[200].monitors(), solo.monitors()):
+        assert np.array_equal(bits(a), bits(b))
+    np.testing.assert_array_equal(stars[200].counters(), solo.counters())
+    for s in stars:
+        s.free()
