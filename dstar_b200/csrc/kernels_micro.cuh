@@ -132,11 +132,16 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, doub
 // launch keeps it out of the hot loop's register allocation (a conditional call inside the loop cost 10 %).
 // With FAST = false and a.redo == null the kernel is the single plain pass (used for the faces, whose EOS is
 // mostly dead code: only Gamma, Theta and mu_e feed the conductivity).
+struct DsZoneIn {
+    DsComp c;
+    double rho, chi, Tc[3];
+};
 template <bool FACE, int G, bool FAST>
 __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     __shared__ double s_h[DS_NTAB], s_v[G][3][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
+    __shared__ DsZoneIn s_zone[G];
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
@@ -151,21 +156,26 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         // groups past the end re-evaluate the last zone (results discarded) so that every thread of the
         // CTA reaches the DS_PHASE alignment points inside the evaluators
         const int g = on ? gq : a.total_zones - 1;
-        int star = 0, iz = 0, nz = 0;
-        DsComp c{};
-        double rho = 0.0, chi = 0.0, Tc[3] = {0.0, 0.0, 0.0};
-        {
-            star = a.zone_star[g];
-            iz = g - a.zone_offset[star];
-            nz = a.zone_offset[star + 1] - a.zone_offset[star];
-            c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
-            rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
-            chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
-            const double kn = dse::neutron_wavenumber(rho, c, chi);
+        // zone-level inputs live ONCE per group in shared memory (all 128 lanes read them by broadcast) instead of
+        // 16 doubles in every lane's registers: the evaluators are register-starved at 72 registers per thread
+        const int star = a.zone_star[g];
+        const int iz = g - a.zone_offset[star];
+        const int nz = a.zone_offset[star + 1] - a.zone_offset[star];
+        if (it == 0) {
+            DsZoneIn& zi = s_zone[grp];
+            zi.c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
+            zi.rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
+            zi.chi = dse::nuclear_volume_fraction(zi.rho, zi.c, DS_DEFAULT_NUCLEAR_RADIUS);
+            const double kn = dse::neutron_wavenumber(zi.rho, zi.c, zi.chi);
             const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
-            if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
-            else ds_sf_get_results(sf, 0.0, kn, Tc);
+            if (Tcin) { zi.Tc[0] = Tcin[3 * (size_t)g]; zi.Tc[1] = Tcin[3 * (size_t)g + 1]; zi.Tc[2] = Tcin[3 * (size_t)g + 2]; }
+            else ds_sf_get_results(sf, 0.0, kn, zi.Tc);
         }
+        __syncthreads();
+        const DsComp& c = s_zone[grp].c;
+        const double& rho = s_zone[grp].rho;
+        const double& chi = s_zone[grp].chi;
+        const double* Tc = s_zone[grp].Tc;
         if (FACE) {
             if (a.cond.include_neutrons && c.Yn > 0.0 && it == 0) {
                 // impurity Coulomb logarithm: T-independent, once per zone (neutron_conductivity.f:382)
