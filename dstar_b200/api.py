@@ -107,6 +107,27 @@ def host_interp_pm(x, y):
     return f
 
 
+def abuntime_table(path, lgP_increment=0.005, abundance_threshold=0.01):
+    """Preprocess an abuntime composition file as dStar_crust/preprocessor does (read, cull, reduce, extend with
+    HZ90): returns (names, Z, A, lgP(nz), Y(nz, nnet)).  Host only."""
+    import ctypes as C
+    L = lib()
+    nnet, nz = C.c_int32(), C.c_int32()
+    bp = os.fsencode(path)
+    rc = L.dstar_abuntime_table(bp, C.c_double(lgP_increment), C.c_double(abundance_threshold), C.byref(nnet),
+                                C.byref(nz), None, None, None, None, None, 0, 0)
+    if rc != 0:
+        raise DStarError("abuntime_table: %s" % L.dstar_NScool_last_error().decode())
+    names = C.create_string_buffer(6 * nnet.value)
+    Z = np.zeros(nnet.value); A = np.zeros(nnet.value); lgP = np.zeros(nz.value); Y = np.zeros((nz.value, nnet.value))
+    rc = L.dstar_abuntime_table(bp, C.c_double(lgP_increment), C.c_double(abundance_threshold), C.byref(nnet),
+                                C.byref(nz), names, p(Z), p(A), p(lgP), p(Y), nnet.value, nz.value)
+    if rc != 0:
+        raise DStarError("abuntime_table: %s" % L.dstar_NScool_last_error().decode())
+    nm = [names.raw[6 * k:6 * k + 6].split(b"\0")[0].decode() for k in range(nnet.value)]
+    return nm, Z, A, lgP, Y
+
+
 class Batch:
     """dstar_batch: stars flattened zone-major, resident in HBM."""
 

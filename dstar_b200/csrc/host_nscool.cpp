@@ -351,7 +351,8 @@ double synthetic_mass_excess(double Z, double A) {
 }
 const char* element_names[] = {"n", "h", "he", "li", "be", "b", "c", "n", "o", "f", "ne", "na", "mg", "al", "si", "p", "s",
                                "cl", "ar", "k", "ca", "sc", "ti", "v", "cr", "mn", "fe", "co", "ni", "cu", "zn", "ga", "ge",
-                               "as", "se", "br", "kr", "rb", "sr", "y", "zr", "nb", "mo", "tc", "ru", "rh", "pd", "ag", "cd"};
+                               "as", "se", "br", "kr", "rb", "sr", "y", "zr", "nb", "mo", "tc", "ru", "rh", "pd", "ag", "cd",
+                               "in", "sn", "sb", "te", "i", "xe", "cs", "ba"};
 bool nuclide_from_name(const std::string& nm, double& Z, double& A) {
     if (nm == "n") { Z = 0; A = 1; return true; }
     if (nm == "p") { Z = 1; A = 1; return true; }
@@ -422,6 +423,121 @@ void hz90_table(const Network& net, const std::vector<double>& lgP, std::vector<
         Y[(size_t)nis * j + in] = Xn[layer];
         Y[(size_t)nis * j + ii] = (1.0 - Xn[layer]) / net.A[ii];
     }
+}
+
+// ------------------------------------------------------------------ abuntime composition files
+// dStar_crust/preprocessor: read_abuntime (abuntime.f:18-133), reduce_abuntime (:135-179), extend_abuntime
+// (:181-268), driven as in process_abuntime.f:66-76.  Y is (nion, nz) column-major: Y[k + nion * j].
+struct AbunTable {
+    std::vector<std::string> isos;
+    std::vector<double> lgP, Y;
+    double T = 0;
+    int nz() const { return (int)lgP.size(); }
+    int nion() const { return (int)isos.size(); }
+};
+std::string fixed_field(const std::string& line, size_t pos, size_t len) {
+    return pos < line.size() ? line.substr(pos, len) : std::string();
+}
+int read_abuntime(const std::string& path, double delta_lgP, AbunTable& out, std::string& err) {
+    const double gravity = 1.85052e14, mdot = 8.8e4 * 0.3;  // abuntime.f:9-10
+    std::ifstream f(path);
+    if (!f) { err = "read_abuntime: cannot open " + path; return -1; }
+    std::string line;
+    if (!std::getline(f, line)) { err = "read_abuntime: empty file"; return -1; }
+    const int nion = std::atoi(fixed_field(line, 1, 5).c_str());        // (1x,i5)
+    if (nion <= 0) { err = "read_abuntime: bad species count"; return -1; }
+    out.isos.assign(nion, "");
+    out.lgP.clear(); out.Y.clear();
+    std::vector<double> ycur(nion);
+    double last_lgP = -100.0, T = 0.0;
+    while (std::getline(f, line)) {
+        if (trim(line).empty()) continue;
+        // (1x,1e18.10,2e11.3,2X,2E18.10): time, T, rho, EFe, EFn
+        double time = 0;
+        if (!parse_real(trim(fixed_field(line, 1, 18)), time)) { err = "read_abuntime: bad header line: " + line; return -1; }
+        parse_real(trim(fixed_field(line, 19, 11)), T);
+        const double lgP = std::log10(gravity * mdot * time);
+        // (1x,5(a5,1pe10.3)) repeated
+        int k = 0;
+        while (k < nion) {
+            if (!std::getline(f, line)) { err = "read_abuntime: truncated abundance block"; return -1; }
+            for (int c = 0; c < 5 && k < nion; ++c, ++k) {
+                out.isos[k] = lower(trim(fixed_field(line, 1 + 15 * c, 5)));
+                if (!parse_real(trim(fixed_field(line, 6 + 15 * c, 10)), ycur[k])) { err = "read_abuntime: bad abundance: " + line; return -1; }
+            }
+        }
+        std::getline(f, line);  // separator
+        if (lgP > last_lgP + delta_lgP) {  // only keep points that advance lgP by more than the increment (:90-95)
+            last_lgP = lgP;
+            out.lgP.push_back(lgP);
+            out.Y.insert(out.Y.end(), ycur.begin(), ycur.end());
+        }
+    }
+    out.T = T * 1.0e9;
+    if (out.lgP.empty()) { err = "read_abuntime: no zones accepted"; return -1; }
+    return 0;
+}
+void reduce_abuntime(const AbunTable& in, double min_abundance, AbunTable& out) {
+    const int nion = in.nion(), nz = in.nz();
+    std::vector<char> keep(nion, 0);
+    for (int j = 0; j < nz; ++j) {
+        double mx = -1.0e300;
+        for (int k = 0; k < nion; ++k) if (in.isos[k] != "n") mx = std::max(mx, in.Y[k + (size_t)nion * j]);
+        for (int k = 0; k < nion; ++k) if (in.Y[k + (size_t)nion * j] > min_abundance * mx) keep[k] = 1;
+    }
+    out = AbunTable();
+    out.T = in.T; out.lgP = in.lgP;
+    for (int k = 0; k < nion; ++k) if (keep[k]) out.isos.push_back(in.isos[k]);
+    const int nnet = out.nion();
+    out.Y.resize((size_t)nnet * nz);
+    for (int j = 0; j < nz; ++j) {
+        int m = 0;
+        for (int k = 0; k < nion; ++k) if (keep[k]) out.Y[m++ + (size_t)nnet * j] = in.Y[k + (size_t)nion * j];
+    }
+}
+int extend_abuntime(const AbunTable& in, double lgP_increment, AbunTable& out, std::string& err) {
+    const double lgP_blend_width = 0.2, lgPmin = 22.0, lgPmax = 33.5;  // abuntime.f:13-14,185
+    const Network hz = hz90_network();
+    const int nion = in.nion(), nz = in.nz(), nhz = (int)hz.names.size();
+    out = AbunTable();
+    out.T = in.T;
+    out.isos = in.isos;
+    std::vector<int> idx_hz(nhz);
+    for (int i = 0; i < nhz; ++i) {
+        auto it = std::find(out.isos.begin(), out.isos.end(), hz.names[i]);
+        if (it == out.isos.end()) { out.isos.push_back(hz.names[i]); idx_hz[i] = (int)out.isos.size() - 1; }
+        else idx_hz[i] = (int)(it - out.isos.begin());
+    }
+    const int nnet = out.nion();
+    const double lo = *std::min_element(in.lgP.begin(), in.lgP.end()), hi = *std::max_element(in.lgP.begin(), in.lgP.end());
+    const int nlow = std::max((int)((lo - lgPmin) / lgP_increment), 1), nhigh = std::max((int)((lgPmax - hi) / lgP_increment), 1);
+    const int nzout = nlow + nz + nhigh;
+    out.lgP.resize(nzout);
+    for (int i = 0; i < nlow; ++i) out.lgP[i] = lo - lgP_increment * (double)(nlow - i);
+    for (int j = 0; j < nz; ++j) out.lgP[nlow + j] = in.lgP[j];
+    for (int i = 1; i <= nhigh; ++i) out.lgP[nlow + nz + i - 1] = hi + lgP_increment * (double)i;
+    std::vector<double> Yhz;
+    hz90_table(hz, out.lgP, Yhz);
+    out.Y.assign((size_t)nnet * nzout, 0.0);
+    for (int j = 0; j < nzout; ++j) {
+        const int src = std::min(std::max(j - nlow, 0), nz - 1);  // first / last abuntime column replicated outside
+        double beta;
+        if (out.lgP[j] <= hi) beta = 0.0;
+        else if (out.lgP[j] > hi + lgP_blend_width) beta = 1.0;
+        else beta = (out.lgP[j] - hi) / lgP_blend_width;
+        const double alpha = 1.0 - beta;
+        for (int k = 0; k < nion; ++k) out.Y[k + (size_t)nnet * j] = in.Y[k + (size_t)nion * src] * alpha;
+        for (int i = 0; i < nhz; ++i) out.Y[idx_hz[i] + (size_t)nnet * j] += Yhz[i + (size_t)nhz * j] * beta;
+    }
+    (void)err;
+    return 0;
+}
+int process_abuntime(const std::string& path, double lgP_increment, double abundance_threshold, AbunTable& out, std::string& err) {
+    AbunTable raw, red;
+    int rc = read_abuntime(path, lgP_increment, raw, err);
+    if (rc) return rc;
+    reduce_abuntime(raw, abundance_threshold, red);
+    return extend_abuntime(red, lgP_increment, out, err);
 }
 
 // ------------------------------------------------------------------ tables shared between stars
@@ -510,15 +626,37 @@ int build_crust_table(const Controls& c, std::shared_ptr<CrustTable>& out) {
                   c.scale_sf_critical_temperatures[1], c.eos_gamma_melt_pt);
     auto it = g_crust_cache.find(key);
     if (it != g_crust_cache.end()) { out = it->second; return 0; }
-    if (c.crust_composition != "HZ90") { g_err = "crust_composition '" + c.crust_composition + "' not available (HZ90 only)"; return -1; }
     auto tab = std::make_shared<CrustTable>();
-    tab->net = hz90_network();
-    const int N = 2048, nis = (int)tab->net.Z.size();  // generate_HZ90.f:12-14
-    tab->nv = N; tab->T = c.crust_reference_temperature;
-    tab->lgP.resize(N);
-    for (int i = 0; i < N; ++i) tab->lgP[i] = 22.0 + (double)i * (33.5 - 22.0) / (double)(N - 1);
     std::vector<double> Y;
-    hz90_table(tab->net, tab->lgP, Y);
+    tab->T = c.crust_reference_temperature;
+    if (c.crust_composition == "HZ90") {
+        tab->net = hz90_network();
+        const int n_hz = 2048;  // generate_HZ90.f:12-14
+        tab->lgP.resize(n_hz);
+        for (int i = 0; i < n_hz; ++i) tab->lgP[i] = 22.0 + (double)i * (33.5 - 22.0) / (double)(n_hz - 1);
+        hz90_table(tab->net, tab->lgP, Y);
+    } else {
+        // any other name is an abuntime-format composition file <data_dir>/crust_data/<name>[.data] (the
+        // reference caches the preprocessed table as <name>.bin; here the preprocessing runs at load time)
+        std::string path = g_data_dir + "/crust_data/" + c.crust_composition;
+        if (!std::ifstream(path)) path += ".data";
+        AbunTable ab;
+        std::string err;
+        if (process_abuntime(path, 0.005, 0.01, ab, err) != 0) {  // defaults of abuntime.f:11-12
+            g_err = "crust_composition '" + c.crust_composition + "': " + err;
+            return -1;
+        }
+        for (const auto& nm : ab.isos) {
+            double Z, A;
+            if (!nuclide_from_name(nm, Z, A)) { g_err = "crust_composition: unknown nuclide '" + nm + "'"; return -1; }
+            tab->net.names.push_back(nm); tab->net.Z.push_back(Z); tab->net.A.push_back(A);
+            tab->net.mass_excess.push_back(synthetic_mass_excess(Z, A));
+        }
+        tab->lgP = ab.lgP;
+        Y = ab.Y;
+    }
+    const int N = (int)tab->lgP.size(), nis = (int)tab->net.Z.size();
+    tab->nv = N;
     const int nch = tab->net.ncharged();
     std::vector<double> ionic((size_t)11 * N), Yion((size_t)nch * N), Zion, Aion, ME;
     for (int i = 0; i < nis; ++i) if (tab->net.Z[i] > 0) { Zion.push_back(tab->net.Z[i]); Aion.push_back(tab->net.A[i]); ME.push_back(tab->net.mass_excess[i]); }
@@ -773,6 +911,27 @@ extern "C" {
 int dstar_host_interp_pm(const double* x, int n, double* f) {
     if (!x || !f || n < 1) return -1;
     interp_pm(x, n, f);
+    return 0;
+}
+
+int dstar_abuntime_table(const char* path, double lgP_increment, double abundance_threshold, int32_t* nnet, int32_t* nz,
+                         char* names, double* Z, double* A, double* lgP, double* Y, int cap_net, int cap_z) {
+    if (!path || !nnet || !nz) return -1;
+    AbunTable ab;
+    std::string err;
+    if (process_abuntime(path, lgP_increment, abundance_threshold, ab, err) != 0) { g_err = err; return -1; }
+    *nnet = ab.nion(); *nz = ab.nz();
+    if (!names && !Z && !A && !lgP && !Y) return 0;  // size query
+    if (cap_net < ab.nion() || cap_z < ab.nz()) { g_err = "abuntime_table: buffers too small"; return -2; }
+    for (int k = 0; k < ab.nion(); ++k) {
+        double z = 0, a = 0;
+        if (!nuclide_from_name(ab.isos[k], z, a)) { g_err = "abuntime_table: unknown nuclide '" + ab.isos[k] + "'"; return -3; }
+        if (names) { std::memset(names + 6 * k, 0, 6); std::strncpy(names + 6 * k, ab.isos[k].c_str(), 5); }
+        if (Z) Z[k] = z;
+        if (A) A[k] = a;
+    }
+    if (lgP) std::copy(ab.lgP.begin(), ab.lgP.end(), lgP);
+    if (Y) std::copy(ab.Y.begin(), ab.Y.end(), Y);
     return 0;
 }
 

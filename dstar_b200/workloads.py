@@ -93,5 +93,27 @@ def accretion(n_star=4096, resolution=0.05, offset=0):
     return stars
 
 
-BUILDERS = {"basic_run": basic_run, "custom_Tc_Qimp": custom_Tc_Qimp, "fit_lightcurve": fit_lightcurve,
+def int16_demo(n_star=1024, resolution=0.05, offset=0):
+    """configs[4]: examples/INT-16-2b-demo/inlist-Q4-H1.7 -- crust composition from an abuntime network-output table
+    (synthetic file of the same format, tools/make_abuntime.py: 63 nuclides + neutrons per zone, blended into HZ90
+    above lgP 30.6), 10 epochs; Qimp and the shallow heating vary per star."""
+    rng = np.random.default_rng(SEED + 4 + 1000 * offset)
+    Qimp = 10.0 ** rng.uniform(0.0, 2.0, n_star)
+    Qh = rng.uniform(0.0, 3.0, n_star)
+    common = dict(_COMMON)
+    common["lgPcrust_bot"] = 32.9
+    stars = []
+    for k in range(n_star):
+        stars.append(NScool(None, **common, target_resolution_lnP=resolution, fix_core_temperature=True,
+                            core_temperature=9.2e7, fix_atmosphere_temperature_when_accreting=False, number_epochs=10,
+                            basic_epoch_Mdots=[1.0e17] + [0.0] * 9,
+                            basic_epoch_boundaries=[-4383.0, 0.0, 1.0, 3.0, 10.0, 30.0, 100.0, 300.0, 1000.0, 3000.0, 6000.0],
+                            turn_on_extra_heating=True, Q_heating_shallow=float(Qh[k]), lgP_min_heating_shallow=27.0,
+                            lgP_max_heating_shallow=28.0, turn_on_shell_Urca=False, which_neutron_1S0_gap="sfb03",
+                            lg_atm_light_element_column=4.0, fix_Qimp=True, Qimp=float(Qimp[k]),
+                            crust_composition="int16_synth"))
+    return stars
+
+
+BUILDERS = {"int16_demo": int16_demo, "basic_run": basic_run, "custom_Tc_Qimp": custom_Tc_Qimp, "fit_lightcurve": fit_lightcurve,
             "accretion": accretion}

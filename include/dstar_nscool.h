@@ -23,6 +23,16 @@ int dstar_ctx_load_gap_file(dstar_ctx* ctx, int type, const char* path);
 /* MESA interp_pm on (4,n) column-major f with f(1,:) preloaded (host utility) */
 int dstar_host_interp_pm(const double* x, int n, double* f);
 
+/* Crust composition from an "abuntime" network-output file (format: dStar_crust/preprocessor/README:3-31):
+ * read_abuntime + reduce_abuntime + extend_abuntime of dStar_crust/preprocessor/src/abuntime.f:18-268, driven as
+ * process_abuntime.f:66-76 does (points culled to lgP_increment, nuclides below abundance_threshold x the most
+ * abundant non-neutron species at every depth dropped, table extended to lgP 22..33.5 and blended into HZ90 over
+ * 0.2 dex above the file's last point).  Outputs: network (names: 6 bytes each, NUL-padded; Z, A), lgP(nz),
+ * Y(nnet, nz) column-major.  Call with all output buffers NULL to query nnet and nz.  Host only (no device needed).
+ * NScool selects such a table with crust_composition = '<name>' -> <data_dir>/crust_data/<name>[.data]. */
+int dstar_abuntime_table(const char* path, double lgP_increment, double abundance_threshold, int32_t* nnet, int32_t* nz,
+                         char* names, double* Z, double* A, double* lgP, double* Y, int cap_net, int cap_z);
+
 /* ---- NScool_lib (NScool/public/NScool_lib.f:6-91) ---- */
 /* NScool_init(my_dStar_dir, ierr): data_dir holds helm_table.bin and Tc_data/ */
 int dstar_NScool_init(const char* data_dir, int device);

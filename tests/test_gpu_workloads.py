@@ -190,3 +190,28 @@ def test_full_size_sweep_properties(nscool):
     np.testing.assert_array_equal(stars[200].counters(), solo.counters())
     for s in stars:
         s.free()
+
+
+def test_abuntime_composition_many_species(nscool, oracle):
+    """configs[4] flavour (INT-16-2b-demo): crust composition from an abuntime-format table -- ~60 nuclides above the
+    abundance threshold per zone (the ion-mixture loop, ion.f:72-83, dominates) blended into HZ90 at depth."""
+    from dstar_b200 import workloads
+    stars = workloads.int16_demo(2, resolution=0.5)
+    nscool.create_models(stars)
+    s = stars[0]
+    nch = s.get_int("ncharged")
+    assert nch >= 60
+    Yion = s.array("Yion").reshape(-1, nch)
+    assert (Yion[0] > 1e-9).sum() >= 40 and (Yion[-1] > 1e-9).sum() <= 2      # many species outside, HZ90 at the bottom
+    y0 = [x.array("lnT").copy() for x in stars]
+    nscool.evolve_models(stars)
+    check_tables(s, oracle_micro_tables(oracle, s, gaps=("ns", "sfb03", "t72")))
+    rng = np.random.default_rng(workloads.SEED + 4)
+    rng.uniform(0, 1, 2)
+    Qh = rng.uniform(0.0, 3.0, 2)
+    ev = oracle_evolve_star(oracle, s, y0[0], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, float(Qh[0])],
+                            ctrl=dict(turn_on_extra_heating=1, fix_atmosphere_temperature_when_accreting=0))
+    t, Teff, Qb = s.monitors()
+    assert len(Teff) == 10 and rel(Teff, ev["Teff_monitor"]) < 1e-6
+    for x in stars:
+        x.free()
