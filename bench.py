@@ -220,7 +220,7 @@ def workload_ctrl(ds, args):
         heat[6:9] = [27.0, 28.0, 1.7]; T_atm = 2.4e8
     elif args.workload == "basic_run":
         ec.turn_on_extra_heating = 1; heat[6:9] = [27.5, 28.5, 0.1]; T_atm = 2.4e8
-    elif args.workload == "fit_lightcurve":
+    elif args.workload in ("fit_lightcurve", "int16_demo"):
         ec.fix_atmosphere_temperature_when_accreting = 0; ec.turn_on_extra_heating = 1
     elif args.workload == "accretion":
         mc.use_neutron_conductivity = 1; mc.use_superfluid_phonon_conductivity = 1; mc.turn_on_shell_Urca = 1

@@ -215,3 +215,24 @@ def test_abuntime_composition_many_species(nscool, oracle):
     assert len(Teff) == 10 and rel(Teff, ev["Teff_monitor"]) < 1e-6
     for x in stars:
         x.free()
+
+
+def test_second_outburst_recovers_from_oversized_first_step(nscool, oracle):
+    """examples/accretion at full resolution: the second accretion cycle starts with the step size left over from
+    3e4 days of cooling; the first trial steps overflow (NaN error norm) and must simply be halved until one fits,
+    on the device as in the oracle."""
+    from dstar_b200 import workloads
+    stars = workloads.accretion(2, resolution=0.05)
+    for s in stars:   # the electron-only conductivity keeps the oracle's share of this test short
+        s.set_control("use_neutron_conductivity", False); s.set_control("use_superfluid_phonon_conductivity", False)
+    nscool.create_models(stars)
+    y0 = [s.array("lnT").copy() for s in stars]
+    nscool.evolve_models(stars)
+    for k, s in enumerate(stars):
+        t, Teff, Qb = s.monitors()
+        assert len(Teff) == 10 and np.all(Teff > 0)
+        ev = oracle_evolve_star(oracle, s, y0[k], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, 1.0], T_atm=5.0e8,
+                                ctrl=dict(turn_on_extra_heating=1))
+        assert rel(Teff, ev["Teff_monitor"]) < 1e-6
+        np.testing.assert_array_equal(s.counters(), ev["counters"])
+        s.free()
