@@ -73,6 +73,8 @@ struct dstar_batch {
          have_enuc = false;
     DevBuf<int> zone_offset, zone_star, status, redo, redo_count, atm_index, idid, counters, model, trace_count, trace_model;
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
+    DevBuf<DsIonZ> ionz;
+    std::vector<DsIonZ> h_ionz;
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
@@ -83,6 +85,15 @@ struct dstar_batch {
 };
 
 namespace {
+void fill_host_consts(DsHostConsts& h);
+// per-species functions of Z for the ion-electron fits (eos.cuh: DsIonZ), evaluated here with the same dsmath
+cudaError_t upload_ionz(DevBuf<DsIonZ>& d, std::vector<DsIonZ>& h, int ncharged, const double* Zion, cudaStream_t s) {
+    DsHostConsts hc;
+    fill_host_consts(hc);
+    h.resize(ncharged);
+    for (int i = 0; i < ncharged; ++i) h[i] = ds_ionz_compute(Zion[i], hc.ctf_fac);
+    return d.upload(h.data(), ncharged, s);
+}
 void fill_host_consts(DsHostConsts& h) {
     using namespace dsc;
     h.theta_fac = 2.0 * dsm::pow((double)(4.0f / 9.0f) / pi, (double)(2.0f / 3.0f));
@@ -253,6 +264,9 @@ static int eval_crust_eos_impl(dstar_ctx* c, int n, const double* rho, const dou
     DevBuf<int> d_ph, d_ie;
     CK(d_rho.upload(rho, n, s)); CK(d_T.upload(T, n, s)); CK(d_ion.upload(ionic, (size_t)11 * n, s));
     CK(d_Z.upload(Zion, ncharged, s)); CK(d_A.upload(Aion, ncharged, s));
+    DevBuf<DsIonZ> d_ionz;
+    std::vector<DsIonZ> h_ionz;
+    CK(upload_ionz(d_ionz, h_ionz, ncharged, Zion, s));
     CK(d_Y.upload(Yion, (size_t)ncharged * n, s)); CK(d_Tc.upload(Tcs, (size_t)3 * n, s));
     if (chi_in) CK(d_chi.upload(chi_in, n, s));
     CK(d_res.alloc((size_t)15 * n)); CK(d_chio.alloc(n)); CK(d_ph.alloc(n)); CK(d_ie.alloc(n));
@@ -260,6 +274,7 @@ static int eval_crust_eos_impl(dstar_ctx* c, int n, const double* rho, const dou
     if (components) CK(d_comp.alloc((size_t)28 * n));
     DsEvalEosArgs a{};
     a.n = n; a.ncharged = ncharged; a.rho = d_rho.p; a.T = d_T.p; a.ionic = d_ion.p; a.Zion = d_Z.p; a.Aion = d_A.p;
+    a.ionz = d_ionz.p;
     a.Yion = d_Y.p; a.Tcs = d_Tc.p; a.chi_in = chi_in ? d_chi.p : nullptr;
     a.eos = DsEosCtrl{175.0, 140.0, DS_R4(1.0e-9)};
     if (eos_ctrl) a.eos = DsEosCtrl{eos_ctrl[0], eos_ctrl[1], eos_ctrl[2]};
@@ -423,6 +438,7 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
     CK(b->ionic_bar.upload(ionic_bar, 11 * n, s)); CK(b->Yion.upload(Yion, b->ncharged * n, s));
     CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, s)); CK(b->Zion.upload(Zion, b->ncharged, s));
     CK(b->Aion.upload(Aion, b->ncharged, s));
+    CK(upload_ionz(b->ionz, b->h_ionz, b->ncharged, Zion, s));
     b->have_Tc_cell = Tc_cell != nullptr; b->have_Tc_face = Tc_face != nullptr;
     if (Tc_cell) CK(b->Tc_cell.upload(Tc_cell, 3 * n, s));
     if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, s));
@@ -473,7 +489,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     a.total_zones = b->total; a.ncharged = b->ncharged; a.zone_star = b->zone_star.p; a.zone_offset = b->zone_offset.p;
     a.rho = b->rho.p; a.rho_bar = b->rho_bar.p; a.P = b->P.p; a.P_bar = b->P_bar.p; a.dm = b->dm.p;
     a.ionic = b->ionic.p; a.ionic_bar = b->ionic_bar.p; a.Yion = b->Yion.p; a.Yion_bar = b->Yion_bar.p;
-    a.Zion = b->Zion.p; a.Aion = b->Aion.p;
+    a.Zion = b->Zion.p; a.Aion = b->Aion.p; a.ionz = b->ionz.p;
     a.Tc_cell = b->have_Tc_cell ? b->Tc_cell.p : nullptr;
     a.Tc_face = b->have_Tc_face ? b->Tc_face.p : nullptr;
     a.tab_lnT = c->tab_lnT.p; a.tab_T = c->tab_T.p; a.tab_lgT = c->tab_lgT.p;

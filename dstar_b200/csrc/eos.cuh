@@ -65,6 +65,41 @@ DS_D double neutron_wavenumber(double rho, const DsComp& c, double chi) {
     return dsm::pow(threepisquare * n, onethird) / cm_to_fm;
 }
 
+// Functions of the nuclear charge alone that the ion-electron fits need (11 full pow/log evaluations per species
+// and call).  They do not depend on the zone or on T, so the host evaluates them ONCE per species of the network
+// with the same dsmath and the same expression order -- bit-identical by construction (tests/test_dsmath.py) --
+// and the kernels read them by broadcast (all lanes of a group work on the same species at the same time).
+struct DsIonZ {
+    double Z53, Z76;                                     // one_ion   (ion.f:152-153)
+    double Z13, cDH, cTF, lZ, aL, bL, nuL, q1L, q2L;     // ie_liquid (ion.f:178-285)
+    double r3, b0, b1, b2, b3, Z23;                      // ie_lattice (ion.f:287-405)
+};
+DS_HD DsIonZ ds_ionz_compute(double Z, double ctf_fac) {
+    DsIonZ q;
+    const double sevensixth = (double)(7.0f / 6.0f);
+    q.Z53 = dsm::pow(Z, dsc::fivethird);
+    q.Z76 = dsm::pow(Z, sevensixth);
+    const double s3 = (double)sqrtf(3.0f);
+    q.Z13 = dsm::pow(Z, dsc::onethird);
+    q.cDH = (Z / s3) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
+    q.cTF = ctf_fac * (Z * Z) * (q.Z13 - 1.0 + DS_R4(0.2) / sqrt(q.Z13));
+    q.lZ = dsm::log(Z);
+    q.aL = DS_R4(1.11) * dsm::pow(Z, DS_R4(0.475));
+    q.bL = DS_R4(0.2) + DS_R4(0.078) * (q.lZ * q.lZ);
+    q.nuL = DS_R4(1.16) + DS_R4(0.08) * q.lZ;
+    q.q1L = DS_R4(0.18) / dsm::pow(Z, 0.25);
+    q.q2L = DS_R4(0.2) + DS_R4(0.37) / sqrt(Z);
+    const double a[4] = {DS_R4(1.1866), DS_R4(0.684), DS_R4(17.9), DS_R4(41.5)};
+    q.r3 = 1.0 / (1.0 + DS_R4(0.01) * dsm::pow(q.lZ, 1.5) + DS_R4(0.097) / (Z * Z));
+    q.b0 = 1.0 - a[0] / dsm::pow(Z, DS_R4(0.267)) + DS_R4(0.27) / Z;
+    q.b1 = 1.0 + 2.25 / dsm::pow(Z, dsc::onethird) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
+                     (1.0 + DS_R4(0.222) * dsd::ipow<6>(Z));
+    q.b2 = a[3] / (1.0 + q.lZ);
+    q.b3 = DS_R4(0.395) * q.lZ + DS_R4(0.347) / dsm::pow(Z, 1.5);
+    q.Z23 = dsm::pow(Z, dsc::twothird);
+    return q;
+}
+
 template <bool FAST>
 DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
@@ -263,21 +298,13 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
 }
 
 template <bool FAST>
-DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad) {
+DS_D void ie_liquid(double Gamma_e, double rs, double Z, const DsIonZ& zc, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
-    const double s3 = (double)sqrtf(3.0f);
-    const double CTFfac = ds_hc.ctf_fac;
-    double Z13 = dsm::pow(Z, onethird);
-    double cDH = (Z / den(s3)) * (dsm::pow(1.0 + Z, 1.5) - 1.0 - dsm::pow(Z, 1.5));
-    double cTF = CTFfac * (Z * Z) * (Z13 - 1.0 + DS_R4(0.2) / den(sq(Z13)));
+    const double cDH = zc.cDH, cTF = zc.cTF;   // Z-only pieces: DsIonZ
     double xrs = ds_hc.xrs;
     const DsDen<FAST> rsD = den(rs), Gamma_eD = den(Gamma_e);
     const DsDen<FAST> xr = den(xrs / rsD);
-    double lZ = dsm::log(Z);
-
-    double a = DS_R4(1.11) * dsm::pow(Z, DS_R4(0.475));
-    double b = DS_R4(0.2) + DS_R4(0.078) * (lZ * lZ);
-    double nu = DS_R4(1.16) + DS_R4(0.08) * lZ;
+    const double a = zc.aL, b = zc.bL, nu = zc.nuL;
     double sGam = sq(Gamma_e);
     double nuGam = dsm::pow(Gamma_e, nu);
     double nuGam_g = nu * nuGam / Gamma_eD;
@@ -318,8 +345,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
     double cor0_xg = (u0_xg - (u0_x * d0_g + u0_g * d0_x) / d0 + 2.0 * u0 * d0_x * d0_g / den(d0 * d0)) / d0;
 
     const DsDen<FAST> rgam = den(sq(1.0 + xr * xr));
-    double q1 = DS_R4(0.18) / den(dsm::pow(Z, 0.25));
-    double q2 = DS_R4(0.2) + DS_R4(0.37) / den(sq(Z));
+    const double q1 = zc.q1L, q2 = zc.q2L;
     const DsDen<FAST> h1u = den(1.0 + DS_R4(0.2) * (xr * xr));
     const DsDen<FAST> h1d = den(1.0 + q1 * xr + q2 * (xr * xr));
     double h1 = h1u / h1d;
@@ -366,7 +392,7 @@ DS_D void ie_liquid(double Gamma_e, double rs, double Z, DsThermo& r, bool& bad)
 }
 
 template <bool FAST>
-DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& r, bool& bad) {
+DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, const DsIonZ& zc, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double a[4] = {DS_R4(1.1866), DS_R4(0.684), DS_R4(17.9), DS_R4(41.5)};
     const double px = DS_R4(0.205);
@@ -374,16 +400,9 @@ DS_D void ie_lattice(double Gamma, double theta, double rs, double Z, DsThermo& 
     double aTF = ds_hc.atf;
     double xrs = ds_hc.xrs;
     const DsDen<FAST> xr = den(xrs / den(rs));
-    double lZ = dsm::log(Z);
-    double r3 = 1.0 / den(1.0 + DS_R4(0.01) * dsm::pow(lZ, 1.5) + DS_R4(0.097) / (Z * Z));
-    double b[4];
-    b[0] = 1.0 - a[0] / den(dsm::pow(Z, DS_R4(0.267))) + DS_R4(0.27) / den(Z);
-    b[1] = 1.0 + 2.25 / den(dsm::pow(Z, onethird)) * (1.0 + a[1] * dsd::ipow<5>(Z) + DS_R4(0.222) * dsd::ipow<6>(Z)) /
-                     (1.0 + DS_R4(0.222) * dsd::ipow<6>(Z));
-    b[2] = a[3] / den(1.0 + lZ);
-    b[3] = DS_R4(0.395) * lZ + DS_R4(0.347) / den(dsm::pow(Z, 1.5));
-
-    double finf = aTF * dsm::pow(Z, twothird) * b[0] * sq(1.0 + b[1] / den(xr * xr));
+    const double r3 = zc.r3;
+    const double b[4] = {zc.b0, zc.b1, zc.b2, zc.b3};   // Z-only pieces: DsIonZ
+    double finf = aTF * zc.Z23 * b[0] * sq(1.0 + b[1] / den(xr * xr));
     double finfx = -b[1] / den((b[1] + xr * xr) * xr);
     double finf_x = finf * finfx;
     double finf_xx = finf_x * finfx - finf_x * (b[1] + 3.0 * (xr * xr)) / den((b[1] + xr * xr) * xr);
@@ -621,17 +640,16 @@ DS_D void ii_lattice(double Gamma, double theta, DsThermo& tot, bool& bad) {
 }
 
 template <bool FAST>
-DS_D void one_ion(double Gamma_e, double rs, double Z, double A, int phase, DsThermo& r, bool& bad) {
+DS_D void one_ion(double Gamma_e, double rs, double Z, double A, const DsIonZ& zc, int phase, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
-    const double sevensixth = (double)(7.0f / 6.0f);
-    double Gamma = Gamma_e * dsm::pow(Z, fivethird);
-    double theta = Gamma * sq(3.0 * Melectron / den(A) / den_c(amu) / den(rs)) / den(dsm::pow(Z, sevensixth));
+    double Gamma = Gamma_e * zc.Z53;
+    double theta = Gamma * sq(3.0 * Melectron / den(A) / den_c(amu) / den(rs)) / den(zc.Z76);
     DsThermo ie, ii;
     if (phase == ds_liquid_phase) {
-        ie_liquid<FAST>(Gamma_e, rs, Z, ie, bad);
+        ie_liquid<FAST>(Gamma_e, rs, Z, zc, ie, bad);
         ii_liquid<FAST>(Gamma, theta, ii, bad);
     } else {
-        ie_lattice<FAST>(Gamma, theta, rs, Z, ie, bad);
+        ie_lattice<FAST>(Gamma, theta, rs, Z, zc, ie, bad);
         ii_lattice<FAST>(Gamma, theta, ii, bad);
     }
     r.f = ie.f + ii.f; r.u = ie.u + ii.u; r.p = ie.p + ii.p; r.s = ie.s + ii.s;
@@ -673,8 +691,8 @@ DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r
 
 template <bool FAST>
 DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsComp& c,
-                int ncharged, const double* Zion, const double* Aion, const double* Yion,
-                double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad) {
+                int ncharged, const double* Zion, const double* Aion, const DsIonZ* __restrict__ ionz,
+                const double* Yion, double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double Q2_threshold = 18.0;
     int err = 0;
@@ -689,7 +707,7 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
     for (int i = 0; i < ncharged; ++i) {
         if (Yion[i] > rq.Ythresh) {
             DsThermo t;
-            one_ion<FAST>(Gamma_e, rs, Zion[i], Aion[i], phase, t, bad);
+            one_ion<FAST>(Gamma_e, rs, Zion[i], Aion[i], ionz[i], phase, t, bad);
             f = f + Yion[i] * t.f;
             u = u + Yion[i] * t.u;
             s = s + Yion[i] * (t.s - dsm::log(Yion[i]));
@@ -802,6 +820,8 @@ DS_D void get_radiation_eos(double rho, double T, DsThermo& r, bool& bad) {
 }
 
 }  // namespace dse
+using dse::DsIonZ;
+using dse::ds_ionz_compute;
 
 // Result of one EOS evaluation; fields follow dStar_eos_def.f:6-36 (res(1:15)).
 struct DsEosRes {
@@ -819,7 +839,8 @@ template <bool FAST>
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
                             double logT, const DsComp& c, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
-                            const double* __restrict__ Yion, double Tns, double chi, DsEosRes& o, bool& bad,
+                            const DsIonZ* __restrict__ ionz, const double* __restrict__ Yion, double Tns, double chi,
+                            DsEosRes& o, bool& bad,
                             double* __restrict__ comps = nullptr) {
     DS_DEN_SCOPE(FAST);
     using namespace dsc;
@@ -851,7 +872,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     // ions (ion.f:20-92)
     DsThermo ion;
     int phase;
-    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, Yion, Gamma, ionQ, phase, ion, bad);
+    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad);
     DS_PHASE();
     const double n_i = ne / den(c.Z);
     const double nik = n_i * boltzmann;

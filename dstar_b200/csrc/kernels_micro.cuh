@@ -64,6 +64,7 @@ struct DsMicroArgs {
     const double *ionic, *ionic_bar;               // (11, total_zones)
     const double *Yion, *Yion_bar;                 // (ncharged, total_zones)
     const double *Zion, *Aion;                     // (ncharged)
+    const DsIonZ* ionz;                            // (ncharged) host-evaluated functions of Z (eos.cuh)
     const double *Tc_cell, *Tc_face;               // (3, total_zones) or null -> gap tables
     const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, dsm::exp(lnT), dsm::log10(T)
     DsEosCtrl eos;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             DsEosRes r;
             const double* Yz = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, Yz, Tc[1], chi, r, bad);
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, a.ionz, Yz, Tc[1], chi, r, bad);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
 struct DsEvalEosArgs {
     int n, ncharged;
     const double *rho, *T, *ionic, *Zion, *Aion, *Yion, *Tcs, *chi_in;
+    const DsIonZ* ionz;
     DsEosCtrl eos;
     double* res;  // (15, n)
     double* comps;  // (7, 4, n) or null
@@ -251,11 +253,11 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     DsEosRes r;
     bool bad = false;
     double* cp = (a.comps && live) ? a.comps + (size_t)28 * k : nullptr;
-    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
+    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion, a.ionz,
                             a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, bad, cp);
     if (__syncthreads_or(bad)) {
         bool unused = false;
-        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion,
+        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion, a.ionz,
                                  a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, unused, cp);
     }
     if (!live) return;
