@@ -138,7 +138,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double a_hh = a_h * ah + a * (a0_hh / a0 - dsd::ipow<2>(a0_h / a0) - a1_hh / a1 + dsd::ipow<2>(a1_h / a1) +
                                   t1_hh / t1D - dsd::ipow<2>(t1_h / t1D));
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     const DsDen<FAST> b0 = den(DS_R4(0.341308) + DS_R4(12.070873) * theta2 + DS_R4(1.148889) * theta4);
     double b0_h = DS_R4(24.141746) * theta + DS_R4(4.595556) * theta3;
     double b0_hh = DS_R4(24.141746) + DS_R4(13.786668) * theta2;
@@ -163,7 +163,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double d_hh = d_h * dh + d * (-0.5 / theta2D + t2_hh / t2D - dsd::ipow<2>(t2_h / t2D) + d0_hh / d0 -
                                   dsd::ipow<2>(d0_h / d0) - d1_hh / d1 + dsd::ipow<2>(d1_h / d1));
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     const DsDen<FAST> e0 = den(DS_R4(0.539409) + DS_R4(2.522206) * theta2 + DS_R4(0.178484) * theta4);
     double e0_h = DS_R4(5.044412) * theta + DS_R4(0.713936) * theta3;
     double e0_hh = DS_R4(5.044412) + DS_R4(2.141808) * theta2;
@@ -188,14 +188,14 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double di_h = 0.5 / discr * (4.0 * e_h - 2.0 * d * d_h);
     double di_hh = (-dsd::ipow<2>((2.0 * e_h - d * d_h) / discr) + 2.0 * e_hh - d_h * d_h - d * d_hh) / discr;
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     double s1 = -c / e * Gamma_e;
     double s1h = c_h / c - e_h / e;
     double s1_h = s1 * s1h;
     double s1_hh = s1_h * s1h + s1 * (c_hh / c - dsd::ipow<2>(c_h / c) - e_hh / e + dsd::ipow<2>(e_h / e));
     double s1_g = -c / e;
     double s1_hg = s1_g * (c_h / c - e_h / e);
-    DS_PHASE();
+    DS_PHASE_INNER();
     const DsDen<FAST> b2 = den(b - c * d / e);
     double b2_h = b_h - (c_h * d + c * d_h) / e + c * d * e_h / e2D;
     double b2_hh = b_hh - (c_hh * d + 2.0 * c_h * d_h + c * d_hh) / e +
@@ -217,7 +217,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double r3_gg = -0.25 * d / den(Gamma_e * sqge);
     double r3_hg = e_h + 0.5 * d_h / sqge;
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     double b3 = a - c / e;
     double b3_h = a_h - c_h / e + c * e_h / e2D;
     double b3_hh = a_hh - c_hh / e + (2.0 * c_h * e_h + c * e_hh) / e2D - 2.0 * c * (e_h * e_h) / den(dsd::ipow<3>(e));
@@ -236,7 +236,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double s3_gg = c3 * (r3_gg / r3 - dsd::ipow<2>(r3_g / r3));
     double s3_hg = (c3_h * r3_g + c3 * r3_hg) / r3 - c3 * r3_g * r3_h / den(r3 * r3);
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     double b4 = 2.0 - d * d / e;
     double b4_h = e_h * dsd::ipow<2>(d / e) - 2.0 * d * d_h / e;
     double b4_hh = e_hh * dsd::ipow<2>(d / e) + 2.0 * e_h * dsd::ipow<2>(d / e) * (d_h / den(d) - e_h / e) -
@@ -249,7 +249,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double c4_gg = -0.5 * e / den(Gamma_e * sqge);
     double c4_hg = e_h / sqge;
 
-    DS_PHASE();
+    DS_PHASE_INNER();
     double s4a = 2.0 / e / discr;
     double s4ah = e_h / e + di_h / discr;
     double s4a_h = -s4a * s4ah;
@@ -268,7 +268,7 @@ DS_D void ee_exchange(double Gamma_e, double rs, DsThermo& r, bool& bad) {
     double s4c_g = c4_g * discr / dn1;
     double s4c_gg = c4_gg * discr / dn1 - 2.0 * c4 * discr * dsd::ipow<2>(c4_g / dn1);
     double s4c_hg = (c4_hg * discr + c4_g * di_h - c4_g * discr / dn1 * 2. * (discr * di_h + c4 * c4_h)) / dn1;
-    DS_PHASE();
+    DS_PHASE_INNER();
     double s4 = s4a * s4b * s4c;
     double s4_h = s4a_h * s4b * s4c + s4a * s4b_h * s4c + s4a * s4b * s4c_h;
     double s4_hh = s4a_hh * s4b * s4c + s4a * s4b_hh * s4c + s4a * s4b * s4c_hh +
