@@ -351,6 +351,30 @@ class NScool:
     def write_history(self, path):
         _nerr(self.L.dstar_NScool_write_history(self.id, path.encode()), "write_history")
 
+    PROFILE_COLUMNS = ("zone", "mass", "dm", "area", "gravity", "eLambda", "ePhi", "temperature", "luminosity", "pressure",
+                       "density", "zbar", "abar", "Xn", "Qimp", "Gamma", "cp", "eps_nu", "eps_nuc", "K")
+
+    def profile_count(self):
+        """(profiles kept, profiles the run produced): mod(model, write_interval_for_profile) == 0."""
+        kept, made = C.c_int32(), C.c_int32()
+        _nerr(self.L.dstar_NScool_profile_count(self.id, C.byref(kept), C.byref(made)), "profile_count")
+        return kept.value, made.value
+
+    def profile(self, index):
+        """One captured profile: dict with the header scalars and the 20 zone columns of NScool_profile.f."""
+        nz = self.get_int("nz")
+        model = C.c_int32(); hdr = np.zeros(8); cols = np.zeros((nz, 20))
+        _nerr(self.L.dstar_NScool_get_profile(self.id, index, C.byref(model), p(hdr), p(cols)), "get_profile")
+        out = {"model": model.value}
+        out.update(dict(zip(("time", "core_mass", "core_radius", "accretion_rate", "heating_lum", "cooling_lum",
+                             "total_mass", "total_radius"), hdr)))
+        out.update({k: cols[:, j].copy() for j, k in enumerate(self.PROFILE_COLUMNS)})
+        return out
+
+    def write_profiles(self, directory):
+        os.makedirs(directory, exist_ok=True)
+        _nerr(self.L.dstar_NScool_write_profiles(self.id, os.fsencode(directory)), "write_profiles")
+
 
 def create_models(stars):
     ids = i32([s.id for s in stars])

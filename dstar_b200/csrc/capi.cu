@@ -67,6 +67,9 @@ struct dstar_ctx {
 struct dstar_batch {
     dstar_ctx* ctx = nullptr;
     int n_star = 0, total = 0, ncharged = 0, n_epoch = 0, n_atm = 0, atm_nv = 0, trace_cap = 0;
+    int prof_interval = 0, prof_cap = 0;
+    DevBuf<int> prof_count, prof_model;
+    DevBuf<double> prof_tsec, prof_Mdot, prof_lnT;
     std::vector<int> h_zone_offset;
     int max_nz = 0;
     bool have_structure = false, have_tables = false, have_evolve = false, have_Tc_cell = false, have_Tc_face = false,
@@ -661,6 +664,9 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     a.trace_cap = trace_cap; a.trace_count = trace_cap ? b->trace_count.p : nullptr; a.trace_model = b->trace_model.p;
     a.trace_tsec = b->tr_tsec.p; a.trace_dt = b->tr_dt.p; a.trace_Teff = b->tr_Teff.p; a.trace_Lsurf = b->tr_Lsurf.p;
     a.trace_Lnu = b->tr_Lnu.p; a.trace_Lnuc = b->tr_Lnuc.p; a.trace_Mdot = b->tr_Mdot.p;
+    a.prof_interval = b->prof_interval; a.prof_cap = b->prof_cap; a.total_zones = b->total;
+    a.prof_count = b->prof_cap ? b->prof_count.p : nullptr; a.prof_model = b->prof_model.p; a.prof_tsec = b->prof_tsec.p;
+    a.prof_Mdot = b->prof_Mdot.p; a.prof_lnT = b->prof_lnT.p;
     // the star's rho_bar(1) is the fixed-up one (create_model.f:367-369): patch it into rho_bar
     // (the evolve kernel never reads face 0's rho_bar, L(1) comes from the atmosphere; kept for symmetry)
     CK(cudaEventRecord(b->ev0, s));
@@ -672,6 +678,33 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     CK(cudaEventSynchronize(b->ev1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[2] = ms;
     b->launches = 1;
+    return DSTAR_OK;
+}
+
+int dstar_batch_set_profile_capture(dstar_batch* b, int interval, int capacity) {
+    if (!b || interval < 0 || capacity < 0) return fail(DSTAR_ERR_ARG, "batch_set_profile_capture");
+    CK(cudaSetDevice(b->ctx->device));
+    if (interval == 0 || capacity == 0) { b->prof_interval = 0; b->prof_cap = 0; return DSTAR_OK; }
+    const size_t ns = b->n_star;
+    CK(b->prof_count.alloc(ns)); CK(b->prof_model.alloc((size_t)capacity * ns)); CK(b->prof_tsec.alloc((size_t)capacity * ns));
+    CK(b->prof_Mdot.alloc((size_t)capacity * ns)); CK(b->prof_lnT.alloc((size_t)capacity * b->total));
+    CK(cudaMemsetAsync(b->prof_count.p, 0, ns * sizeof(int), b->ctx->stream));
+    b->prof_interval = interval; b->prof_cap = capacity;
+    return DSTAR_OK;
+}
+
+int dstar_batch_download_profiles(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* Mdot, double* lnT) {
+    if (!b || b->prof_cap <= 0) return fail(DSTAR_ERR_STATE, "no profiles kept");
+    if (!b->have_evolve) return fail(DSTAR_ERR_STATE, "nothing evolved");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t pn = (size_t)b->prof_cap * b->n_star;
+    if (count) CK(b->prof_count.download(count, b->n_star, s));
+    if (model) CK(b->prof_model.download(model, pn, s));
+    if (tsec) CK(b->prof_tsec.download(tsec, pn, s));
+    if (Mdot) CK(b->prof_Mdot.download(Mdot, pn, s));
+    if (lnT) CK(b->prof_lnT.download(lnT, (size_t)b->prof_cap * b->total, s));
+    CK(cudaStreamSynchronize(s));
     return DSTAR_OK;
 }
 

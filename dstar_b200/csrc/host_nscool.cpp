@@ -85,6 +85,8 @@ struct Controls {  // NScool/public/NScool_controls.inc, defaults NScool/default
     bool fix_Qimp = false;
     double Qimp = 0.0;
     int trace_capacity = -1;  // dstar_b200 extension: history rows kept on the device (-1: automatic)
+    int profile_capacity = -1;  // dstar_b200 extension: profiles kept on the device per star (-1: automatic, 0: none)
+    std::string base_profile_filename = "profile", profile_manifest_filename = "profiles";
     Controls() { basic_epoch_boundaries[1] = 365.0; }
 };
 
@@ -165,7 +167,7 @@ int set_control(Controls& c, const std::string& name_in, const std::string& valu
         return 0; }
     INT(write_interval_for_terminal) INT(write_interval_for_terminal_header) INT(write_interval_for_history)
     INT(write_interval_for_profile) INT(starting_number_for_profile) LOG(suppress_first_step_output)
-    STR(output_directory) STR(which_solver) INT(maximum_number_of_models) REAL(maximum_timestep)
+    STR(output_directory) STR(base_profile_filename) STR(profile_manifest_filename) STR(which_solver) INT(maximum_number_of_models) REAL(maximum_timestep)
     REAL(integration_tolerance) REAL(min_lg_temperature_integration) REAL(max_lg_temperature_integration)
     LOG(fix_core_temperature) REAL(core_temperature) LOG(make_inner_boundary_insulating)
     LOG(fix_atmosphere_temperature_when_accreting) REAL(atmosphere_temperature_when_accreting)
@@ -214,7 +216,7 @@ int set_control(Controls& c, const std::string& name_in, const std::string& valu
     REAL(lg_atm_light_element_column) STR(atm_model) REAL(crust_reference_temperature) STR(crust_composition)
     if (name == "fix_qimp") return parse_logical(vals[0], c.fix_Qimp) ? 0 : -1;
     if (name == "qimp") return parse_real(vals[0], c.Qimp) ? 0 : -1;
-    INT(trace_capacity)
+    INT(trace_capacity) INT(profile_capacity)
     // stored-but-unused controls of the reference (load_model_file, model_file, use_core_nu_*)
     if (name == "load_model_file" || name == "model_file" || name.rfind("use_core_nu_", 0) == 0) return 0;
     return -2;
@@ -584,6 +586,10 @@ struct Star {
     // history rows
     std::vector<int> h_model;
     std::vector<double> h_tsec, h_Mdot, h_Teff, h_Lsurf, h_Lnu, h_Lnuc;
+    // captured profiles: model number, time, accretion rate and ln T (nz each)
+    std::vector<int> p_model;
+    std::vector<double> p_tsec, p_Mdot, p_lnT;
+    int p_total = 0;  // profiles the run produced (>= kept ones)
     std::string err;
 };
 constexpr int max_handles = 1 << 16;  // the reference allows 10 (NScool_def.f:159); batches need many more
@@ -1197,6 +1203,10 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     dstar_evolve_ctrl ec = evolve_ctrl_of(ss[0]->c);
     int cap = ss[0]->c.trace_capacity;
     if (cap < 0) cap = (n <= 64) ? 2048 : 0;
+    int pcap = ss[0]->c.profile_capacity;
+    if (pcap < 0) pcap = (n <= 64) ? 512 : 0;
+    const int pint = std::max(1, ss[0]->c.write_interval_for_profile);
+    if (rc == 0) rc = dstar_batch_set_profile_capture(b, pcap > 0 ? pint : 0, pcap);
     if (rc == 0) rc = dstar_batch_evolve(b, &ec, cap);
     if (rc == 0) g_ms[2] = dstar_batch_last_kernel_ms(b, 2);
     std::vector<double> tm((size_t)ne * n), Tm(tm.size()), Qm(tm.size()), lnT(total), Teff(n), Lsurf(n), dt(n), tsec(n);
@@ -1211,6 +1221,13 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
         tLnuc.resize(tn); tMdot.resize(tn);
         rc = dstar_batch_download_trace(b, tc.data(), tmodel.data(), ttsec.data(), tdt.data(), tTeff.data(), tLs.data(),
                                         tLnu.data(), tLnuc.data(), tMdot.data());
+    }
+    std::vector<int32_t> pc, pmodel;
+    std::vector<double> ptsec, pMdot, plnT;
+    if (rc == 0 && pcap > 0) {
+        pc.resize(n); pmodel.resize((size_t)pcap * n); ptsec.resize(pmodel.size()); pMdot.resize(pmodel.size());
+        plnT.resize((size_t)pcap * total);
+        rc = dstar_batch_download_profiles(b, pc.data(), pmodel.data(), ptsec.data(), pMdot.data(), plnT.data());
     }
     if (rc != 0) { g_err = dstar_last_error(); return rc; }
     int worst = 0;
@@ -1233,6 +1250,17 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
                 size_t q = (size_t)r * n + i;
                 s->h_model.push_back(tmodel[q]); s->h_tsec.push_back(ttsec[q]); s->h_Mdot.push_back(tMdot[q]);
                 s->h_Teff.push_back(tTeff[q]); s->h_Lsurf.push_back(tLs[q]); s->h_Lnu.push_back(tLnu[q]); s->h_Lnuc.push_back(tLnuc[q]);
+            }
+        }
+        s->p_model.clear(); s->p_tsec.clear(); s->p_Mdot.clear(); s->p_lnT.clear(); s->p_total = 0;
+        if (pcap > 0) {
+            s->p_total = pc[i];
+            const int rows = std::min(pc[i], pcap);
+            for (int r = 0; r < rows; ++r) {
+                const size_t q = (size_t)r * n + i;
+                s->p_model.push_back(pmodel[q]); s->p_tsec.push_back(ptsec[q]); s->p_Mdot.push_back(pMdot[q]);
+                const double* src = &plnT[(size_t)r * total + zoff[i]];
+                s->p_lnT.insert(s->p_lnT.end(), src, src + s->nz);
             }
         }
         s->evolved = true;
@@ -1365,6 +1393,123 @@ int dstar_NScool_write_history(int id, const char* path) {
                      safe_log10(s->h_Lnuc[r]));
     }
     std::fclose(fp);
+    return 0;
+}
+
+// ---- profiles (NScool_profile.f): the device keeps ln T per zone at the profile models; every other column is
+// rebuilt here from the star's structure and coefficient tables exactly as evaluate_timestep refreshes the state
+// (interpolate_temps :452-459, get_coefficients :461-524, evaluate_luminosity :433-450, get_nuclear_heating :526-568)
+namespace {
+void profile_columns(Star* s, int ip, std::vector<double>& col /* (20, nz) row-major by zone: col[20*iz + c] */, double& Lnu, double& Lnuc) {
+    const int nz = s->nz, nt = 128;
+    auto& Z = s->z;
+    const double* lnT = &s->p_lnT[(size_t)ip * nz];
+    const double Mdot = s->p_Mdot[ip];
+    const std::vector<double>& tab = Z["tab_lnT"];
+    std::vector<double> T(nz), K(nz), Cp(nz), Gam(nz), enu(nz), enuc(nz, 0.0), L(nz);
+    for (int i = 0; i < nz; ++i) T[i] = std::exp(lnT[i]);
+    for (int i = 0; i < nz; ++i) {
+        const double Tbar = (i == 0) ? T[0] : 0.5 * (T[i - 1] * Z["dm"][i] + T[i] * Z["dm"][i - 1]) / Z["dm_bar"][i];
+        const double lnTbar = std::log(Tbar);
+        K[i] = std::exp(interp_value(tab.data(), nt, &Z["tab_lnK"][(size_t)4 * nt * i], lnTbar));
+        Cp[i] = std::exp(interp_value(tab.data(), nt, &Z["tab_lnCp"][(size_t)4 * nt * i], lnT[i]));
+        Gam[i] = std::exp(interp_value(tab.data(), nt, &Z["tab_lnGamma"][(size_t)4 * nt * i], lnT[i]));
+        enu[i] = std::exp(interp_value(tab.data(), nt, &Z["tab_lnEnu"][(size_t)4 * nt * i], lnT[i]));
+        if (i == 0) {
+            double lgTb = lnTbar / k::ln10;
+            lgTb = std::min(std::max(lgTb, s->atm.lgTb.front()), s->atm.lgTb.back());
+            L[0] = Z["area"][0] * std::pow(10.0, interp_value(s->atm.lgTb.data(), s->atm.nv, s->atm.lgflux.data(), lgTb));
+        } else {
+            L[i] = -(Z["area"][i] * Z["area"][i]) * Z["rho_bar"][i] * K[i] * (Z["ePhi"][i - 1] * T[i - 1] - Z["ePhi"][i] * T[i]) /
+                   Z["ePhi_bar"][i] / Z["dm_bar"][i];
+        }
+    }
+    const Controls& c = s->c;
+    const double hw[9] = {c.lgP_min_heating_outer, c.lgP_max_heating_outer, c.Q_heating_outer, c.lgP_min_heating_inner,
+                          c.lgP_max_heating_inner, c.Q_heating_inner, c.lgP_min_heating_shallow, c.lgP_max_heating_shallow,
+                          c.Q_heating_shallow};
+    for (int w = 0; w < (c.turn_on_extra_heating ? 3 : 2); ++w) {
+        const double Ptop = std::pow(10.0, hw[3 * w]), Pbot = std::pow(10.0, hw[3 * w + 1]);
+        double M = 0;
+        for (int i = 0; i < nz; ++i) if (Z["P"][i] >= Ptop && Z["P"][i] <= Pbot) M += Z["dm"][i];
+        for (int i = 0; i < nz; ++i) if (Z["P"][i] >= Ptop && Z["P"][i] <= Pbot) enuc[i] = Mdot * hw[3 * w + 2] * k::mev_to_ergs * k::avogadro / M;
+    }
+    Lnu = 0; Lnuc = 0;
+    for (int i = 0; i < nz; ++i) { Lnu += enu[i] * Z["dm"][i]; Lnuc += enuc[i] * Z["dm"][i]; }
+    col.assign((size_t)20 * nz, 0.0);
+    for (int i = 0; i < nz; ++i) {
+        double* q = &col[(size_t)20 * i];
+        const double* io = &Z["ionic"][(size_t)11 * i];
+        const double grav = k::fourpi * k::Gnewton * k::Msun * s->Mcore * Z["eLambda"][i] / Z["area"][i];
+        q[0] = i + 1; q[1] = Z["m"][i]; q[2] = Z["dm"][i]; q[3] = Z["area"][i]; q[4] = grav; q[5] = Z["eLambda"][i];
+        q[6] = Z["ePhi"][i]; q[7] = T[i]; q[8] = L[i]; q[9] = Z["P_bar"][i]; q[10] = Z["rho"][i]; q[11] = io[1]; q[12] = io[0];
+        q[13] = Z["Xneut"][i]; q[14] = io[10]; q[15] = Gam[i]; q[16] = Cp[i]; q[17] = enu[i]; q[18] = enuc[i]; q[19] = K[i];
+    }
+}
+}  // namespace
+
+int dstar_NScool_profile_count(int id, int32_t* kept, int32_t* produced) {
+    Star* s = get(id);
+    if (!s || !s->evolved) return -1;
+    if (kept) *kept = (int)s->p_model.size();
+    if (produced) *produced = s->p_total;
+    return 0;
+}
+
+int dstar_NScool_get_profile(int id, int index, int32_t* model, double* header /* 8 */, double* columns /* 20*nz */) {
+    Star* s = get(id);
+    if (!s || !s->evolved || index < 0 || index >= (int)s->p_model.size()) return -1;
+    std::vector<double> col;
+    double Lnu, Lnuc;
+    profile_columns(s, index, col, Lnu, Lnuc);
+    if (model) *model = s->p_model[index];
+    if (header) {
+        header[0] = s->p_tsec[index] / k::julian_day; header[1] = s->Mcore; header[2] = s->Rcore; header[3] = s->p_Mdot[index];
+        header[4] = Lnuc; header[5] = Lnu; header[6] = s->Mtotal; header[7] = s->Rtotal;
+    }
+    if (columns) std::copy(col.begin(), col.end(), columns);
+    return 0;
+}
+
+// do_write_profile (NScool_profile.f:27-106): one file "<base><model>" per kept profile + the manifest
+int dstar_NScool_write_profiles(int id, const char* directory) {
+    Star* s = get(id);
+    if (!s || !s->evolved || !directory) return -1;
+    const std::string dir = directory, base = dir + "/" + s->c.base_profile_filename;
+    FILE* mf = std::fopen((dir + "/" + s->c.profile_manifest_filename).c_str(), "w");
+    if (!mf) { g_err = "write_profiles: cannot open manifest in " + dir; return -1; }
+    std::fprintf(mf, "%15s%15s    %s\n", "model", "time [d]", ("base profile filename = " + s->c.base_profile_filename).c_str());
+    static const char* hcols[9] = {"model", "time", "core_mass", "core_radius", "accretion_rate", "heating_lum", "cooling_lum",
+                                   "total_mass", "total_radius"};
+    static const char* pcols[20] = {"zone", "mass", "dm", "area", "gravity", "eLambda", "ePhi", "temperature", "luminosity",
+                                    "pressure", "density", "zbar", "abar", "Xn", "Qimp", "Gamma", "cp", "eps_nu", "eps_nuc", "K"};
+    for (size_t ip = 0; ip < s->p_model.size(); ++ip) {
+        std::vector<double> col;
+        double Lnu, Lnuc;
+        profile_columns(s, (int)ip, col, Lnu, Lnuc);
+        FILE* fp = std::fopen((base + std::to_string(s->p_model[ip])).c_str(), "w");
+        if (!fp) { std::fclose(mf); g_err = "write_profiles: cannot open profile file"; return -1; }
+        std::fprintf(fp, "dstar-b200/profile\n\n");
+        for (int i = 1; i <= 9; ++i) std::fprintf(fp, "%15d", i);
+        std::fprintf(fp, "\n");
+        for (int i = 0; i < 9; ++i) std::fprintf(fp, "%15s", hcols[i]);
+        std::fprintf(fp, "\n%15d%15.6E%15.6f%15.6f%15.6E%15.6E%15.6E%15.6f%15.6f\n\n\n", s->p_model[ip], s->p_tsec[ip] / k::julian_day,
+                     s->Mcore, s->Rcore, s->p_Mdot[ip], Lnuc, Lnu, s->Mtotal, s->Rtotal);
+        for (int i = 1; i <= 20; ++i) std::fprintf(fp, "%15d", i);
+        std::fprintf(fp, "\n");
+        for (int i = 0; i < 20; ++i) std::fprintf(fp, "%15s", pcols[i]);
+        std::fprintf(fp, "\n");
+        for (int iz = 0; iz < s->nz; ++iz) {
+            const double* q = &col[(size_t)20 * iz];
+            // (i15, 4es15.6, 2f15.6, 4es15.6, 5f15.6, 4es15.6)
+            std::fprintf(fp, "%15d%15.6E%15.6E%15.6E%15.6E%15.6f%15.6f%15.6E%15.6E%15.6E%15.6E%15.6f%15.6f%15.6f%15.6f%15.6f%15.6E%15.6E%15.6E%15.6E\n",
+                         iz + 1, q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15],
+                         q[16], q[17], q[18], q[19]);
+        }
+        std::fclose(fp);
+        std::fprintf(mf, "%15d%15.6E\n", s->p_model[ip], s->p_tsec[ip] / k::julian_day);
+    }
+    std::fclose(mf);
     return 0;
 }
 

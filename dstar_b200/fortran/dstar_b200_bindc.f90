@@ -126,5 +126,22 @@ module dstar_b200
          type(c_ptr), value :: batch, t_monitor, Teff_monitor, Qb_monitor, idid, counters, lnT, Teff, Lsurf, dt, &
             & tsec, model
       end function
+      ! history rows and profiles kept on the device (feed do_write_history / do_write_profile)
+      integer(c_int) function dstar_batch_download_trace(batch, count, model, tsec, dt, Teff, Lsurf, Lnu, Lnuc, Mdot) &
+         & bind(C, name='dstar_batch_download_trace')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: batch, count, model, tsec, dt, Teff, Lsurf, Lnu, Lnuc, Mdot
+      end function
+      integer(c_int) function dstar_batch_set_profile_capture(batch, interval, capacity) &
+         & bind(C, name='dstar_batch_set_profile_capture')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: batch
+         integer(c_int), value :: interval, capacity
+      end function
+      integer(c_int) function dstar_batch_download_profiles(batch, count, model, tsec, Mdot, lnT) &
+         & bind(C, name='dstar_batch_download_profiles')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: batch, count, model, tsec, Mdot, lnT
+      end function
    end interface
 end module dstar_b200

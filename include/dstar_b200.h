@@ -159,6 +159,15 @@ int dstar_batch_download_results(dstar_batch* b, double* t_monitor, double* Teff
 /* D2H of the trace: count(n_star); the rest (trace_cap,n_star): model, tsec, dt, Teff, Lsurf, Lnu, Lnuc, Mdot */
 int dstar_batch_download_trace(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* dt,
                                double* Teff, double* Lsurf, double* Lnu, double* Lnuc, double* Mdot);
+
+/* Profile capture (evaluate_timestep, NScool/private/NScool_evolve.f:227-233 -> do_write_profile,
+ * NScool/private/NScool_profile.f:27-106): before dstar_batch_evolve, ask the kernel to keep ln T of every zone at
+ * the models with mod(model, interval) == 0, at most `capacity` per star (interval or capacity 0: off).
+ * download: count(n_star) = profiles the run produced (may exceed capacity; only the first `capacity` are kept),
+ * model/tsec/Mdot (capacity, n_star), lnT (capacity, total_zones).  Every other profile column (L, Gamma, Cp,
+ * eps_nu, K) follows from ln T through the coefficient tables on the host. */
+int dstar_batch_set_profile_capture(dstar_batch* b, int interval, int capacity);
+int dstar_batch_download_profiles(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* Mdot, double* lnT);
 /* device time [ms] of the last launch of kernel `which` (0 = cell loop, 1 = face loop, 2 = evolve),
  * measured with CUDA events on the library's stream; launches = kernels launched by the last call */
 double dstar_batch_last_kernel_ms(dstar_batch* b, int which);

@@ -76,6 +76,18 @@ int dstar_NScool_get_history(int id, int capacity, int32_t* model, double* time_
                              double* lg_Teff, double* lg_Lsurf, double* lg_Lnu, double* lg_Lnuc);
 /* write LOGS/history.data in the reference's format (readable by tools/reader.py) */
 int dstar_NScool_write_history(int id, const char* path);
+
+/* Profiles (do_write_profile, NScool/private/NScool_profile.f:27-106; written when mod(model,
+ * write_interval_for_profile) == 0, NScool_evolve.f:227-233).  The device keeps ln T of every zone at those
+ * models (control `profile_capacity`: profiles kept per star; -1 = 512 for batches of <= 64 stars, else 0).
+ * get_profile: header = time[d], core_mass, core_radius, accretion_rate, heating_lum, cooling_lum, total_mass,
+ * total_radius; columns(20, nz) zone-major in the reference's column order (zone, mass, dm, area, gravity, eLambda,
+ * ePhi, temperature, luminosity, pressure, density, zbar, abar, Xn, Qimp, Gamma, cp, eps_nu, eps_nuc, K).
+ * write_profiles: "<directory>/<base_profile_filename><model>" per profile + the manifest
+ * "<directory>/<profile_manifest_filename>", same layout as the reference's files (tools/reader.py reads them). */
+int dstar_NScool_profile_count(int id, int32_t* kept, int32_t* produced);
+int dstar_NScool_get_profile(int id, int index, int32_t* model, double* header, double* columns);
+int dstar_NScool_write_profiles(int id, const char* directory);
 /* device timing of the last batch calls [ms]: which = 0 cell loop, 1 face loop, 2 evolve */
 double dstar_NScool_last_kernel_ms(int which);
 /* message of the last failed dstar_NScool_* call */

@@ -236,3 +236,61 @@ def test_second_outburst_recovers_from_oversized_first_step(nscool, oracle):
         assert rel(Teff, ev["Teff_monitor"]) < 1e-6
         np.testing.assert_array_equal(s.counters(), ev["counters"])
         s.free()
+
+
+def test_profiles_from_device_capture(nscool, tmp_path):
+    """do_write_profile (NScool_profile.f): ln T of every zone captured on the device at mod(model, interval) == 0;
+    the other columns rebuilt from the tables.  Checked: model numbering, the last profile against the final state,
+    columns against a direct numpy evaluation of the same splines, file layout (header, 20 columns, manifest)."""
+    s = _star(nscool, 0.3, write_interval_for_profile=3, suppress_first_step_output=False)
+    s.create_model()
+    s.evolve_model()
+    kept, made = s.profile_count()
+    naccpt = s.counters()[3]
+    assert kept == made and kept >= (naccpt // 3) and kept <= naccpt // 3 + 4
+    nz = s.get_int("nz")
+    profs = [s.profile(i) for i in range(kept)]
+    models = [q["model"] for q in profs]
+    assert all(m % 3 == 0 for m in models) and models == sorted(models) and len(set(models)) == len(models)
+    times = [q["time"] for q in profs]
+    assert times == sorted(times) and times[-1] <= 1050.0 + 1e-9
+    q = profs[-1]
+    # columns: structure straight from the star, microphysics from the tables at the profile's temperature
+    assert np.array_equal(q["zone"], np.arange(1, nz + 1))
+    assert np.array_equal(q["dm"], s.array("dm")) and np.array_equal(q["density"], s.array("rho"))
+    assert np.array_equal(q["pressure"], s.array("P_bar"))
+    tab = s.array("tab_lnT"); lnT = np.log(q["temperature"])
+
+    def spline(name, x):
+        f = s.array(name).reshape(nz, 128, 4)
+        k = np.clip(np.searchsorted(tab, x, side="right") - 1, 0, 126)
+        dx = x - tab[k]
+        c = f[np.arange(nz), k]
+        return np.exp(c[:, 0] + dx * (c[:, 1] + dx * (c[:, 2] + dx * c[:, 3])))
+    assert rel(q["cp"], spline("tab_lnCp", lnT)) < 1e-12
+    assert rel(q["Gamma"], spline("tab_lnGamma", lnT)) < 1e-12
+    assert rel(q["eps_nu"], spline("tab_lnEnu", lnT)) < 1e-12
+    assert q["cooling_lum"] == pytest.approx(float(np.dot(q["eps_nu"], q["dm"])), rel=1e-12)
+    assert q["accretion_rate"] == 0.0 and np.all(q["eps_nuc"] == 0.0) and q["heating_lum"] == 0.0   # quiescent epoch
+    assert profs[0]["accretion_rate"] == 1.0e17 and profs[0]["heating_lum"] > 0.0                  # outburst epoch
+    T = q["temperature"]; dm = s.array("dm"); dmb = s.array("dm_bar")
+    Tbar = np.concatenate([[T[0]], 0.5 * (T[:-1] * dm[1:] + T[1:] * dm[:-1]) / dmb[1:]])
+    assert rel(q["K"], spline("tab_lnK", np.log(Tbar))) < 1e-12
+    ePhi = s.array("ePhi"); area = s.array("area")
+    Lref = -(area[1:] ** 2) * s.array("rho_bar")[1:] * q["K"][1:] * (ePhi[:-1] * T[:-1] - ePhi[1:] * T[1:]) \
+        / s.array("ePhi_bar")[1:] / dmb[1:]
+    assert rel(q["luminosity"][1:], Lref) < 1e-12 and q["luminosity"][0] > 0      # heat flows out at the surface
+    # if the last accepted model is a profile model it equals the final state
+    if models[-1] == s.get_int("model"):
+        assert np.array_equal(lnT, s.array("lnT"))
+    # files
+    s.write_profiles(str(tmp_path))
+    man = (tmp_path / "profiles").read_text().splitlines()
+    assert len(man) == kept + 1 and "base profile filename = profile" in man[0]
+    lines = (tmp_path / ("profile%d" % models[-1])).read_text().split("\n")
+    assert lines[3].split()[:3] == ["model", "time", "core_mass"] and int(lines[4].split()[0]) == models[-1]
+    assert lines[8].split()[0] == "zone" and lines[8].split()[-1] == "K" and len(lines[8]) == 20 * 15
+    rows = [l for l in lines[9:] if l.strip()]
+    assert len(rows) == nz and all(len(r) == 20 * 15 for r in rows)
+    assert float(rows[0].split()[7]) == pytest.approx(q["temperature"][0], rel=1e-6)
+    s.free()
