@@ -317,21 +317,32 @@ def run_b200(args):
                                      "dt", "tsec", "model"))
     # ---------------- roofline of the dominant kernel (coefficient pass), FP64 pipe
     fp64_peak = ctx.fp64_peak_tflops()
+    # dominant kernel = the cell pass (ds_micro_kernel<cell>: EOS + neutrino emissivities, ~60 % of the step); its
+    # duration is the library's CUDA-event time on the launching stream, averaged over the timed steps
+    cell_ms = tc / args.steps
     micro_ms = (tc + tf) / args.steps
-    flops = FLOP_CELL * evals_cell + FLOP_FACE * evals_cell
-    achieved_tf = flops / (micro_ms * 1e-3) / 1e12
-    alg_bytes = 64.0 * evals            # ~64 B / eval (32 B of spline coefficients per knot and quantity)
+    achieved_tf = FLOP_CELL * evals_cell / (cell_ms * 1e-3) / 1e12
+    both_tf = (FLOP_CELL + FLOP_FACE) * evals_cell / (micro_ms * 1e-3) / 1e12
+    alg_bytes = 64.0 * evals_cell       # ~64 B / eval (32 B of spline coefficients per knot and quantity)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>+<face>", "achieved": achieved_tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+    # DRAM bytes of one cell-pass launch from the committed ncu --set full capture of this very configuration
+    # (profiles/r01d_ncu_full_summary.md, r01e table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
+    traffic = 7.66e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
+    roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>", "achieved": achieved_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "traffic_note": "bytes per launch, ncu capture r01e (mostly register-spill frames cycling through L2); "
+                                "algorithmic bytes per launch %.3g" % alg_bytes,
+                "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
+                               "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
                 "flops_per_eval": {"cell": FLOP_CELL, "face": FLOP_FACE},
-                "hbm": {"achieved_gbs": alg_bytes / (micro_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "cell_plus_face": {"achieved": both_tf, "frac": both_tf / fp64_peak if fp64_peak > 0 else None},
+                "fp64_pipe_busy_ncu": {"cell": 0.41, "face": 0.50, "source": "profiles/r01d_ncu_full_summary.md"},
+                "hbm": {"achieved_gbs": alg_bytes / (cell_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                 "kernel_ms": {"cells": tc / args.steps, "faces": tf / args.steps, "evolve": te / args.steps}}
     # ---------------- CPU baseline (oracle) on rank 0, N = 1
