@@ -78,6 +78,7 @@ struct dstar_batch {
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<DsIonZ> ionz;
     std::vector<DsIonZ> h_ionz;
+    DevBuf<double> aux;   // (5, total) zone-level inputs of the coefficient pass (ds_zone_aux_kernel)
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
@@ -493,6 +494,8 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     a.rho = b->rho.p; a.rho_bar = b->rho_bar.p; a.P = b->P.p; a.P_bar = b->P_bar.p; a.dm = b->dm.p;
     a.ionic = b->ionic.p; a.ionic_bar = b->ionic_bar.p; a.Yion = b->Yion.p; a.Yion_bar = b->Yion_bar.p;
     a.Zion = b->Zion.p; a.Aion = b->Aion.p; a.ionz = b->ionz.p;
+    if (!b->aux.p) CK(b->aux.alloc((size_t)5 * b->total));
+    a.aux = b->aux.p;
     a.Tc_cell = b->have_Tc_cell ? b->Tc_cell.p : nullptr;
     a.Tc_face = b->have_Tc_face ? b->Tc_face.p : nullptr;
     a.tab_lnT = c->tab_lnT.p; a.tab_T = c->tab_T.p; a.tab_lgT = c->tab_lgT.p;
@@ -514,6 +517,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = b->redo.p; a.redo_count = b->redo_count.p;
+            ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->sf);
             CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
             { const char* e = std::getenv("DSTAR_FORCE_REDO"); a.force_redo = (e && e[0] == '1') ? 1 : 0; }  // test hook
             launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
@@ -530,6 +534,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = nullptr; a.redo_count = nullptr;
+            ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->sf);
             launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());

@@ -65,6 +65,7 @@ struct DsMicroArgs {
     const double *Yion, *Yion_bar;                 // (ncharged, total_zones)
     const double *Zion, *Aion;                     // (ncharged)
     const DsIonZ* ionz;                            // (ncharged) host-evaluated functions of Z (eos.cuh)
+    double* aux;                                   // (5, total_zones) zone-level inputs prepared by ds_zone_aux_kernel
     const double *Tc_cell, *Tc_face;               // (3, total_zones) or null -> gap tables
     const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, dsm::exp(lnT), dsm::log10(T)
     DsEosCtrl eos;
@@ -133,16 +134,40 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, doub
 // launch keeps it out of the hot loop's register allocation (a conditional call inside the loop cost 10 %).
 // With FAST = false and a.redo == null the kernel is the single plain pass (used for the faces, whose EOS is
 // mostly dead code: only Gamma, Theta and mu_e feed the conductivity).
-struct DsZoneIn {
+struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 moments, then the 5 aux values)
     DsComp c;
     double rho, chi, Tc[3];
 };
+static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
+constexpr int DS_YMAX = 128;  // species kept in shared memory per group (more: read from global memory)
+
+// Zone-level inputs that need transcendental functions and table searches (rho of the face pass with the rho_bar(1)
+// fix-up, chi, the three critical temperatures): one thread per zone, once per pass, instead of one lane per group
+// doing three binary searches through HBM while the other 127 wait at the round's first barrier.
+template <bool FACE>
+__global__ void ds_zone_aux_kernel(DsMicroArgs a, DsSfDev sf) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.total_zones) return;
+    const int star = a.zone_star[g];
+    const int iz = g - a.zone_offset[star];
+    const DsComp c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
+    const double rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
+    const double chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
+    double Tc[3];
+    const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
+    if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
+    else ds_sf_get_results(sf, 0.0, dse::neutron_wavenumber(rho, c, chi), Tc);
+    double* o = a.aux + (size_t)5 * g;
+    o[0] = rho; o[1] = chi; o[2] = Tc[0]; o[3] = Tc[1]; o[4] = Tc[2];
+}
+
 template <bool FACE, int G, bool FAST>
 __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     __shared__ double s_h[DS_NTAB], s_v[G][3][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
+    __shared__ double s_Y[G][DS_YMAX];
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
@@ -162,16 +187,12 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         const int star = a.zone_star[g];
         const int iz = g - a.zone_offset[star];
         const int nz = a.zone_offset[star + 1] - a.zone_offset[star];
-        if (it == 0) {
-            DsZoneIn& zi = s_zone[grp];
-            zi.c = ds_load_comp((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g);
-            zi.rho = FACE ? ((iz == 0) ? a.rho_bar1[star] : a.rho_bar[g]) : a.rho[g];
-            zi.chi = dse::nuclear_volume_fraction(zi.rho, zi.c, DS_DEFAULT_NUCLEAR_RADIUS);
-            const double kn = dse::neutron_wavenumber(zi.rho, zi.c, zi.chi);
-            const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
-            if (Tcin) { zi.Tc[0] = Tcin[3 * (size_t)g]; zi.Tc[1] = Tcin[3 * (size_t)g + 1]; zi.Tc[2] = Tcin[3 * (size_t)g + 2]; }
-            else ds_sf_get_results(sf, 0.0, kn, zi.Tc);
-        }
+        // prologue: 16 lanes fetch the zone's 11 composition moments and 5 prepared values, the next lanes its
+        // abundances -- independent loads, one memory round trip per round
+        if (it < 11) reinterpret_cast<double*>(&s_zone[grp])[it] = ((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g)[it];
+        else if (it < 16) reinterpret_cast<double*>(&s_zone[grp])[it] = a.aux[(size_t)5 * g + (it - 11)];
+        const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
+        if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
         const DsComp& c = s_zone[grp].c;
         const double& rho = s_zone[grp].rho;
@@ -189,7 +210,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         }
         {
             DsEosRes r;
-            const double* Yz = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
+            const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
             ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, a.ionz, Yz, Tc[1], chi, r, bad);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
