@@ -139,7 +139,8 @@ struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 mom
     double rho, chi, Tc[3];
 };
 static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
-constexpr int DS_YMAX = 128;  // species kept in shared memory per group (more: read from global memory)
+constexpr int DS_YMAX = 96;   // species kept in shared memory per group (more: read from global memory)
+constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each) are kept in shared memory
 
 // Zone-level inputs that need transcendental functions and table searches (rho of the face pass with the rho_bar(1)
 // fix-up, chi, the three critical temperatures): one thread per zone, once per pass, instead of one lane per group
@@ -168,8 +169,19 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
     __shared__ double s_Y[G][DS_YMAX];
+    __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
+    __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
+    const bool net_in_smem = a.ncharged <= DS_YMAX, ionz_in_smem = a.ncharged <= DS_IONZ_SMEM;
+    if (net_in_smem)
+        for (int i = threadIdx.x; i < a.ncharged; i += blockDim.x) { s_ZA[0][i] = a.Zion[i]; s_ZA[1][i] = a.Aion[i]; }
+    if (ionz_in_smem)
+        for (int i = threadIdx.x; i < a.ncharged * (int)(sizeof(DsIonZ) / sizeof(double)); i += blockDim.x)
+            reinterpret_cast<double*>(s_ionz)[i] = reinterpret_cast<const double*>(a.ionz)[i];
+    const double* Zn = net_in_smem ? s_ZA[0] : a.Zion;
+    const double* An = net_in_smem ? s_ZA[1] : a.Aion;
+    const DsIonZ* ionz = ionz_in_smem ? s_ionz : a.ionz;
     const double T = a.tab_T[it], lgT = a.tab_lgT[it];
     // second pass (FAST = false with a redo list): the work items are the list entries, densely packed
     const bool redo_pass = !FAST && a.redo != nullptr;
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             DsEosRes r;
             const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, a.Zion, a.Aion, a.ionz, Yz, Tc[1], chi, r, bad);
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
