@@ -331,11 +331,11 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # DRAM bytes of one cell-pass launch from the committed ncu --set full capture of this very configuration
-    # (profiles/r01d_ncu_full_summary.md, r01e table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
-    traffic = 7.66e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
+    # (profiles/r01d_ncu_full_summary.md, r01g table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
+    traffic = 7.31e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
     roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>", "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                "traffic_note": "bytes per launch, ncu capture r01e (mostly register-spill frames cycling through L2); "
+                "traffic_note": "bytes per launch, ncu capture r01g (mostly register-spill frames cycling through L2); "
                                 "algorithmic bytes per launch %.3g" % alg_bytes,
                 "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
                                "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
@@ -360,8 +360,8 @@ def run_b200(args):
             "curves_per_sec": n_star * world / (ms_step * 1e-3),
             "e2e": {"value": evals * world / e2e_s, "unit": UNIT, "curves_per_sec": n_star * world / e2e_s,
                     "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            # launches per step: cell pass (branch-free) + cell redo pass + face pass + evolve
-            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            # launches per step: zone pre-pass + cell pass (branch-free) + cell redo pass, zone pre-pass + face pass, evolve
+            "gpu_launches": 6 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "all_stars_converged": ok, "wall_s_resident_loop": wall_res}
     if dist is not None:
         # final gather of the light curves (the only collective of the job)
