@@ -692,7 +692,8 @@ DS_D void LM_corrections(double rs, double Gamma_e, const DsComp& c, DsThermo& r
 template <bool FAST>
 DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsComp& c,
                 int ncharged, const double* Zion, const double* Aion, const DsIonZ* __restrict__ ionz,
-                const double* Yion, double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad) {
+                const double* Yion, double& Gamma, double& ionQ, int& phase, DsThermo& r, bool& bad,
+                const unsigned char* act = nullptr, int nact = 0) {
     DS_DEN_SCOPE(FAST);
     const double Q2_threshold = 18.0;
     int err = 0;
@@ -704,7 +705,11 @@ DS_D int ion_mixture(const DsEosCtrl& rq, double rs, double Gamma_e, const DsCom
     if (phase == ds_liquid_phase && ionQ2 > Q2_threshold) err = 1;
 
     double f = 0, u = 0, p = 0, s = 0, cv = 0, dpr = 0, dpt = 0;
-    for (int i = 0; i < ncharged; ++i) {
+    // `act` (optional): the indices of the species above the abundance threshold, ascending -- the coefficient pass
+    // builds it once per zone, so the loop (whose head reloads spilled registers) runs 1-2 times instead of ncharged
+    const int n_iter = act ? nact : ncharged;
+    for (int it_ = 0; it_ < n_iter; ++it_) {
+        const int i = act ? act[it_] : it_;
         if (Yion[i] > rq.Ythresh) {
             DsThermo t;
             one_ion<FAST>(Gamma_e, rs, Zion[i], Aion[i], ionz[i], phase, t, bad);
@@ -841,7 +846,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
                             const DsIonZ* __restrict__ ionz, const double* __restrict__ Yion, double Tns, double chi,
                             DsEosRes& o, bool& bad,
-                            double* __restrict__ comps = nullptr) {
+                            double* __restrict__ comps = nullptr, const unsigned char* act = nullptr, int nact = 0) {
     DS_DEN_SCOPE(FAST);
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
@@ -872,7 +877,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     // ions (ion.f:20-92)
     DsThermo ion;
     int phase;
-    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad);
+    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad, act, nact);
     DS_PHASE();
     const double n_i = ne / den(c.Z);
     const double nik = n_i * boltzmann;

@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
     __shared__ double s_Y[G][DS_YMAX];
+    __shared__ unsigned char s_act[G][DS_YMAX];   // indices of the zone's species above the abundance threshold
+    __shared__ int s_nact[G];
     __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
     __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
@@ -206,6 +208,14 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
         if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
+        if (!FACE) {   // (the face pass never enters the species loop: its ion thermodynamics are dead code)
+            if (a.ncharged <= DS_YMAX && it == 0) {   // active-species list of the zone (ascending, as the reference loops)
+                int na = 0;
+                for (int i = 0; i < a.ncharged; ++i) if (s_Y[grp][i] > a.eos.Ythresh) s_act[grp][na++] = (unsigned char)i;
+                s_nact[grp] = na;
+            }
+            __syncthreads();
+        }
         const DsComp& c = s_zone[grp].c;
         const double& rho = s_zone[grp].rho;
         const double& chi = s_zone[grp].chi;
@@ -224,7 +234,8 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             DsEosRes r;
             const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad);
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
+                                    (!FACE && a.ncharged <= DS_YMAX) ? s_act[grp] : nullptr, FACE ? 0 : s_nact[grp]);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][it] = dsm::log(r.Cp);
