@@ -78,7 +78,7 @@ struct dstar_batch {
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<DsIonZ> ionz;
     std::vector<DsIonZ> h_ionz;
-    DevBuf<double> aux;   // (5, total) zone-level inputs of the coefficient pass (ds_zone_aux_kernel)
+    DevBuf<double> aux;   // (DS_AUX, total) zone-level inputs of the coefficient pass (ds_zone_aux_kernel)
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
@@ -494,7 +494,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     a.rho = b->rho.p; a.rho_bar = b->rho_bar.p; a.P = b->P.p; a.P_bar = b->P_bar.p; a.dm = b->dm.p;
     a.ionic = b->ionic.p; a.ionic_bar = b->ionic_bar.p; a.Yion = b->Yion.p; a.Yion_bar = b->Yion_bar.p;
     a.Zion = b->Zion.p; a.Aion = b->Aion.p; a.ionz = b->ionz.p;
-    if (!b->aux.p) CK(b->aux.alloc((size_t)5 * b->total));
+    if (!b->aux.p) CK(b->aux.alloc((size_t)DS_AUX * b->total));
     a.aux = b->aux.p;
     a.Tc_cell = b->have_Tc_cell ? b->Tc_cell.p : nullptr;
     a.Tc_face = b->have_Tc_face ? b->Tc_face.p : nullptr;

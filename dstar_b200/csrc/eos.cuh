@@ -46,11 +46,12 @@ using namespace dsc;
 
 
 template <bool FAST>
-DS_D void lattice_properties(double rho, double T, const DsComp& c, double& ne, double& rs,
+DS_D void lattice_properties(double rho, double T, const DsComp& c, const DsZonePre& zp, double& ne, double& rs,
                         double& Gamma_e, double& Gamma, double& ionQ, bool& bad) {
     DS_DEN_SCOPE(FAST);
-    ne = rho * c.Ye / den_c(amu);
-    rs = dsm::pow(3.0 / den_c(fourpi) / den(ne), onethird) / den_c(a_Bohr);
+    (void)rho;
+    ne = zp.ne;   // rho Ye / amu and (3 / 4 pi ne)^(1/3) / a_Bohr: zone-level, see DsZonePre
+    rs = zp.rs;
     Gamma_e = 2.0 * Rydberg / den_c(boltzmann) / den(T) / den(rs);
     Gamma = Gamma_e * c.Z53;
     ionQ = sq(3.0 * (Gamma_e * Gamma_e) * Melectron / den(rs) / den_c(amu) * c.Z2XoA2 * c.A / den(c.Z));
@@ -773,12 +774,12 @@ DS_D double ifermi12(double f) {  // :528-580
 }
 
 template <bool FAST>
-DS_D void MB77(double n, double T, double Tns, DsThermo& r, bool& bad) {
+DS_D void MB77(double n, double T, double Tns, const DsZonePre& zp, DsThermo& r, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double c[4] = {DS_R4(1.2974), DS_R4(15.0298), DS_R4(-15.2343), DS_R4(7.4663)};
     r = DsThermo{0, 0, 0, 0, 0, 0, 0};
     if (n == 0.0) return;
-    double k = dsm::pow(0.5 * threepisquare * n, onethird) / den_c(cm_to_fm);
+    double k = zp.k_mb;   // (3 pi^2 n / 2)^(1/3) / cm_to_fm: zone-level, see DsZonePre
     double dkdn = onethird * k / den(n);
     double u = k * (c[0] + k * (c[1] + k * (c[2] + k * c[3])));
     u = u * mev_to_ergs;
@@ -842,7 +843,7 @@ struct DsEosRes {
 // because of the DS_PHASE barriers inside).
 template <bool FAST>
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
-                            double logT, const DsComp& c, int ncharged,
+                            double logT, const DsComp& c, const DsZonePre& zp, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
                             const DsIonZ* __restrict__ ionz, const double* __restrict__ Yion, double Tns, double chi,
                             DsEosRes& o, bool& bad,
@@ -850,7 +851,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     DS_DEN_SCOPE(FAST);
     using namespace dsc;
     double ne, rs, Gamma_e, Gamma, ionQ;
-    dse::lattice_properties<FAST>(rho, T, c, ne, rs, Gamma_e, Gamma, ionQ, bad);
+    dse::lattice_properties<FAST>(rho, T, c, zp, ne, rs, Gamma_e, Gamma, ionQ, bad);
     DS_PHASE();
 
     // electrons: table + exchange (electron.f:10-51, :53-250)
@@ -887,7 +888,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     // dripped neutrons (neutron.f:15-69)
     const double nn = rho * c.Yn / den_c(amu) / den(1.0 - chi);
     DsThermo nt;
-    dse::MB77<FAST>(nn, T, Tns, nt, bad);
+    dse::MB77<FAST>(nn, T, Tns, zp, nt, bad);
     DS_PHASE();
     const double unfac = avogadro * c.Yn, pnfac = 1.0, snfac = unfac;
 

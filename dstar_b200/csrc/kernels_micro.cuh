@@ -65,7 +65,7 @@ struct DsMicroArgs {
     const double *Yion, *Yion_bar;                 // (ncharged, total_zones)
     const double *Zion, *Aion;                     // (ncharged)
     const DsIonZ* ionz;                            // (ncharged) host-evaluated functions of Z (eos.cuh)
-    double* aux;                                   // (5, total_zones) zone-level inputs prepared by ds_zone_aux_kernel
+    double* aux;                                   // (DS_AUX, total_zones) zone-level inputs prepared by ds_zone_aux_kernel
     const double *Tc_cell, *Tc_face;               // (3, total_zones) or null -> gap tables
     const double *tab_lnT, *tab_T, *tab_lgT;       // (128) host-evaluated knots: lnT, dsm::exp(lnT), dsm::log10(T)
     DsEosCtrl eos;
@@ -139,6 +139,7 @@ struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 mom
     double rho, chi, Tc[3];
 };
 static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
+constexpr int DS_AUX = 5 + (int)(sizeof(DsZonePre) / sizeof(double));   // rho, chi, Tc(3), then DsZonePre
 constexpr int DS_YMAX = 96;   // species kept in shared memory per group (more: read from global memory)
 constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each) are kept in shared memory
 
@@ -158,8 +159,10 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsSfDev sf) {
     const double* Tcin = FACE ? a.Tc_face : a.Tc_cell;
     if (Tcin) { Tc[0] = Tcin[3 * (size_t)g]; Tc[1] = Tcin[3 * (size_t)g + 1]; Tc[2] = Tcin[3 * (size_t)g + 2]; }
     else ds_sf_get_results(sf, 0.0, dse::neutron_wavenumber(rho, c, chi), Tc);
-    double* o = a.aux + (size_t)5 * g;
+    double* o = a.aux + (size_t)DS_AUX * g;
     o[0] = rho; o[1] = chi; o[2] = Tc[0]; o[3] = Tc[1]; o[4] = Tc[2];
+    const DsZonePre zp = ds_zone_pre(rho, c, chi);
+    for (int q = 0; q < DS_AUX - 5; ++q) o[5 + q] = reinterpret_cast<const double*>(&zp)[q];
 }
 
 template <bool FACE, int G, bool FAST>
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     __shared__ double s_Y[G][DS_YMAX];
     __shared__ unsigned char s_act[G][DS_YMAX];   // indices of the zone's species above the abundance threshold
     __shared__ int s_nact[G];
+    __shared__ DsZonePre s_pre[G];
     __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
     __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         // prologue: 16 lanes fetch the zone's 11 composition moments and 5 prepared values, the next lanes its
         // abundances -- independent loads, one memory round trip per round
         if (it < 11) reinterpret_cast<double*>(&s_zone[grp])[it] = ((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g)[it];
-        else if (it < 16) reinterpret_cast<double*>(&s_zone[grp])[it] = a.aux[(size_t)5 * g + (it - 11)];
+        else if (it < 16) reinterpret_cast<double*>(&s_zone[grp])[it] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+        else if (it < 11 + DS_AUX) reinterpret_cast<double*>(&s_pre[grp])[it - 16] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
         if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
@@ -217,6 +222,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             __syncthreads();
         }
         const DsComp& c = s_zone[grp].c;
+        const DsZonePre& zp = s_pre[grp];
         const double& rho = s_zone[grp].rho;
         const double& chi = s_zone[grp].chi;
         const double* Tc = s_zone[grp].Tc;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             DsEosRes r;
             const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, zp, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
                                     (!FACE && a.ncharged <= DS_YMAX) ? s_act[grp] : nullptr, FACE ? 0 : s_nact[grp]);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                 if (on && iz == 0 && it == 0)  // create_model.f:367-369
                     a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
                 DsNeutrino eps;
-                dsn::ds_crust_neutrino<FAST>(rho, T, c, chi, Tc[1], a.nu_channels, eps, bad);
+                dsn::ds_crust_neutrino<FAST>(rho, T, c, zp, chi, Tc[1], a.nu_channels, eps, bad);
                 double lnenu = dsm::log(eps.total / rho);
                 if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
                     if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
@@ -296,12 +302,13 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     if (chi == -1.0) chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
     DsEosRes r;
     bool bad = false;
+    const DsZonePre zp = ds_zone_pre(rho, c, chi);
     double* cp = (a.comps && live) ? a.comps + (size_t)28 * k : nullptr;
-    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion, a.ionz,
+    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, zp, a.ncharged, a.Zion, a.Aion, a.ionz,
                             a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, bad, cp);
     if (__syncthreads_or(bad)) {
         bool unused = false;
-        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, a.ncharged, a.Zion, a.Aion, a.ionz,
+        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, zp, a.ncharged, a.Zion, a.Aion, a.ionz,
                                  a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, unused, cp);
     }
     if (!live) return;
@@ -327,7 +334,8 @@ __global__ void ds_eval_nu_kernel(DsEvalNuArgs a) {
     if (!live) k = a.n - 1;
     DsNeutrino e;
     bool unused = false;
-    dsn::ds_crust_neutrino<false>(a.rho[k], a.T[k], ds_load_comp(a.ionic + (size_t)11 * k), a.chi[k], a.Tcn[k],
+    const DsComp cc = ds_load_comp(a.ionic + (size_t)11 * k);
+    dsn::ds_crust_neutrino<false>(a.rho[k], a.T[k], cc, ds_zone_pre(a.rho[k], cc, a.chi[k]), a.chi[k], a.Tcn[k],
                                   a.channels, e, unused);
     if (!live) return;
     double* o = a.eps + (size_t)6 * k;

@@ -26,10 +26,10 @@ constexpr double cn_cap = 1.0 - cn_ca;
 
 
 template <bool FAST>
-DS_D double plasma(double t, double r, bool& bad) {
+DS_D double plasma(double t, double r, const DsZonePre& zp, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double cvd = cn_cv * cn_cv + cn_dn * (cn_cvp * cn_cvp);
-    double rdouble = dsm::log10(2.0 * r);
+    double rdouble = zp.pl_lg;   // log10(2 r): zone-level, see DsZonePre
     double x = (17.5 + rdouble - 3.0 * t) / den_c(6.0);
     double y = (-24.5 + rdouble + 3.0 * t) / den_c(6.0);
     double enum_ = fmin(0.0, y - 1.6 + 1.25 * x);
@@ -41,7 +41,7 @@ DS_D double plasma(double t, double r, bool& bad) {
                          dsm::exp(-dsd::ipow<2>(enum_ / den(0.57 - 0.25 * x)));
     }
     double lamb = 1.686e-10 * t;
-    double gamd = 1.1095e11 * r / den((t * t) * sq(1.0 + dsm::pow(1.019e-6 * r, two_thirds)));
+    double gamd = 1.1095e11 * r / den((t * t) * sq(1.0 + zp.pl_p23));
     double gam = sq(gamd);
     double ft = 2.4 + 0.6 * sq(gam) + 0.51 * gam + 1.25 * dsm::pow(gam, 1.5);
     double fl = (8.6 * gamd + 1.35 * dsm::pow(gam, 7.0 / den_c(2.0))) / den(225.0 - 17.0 * gam + gamd);
@@ -52,7 +52,7 @@ DS_D double plasma(double t, double r, bool& bad) {
 }
 
 template <bool FAST>
-DS_D double pair(double temp, double rhom, bool& bad) {
+DS_D double pair(double temp, double rhom, const DsZonePre& zp, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double a0 = 6.002e19, a1 = 2.084e20, a2 = 1.872e21;
     const double b1 = 9.383e-1, b2 = -4.141e-1, b3 = 5.829e-2, c = 5.5924e0;
@@ -60,7 +60,7 @@ DS_D double pair(double temp, double rhom, bool& bad) {
     const double coep = (cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap);
     const double coem = (cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap);
     double lam = temp / den_c(5.9302e9);
-    double xi = dsm::pow(rhom * 1.0e-9, onethird) / den(lam);
+    double xi = zp.cbrt_rY9 / den(lam);
     double qp1 = 10.74800 * (lam * lam) + 0.3967 * sq(lam) + 1.005;
     double qp2 = rhom / den(7.692e7 * dsd::ipow<3>(lam) + 9.715e6 * sq(lam));
     double qp = (1.0 / den(qp1)) * dsm::pow(1.0 + qp2, -0.3);
@@ -109,14 +109,14 @@ DS_D double cfp(double lamb, double xi, bool& bad) {
 }
 
 template <bool FAST>
-DS_D double photo(double rhom, double lamb, bool& bad) {
+DS_D double photo(double rhom, double lamb, const DsZonePre& zp, bool& bad) {
     DS_DEN_SCOPE(FAST);
     const double coe1 = 0.5 * ((cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap));
     const double coe2 = ((cn_cv * cn_cv - cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp - cn_cap * cn_cap)) /
                         ((cn_cv * cn_cv + cn_ca * cn_ca) + cn_dn * (cn_cvp * cn_cvp + cn_cap * cn_cap));
     double poly = 1.875e8 * lamb + 1.653e8 * (lamb * lamb) + 8.499e8 * dsd::ipow<3>(lamb) - 1.604e8 * dsd::ipow<4>(lamb);
     double qp = 0.666 * dsm::pow(1.0 + 2.045 * lamb, -2.066) * (1.0 / den(1.0 + rhom * (1.0 / poly)));
-    double xi = dsm::pow(rhom * 1.e-9, onethird) / den(lamb);
+    double xi = zp.cbrt_rY9 / den(lamb);
     double fp = cfp<FAST>(lamb, xi, bad);
     return coe1 * (1.0 - coe2 * qp) * rhom * dsd::ipow<5>(lamb) * fp;
 }
@@ -141,15 +141,14 @@ DS_D double pbf(double kF, double T, double Tns, bool& bad) {
 }
 
 template <bool FAST>
-DS_D double bremsstrahlung(double rho, double T, const DsComp& c, bool& bad) {
+DS_D double bremsstrahlung(double rho, double T, const DsComp& c, const DsZonePre& zp, bool& bad) {
     DS_DEN_SCOPE(FAST);
-    const double threefourth = 3.0 / den_c(4.0), GF = 1.436e-49, Cp2 = 1.675;
+    const double threefourth = 3.0 / 4.0, GF = 1.436e-49, Cp2 = 1.675;
     double qbrems_pre = 8.0 * pi * (GF * GF) * (finestructure * finestructure) * Cp2 *
                         dsd::ipow<6>(boltzmann / den_c(hbar) / den_c(clight)) / den_c(567.0) / den_c(hbar) / den_c(amu);
-    double re = dsm::pow(threefourth / den_c(pi) * amu / den(rho) / den(c.Ye), onethird);
-    double kF = dsm::pow(threepisquare * rho * c.Ye / den_c(amu), onethird);
+    double kF = zp.kFb;   // (3 pi^2 rho Ye / amu)^(1/3); re and eta likewise zone-level, see DsZonePre
     double tau = 0.5 * boltzmann * T / den_c(hbar) / den_c(clight) / den(kF);
-    double eta = dsm::pow(c.A / den(c.Z), onethird) / den(re) / den_c(cm_to_fm);
+    double eta = zp.etab;
     double Zbareta = c.Z * eta;
     double A = 0.269 + 20.0 * tau + 0.0168 * c.Z + 0.00121 * eta - 0.0356 * Zbareta + 0.0137 * c.Z2 * tau +
                1.54 * Zbareta * tau;
@@ -159,7 +158,7 @@ DS_D double bremsstrahlung(double rho, double T, const DsComp& c, bool& bad) {
 }
 
 template <bool FAST>
-DS_D void ds_crust_neutrino(double rho, double T, const DsComp& c, double chi, double Tcn,
+DS_D void ds_crust_neutrino(double rho, double T, const DsComp& c, const DsZonePre& zp, double chi, double Tcn,
                                const int* ch, DsNeutrino& eps, bool& bad) {
     DS_DEN_SCOPE(FAST);
     double Tme = Melectron * clight2 / den_c(boltzmann);
@@ -167,18 +166,17 @@ DS_D void ds_crust_neutrino(double rho, double T, const DsComp& c, double chi, d
     double lambda = T / den(Tme);
     eps = DsNeutrino{0, 0, 0, 0, 0, 0};
     DS_PHASE();
-    if (ch[0]) eps.pair = pair<FAST>(T, rY, bad);
+    if (ch[0]) eps.pair = pair<FAST>(T, rY, zp, bad);
     DS_PHASE();
-    if (ch[1]) eps.photo = photo<FAST>(rY, lambda, bad);
+    if (ch[1]) eps.photo = photo<FAST>(rY, lambda, zp, bad);
     DS_PHASE();
-    if (ch[2]) eps.plasma = plasma<FAST>(T, rY, bad);
+    if (ch[2]) eps.plasma = plasma<FAST>(T, rY, zp, bad);
     DS_PHASE();
-    if (ch[3]) eps.brems = bremsstrahlung<FAST>(rho, T, c, bad);
+    if (ch[3]) eps.brems = bremsstrahlung<FAST>(rho, T, c, zp, bad);
     DS_PHASE();
     if (ch[4]) {
-        double nn = rho * c.Yn / den_c(amu) / den(1.0 - chi);
-        double kn = dsm::pow(DS_R4(1.5) * (pi * pi) * nn, onethird) / den_c(cm_to_fm);
-        eps.pbf = pbf<FAST>(kn, T, Tcn, bad);
+        (void)chi;
+        eps.pbf = pbf<FAST>(zp.kn_pbf, T, Tcn, bad);   // kn = (1.5 pi^2 nn)^(1/3) / cm_to_fm: zone-level
     }
     DS_PHASE();
     eps.total = eps.pair + eps.photo + eps.plasma + eps.brems + eps.pbf;
