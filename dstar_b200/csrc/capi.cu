@@ -41,6 +41,7 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         return cudaMalloc(&p, count * sizeof(T));
     }
+    cudaError_t ensure(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(count); }   // no realloc per step
     cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
         if (count > n || !p) { cudaError_t e = alloc(count); if (e != cudaSuccess) return e; }
         return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
@@ -54,6 +55,7 @@ struct DevBuf {
 struct dstar_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // uploads that only the face pass / the evolve kernel need (overlap the cell pass)
     cudaDeviceProp prop{};
     bool helm_loaded = false;
     DsHelmDev helm{};
@@ -78,12 +80,15 @@ struct dstar_batch {
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<DsIonZ> ionz;
     std::vector<DsIonZ> h_ionz;
+    std::vector<double> h_rb1;
     DevBuf<double> aux;   // (DS_AUX, total) zone-level inputs of the coefficient pass (ds_zone_aux_kernel)
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
     DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // ordering between the two streams: face inputs / evolve inputs uploaded (copy stream), last compute issued (main)
+    cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr;
     double ms[3] = {0, 0, 0};
     int launches = 0;
 };
@@ -172,6 +177,7 @@ int dstar_ctx_create(int device, dstar_ctx** out) {
     c->device = device;
     CK(cudaGetDeviceProperties(&c->prop, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     DsHostConsts hc;
     fill_host_consts(hc);
     CK(cudaMemcpyToSymbol(ds_hc, &hc, sizeof hc));
@@ -195,6 +201,7 @@ void dstar_ctx_destroy(dstar_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -415,6 +422,9 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(b->redo.alloc(b->total)); CK(b->redo_count.alloc(1));
     CK(b->rho_bar1.alloc(n_star));
     CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
+    CK(cudaEventCreateWithFlags(&b->ev_face_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_evolve_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_busy, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(st));
     *out = b;
     return DSTAR_OK;
@@ -423,6 +433,10 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
 void dstar_batch_destroy(dstar_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->copy_stream); cudaStreamSynchronize(b->ctx->stream);
+    if (b->ev_face_in) cudaEventDestroy(b->ev_face_in);
+    if (b->ev_evolve_in) cudaEventDestroy(b->ev_evolve_in);
+    if (b->ev_busy) cudaEventDestroy(b->ev_busy);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     delete b;
@@ -437,20 +451,28 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
     CK(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
     const size_t n = b->total;
-    CK(b->rho.upload(rho, n, s)); CK(b->rho_bar.upload(rho_bar, n, s)); CK(b->P.upload(P, n, s));
+    // Inputs of the cell pass go on the compute stream; what only the face pass needs goes on the copy stream and
+    // overlaps the cell pass.  The copy stream first waits for the compute issued so far (no overwrite of buffers a
+    // running kernel still reads).  With pinned host arrays these copies are asynchronous: the arrays must stay
+    // untouched until the next call that synchronises (micro_tables, evolve, download_*).
+    cudaStream_t cs = b->ctx->copy_stream;
+    CK(cudaStreamWaitEvent(cs, b->ev_busy, 0));
+    CK(b->rho.upload(rho, n, s)); CK(b->P.upload(P, n, s));
     CK(b->P_bar.upload(P_bar, n, s)); CK(b->dm.upload(dm, n, s)); CK(b->ionic.upload(ionic, 11 * n, s));
-    CK(b->ionic_bar.upload(ionic_bar, 11 * n, s)); CK(b->Yion.upload(Yion, b->ncharged * n, s));
-    CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, s)); CK(b->Zion.upload(Zion, b->ncharged, s));
+    CK(b->Yion.upload(Yion, b->ncharged * n, s));
+    CK(b->Zion.upload(Zion, b->ncharged, s));
     CK(b->Aion.upload(Aion, b->ncharged, s));
     CK(upload_ionz(b->ionz, b->h_ionz, b->ncharged, Zion, s));
     b->have_Tc_cell = Tc_cell != nullptr; b->have_Tc_face = Tc_face != nullptr;
     if (Tc_cell) CK(b->Tc_cell.upload(Tc_cell, 3 * n, s));
-    if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, s));
     // rho_bar(1) starts from the uploaded value of each star's first face
-    std::vector<double> rb1(b->n_star);
-    for (int i = 0; i < b->n_star; ++i) rb1[i] = rho_bar[b->h_zone_offset[i]];
-    CK(b->rho_bar1.upload(rb1.data(), b->n_star, s));
-    CK(cudaStreamSynchronize(s));
+    b->h_rb1.resize(b->n_star);
+    for (int i = 0; i < b->n_star; ++i) b->h_rb1[i] = rho_bar[b->h_zone_offset[i]];
+    CK(b->rho_bar1.upload(b->h_rb1.data(), b->n_star, s));
+    CK(b->rho_bar.upload(rho_bar, n, cs)); CK(b->ionic_bar.upload(ionic_bar, 11 * n, cs));
+    CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, cs));
+    if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, cs));
+    CK(cudaEventRecord(b->ev_face_in, cs));
     b->have_structure = true;
     return DSTAR_OK;
 }
@@ -458,6 +480,7 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
 int dstar_batch_set_Tc_face(dstar_batch* b, const double* Tc_face) {
     if (!b || !Tc_face) return fail(DSTAR_ERR_ARG, "set_Tc_face");
     CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamWaitEvent(b->ctx->stream, b->ev_face_in, 0));
     CK(b->Tc_face.upload(Tc_face, (size_t)3 * b->total, b->ctx->stream));
     CK(cudaStreamSynchronize(b->ctx->stream));
     b->have_Tc_face = true;
@@ -466,6 +489,7 @@ int dstar_batch_set_Tc_face(dstar_batch* b, const double* Tc_face) {
 int dstar_batch_set_ionic_bar(dstar_batch* b, const double* ionic_bar) {
     if (!b || !ionic_bar) return fail(DSTAR_ERR_ARG, "set_ionic_bar");
     CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamWaitEvent(b->ctx->stream, b->ev_face_in, 0));
     CK(b->ionic_bar.upload(ionic_bar, (size_t)11 * b->total, b->ctx->stream));
     CK(cudaStreamSynchronize(b->ctx->stream));
     return DSTAR_OK;
@@ -534,6 +558,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = nullptr; a.redo_count = nullptr;
+            CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
             ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->sf);
             launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
@@ -543,6 +568,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[1] = ms;
         ++b->launches;
     }
+    CK(cudaEventRecord(b->ev_busy, s));
     b->have_tables = true;
     return DSTAR_OK;
 }
@@ -591,7 +617,8 @@ int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double
         return fail(DSTAR_ERR_ARG, "batch_upload_evolve");
     if (!b->have_structure) return fail(DSTAR_ERR_STATE, "structure not uploaded");
     CK(cudaSetDevice(b->ctx->device));
-    cudaStream_t s = b->ctx->stream;
+    cudaStream_t s = b->ctx->copy_stream;   // only the evolve kernel reads these: overlap the coefficient pass
+    CK(cudaStreamWaitEvent(s, b->ev_busy, 0));
     const size_t n = b->total, ns = b->n_star;
     CK(b->dm_bar.upload(dm_bar, n, s)); CK(b->area.upload(area, n, s)); CK(b->ePhi.upload(ePhi, n, s));
     CK(b->e2Phi.upload(e2Phi, n, s)); CK(b->ePhi_bar.upload(ePhi_bar, n, s)); CK(b->e2Phi_bar.upload(e2Phi_bar, n, s));
@@ -606,14 +633,14 @@ int dstar_batch_upload_evolve(dstar_batch* b, const double* dm_bar, const double
     b->have_enuc = enuc_per_Mdot != nullptr;
     if (enuc_per_Mdot) CK(b->enuc.upload(enuc_per_Mdot, n, s));
     b->n_epoch = n_epoch; b->n_atm = n_atm; b->atm_nv = atm_nv;
-    CK(b->dt.alloc(ns)); CK(b->tsec.alloc(ns)); CK(b->model.alloc(ns));
+    CK(b->dt.ensure(ns)); CK(b->tsec.ensure(ns)); CK(b->model.ensure(ns));
     CK(cudaMemsetAsync(b->dt.p, 0, ns * sizeof(double), s));   // NScool_init.f:59-62
     CK(cudaMemsetAsync(b->tsec.p, 0, ns * sizeof(double), s));
     CK(cudaMemsetAsync(b->model.p, 0, ns * sizeof(int), s));
-    CK(b->t_mon.alloc((size_t)n_epoch * ns)); CK(b->Teff_mon.alloc((size_t)n_epoch * ns));
-    CK(b->Qb_mon.alloc((size_t)n_epoch * ns)); CK(b->idid.alloc((size_t)n_epoch * ns));
-    CK(b->counters.alloc(7 * ns)); CK(b->Teff.alloc(ns)); CK(b->Lsurf.alloc(ns));
-    CK(cudaStreamSynchronize(s));
+    CK(b->t_mon.ensure((size_t)n_epoch * ns)); CK(b->Teff_mon.ensure((size_t)n_epoch * ns));
+    CK(b->Qb_mon.ensure((size_t)n_epoch * ns)); CK(b->idid.ensure((size_t)n_epoch * ns));
+    CK(b->counters.ensure(7 * ns)); CK(b->Teff.ensure(ns)); CK(b->Lsurf.ensure(ns));
+    CK(cudaEventRecord(b->ev_evolve_in, s));
     b->have_evolve = true;
     return DSTAR_OK;
 }
@@ -624,6 +651,7 @@ int dstar_batch_reset_state(dstar_batch* b) {
     CK(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
     const size_t ns = b->n_star;
+    CK(cudaStreamWaitEvent(s, b->ev_evolve_in, 0));
     CK(cudaMemcpyAsync(b->lnT.p, b->lnT0.p, (size_t)b->total * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemsetAsync(b->dt.p, 0, ns * sizeof(double), s));
     CK(cudaMemsetAsync(b->tsec.p, 0, ns * sizeof(double), s));
@@ -674,6 +702,7 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     a.prof_Mdot = b->prof_Mdot.p; a.prof_lnT = b->prof_lnT.p;
     // the star's rho_bar(1) is the fixed-up one (create_model.f:367-369): patch it into rho_bar
     // (the evolve kernel never reads face 0's rho_bar, L(1) comes from the atmosphere; kept for symmetry)
+    CK(cudaStreamWaitEvent(s, b->ev_evolve_in, 0));   // evolve inputs were uploaded on the copy stream
     CK(cudaEventRecord(b->ev0, s));
     const int threads = ((b->max_nz + 31) / 32) * 32;
     if (threads <= 256) ds_evolve_kernel<256><<<b->n_star, threads, 0, s>>>(a);
@@ -682,6 +711,7 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     CK(cudaEventRecord(b->ev1, s));
     CK(cudaEventSynchronize(b->ev1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[2] = ms;
+    CK(cudaEventRecord(b->ev_busy, s));
     b->launches = 1;
     return DSTAR_OK;
 }
