@@ -111,7 +111,11 @@ void dstar_batch_destroy(dstar_batch* b);
 /* H2D of the structure arrays (type NScool_info, NScool_def.f:85-126).  All (total_zones) unless noted:
  * ionic/ionic_bar (11,total), Yion/Yion_bar (ncharged,total), Zion/Aion (ncharged).
  * Tc_cell/Tc_face (3,total): critical temperatures already evaluated by other_sf_get_results on the
- * host, or NULL to use the context's gap tables (sf_get_results). */
+ * host, or NULL to use the context's gap tables (sf_get_results).
+ * The copies are issued on two streams (what only the face pass needs overlaps the cell pass) and this call and
+ * dstar_batch_upload_evolve do not wait for them: PAGE-LOCKED host arrays must stay unchanged until the next
+ * synchronising call (dstar_batch_micro_tables, dstar_batch_evolve, any download); pageable arrays (what a Fortran
+ * caller passes) are staged by the driver before the call returns. */
 int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double* rho_bar, const double* P,
                                  const double* P_bar, const double* dm, const double* ionic,
                                  const double* ionic_bar, const double* Yion, const double* Yion_bar,
