@@ -119,11 +119,20 @@ void fill_host_consts(DsHostConsts& h) {
 template <bool FACE, int G>
 void launch_micro_g(int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
     const int grid = std::min(sms, (total + G - 1) / G);
+    const size_t dyn = (size_t)G * DS_YMAX * sizeof(double);   // per-group abundances (kernels_micro.cuh: s_Y)
+    static bool once = [] {   // static + dynamic shared memory exceed 48 KB: opt in
+        const int bytes = (int)((size_t)G * DS_YMAX * sizeof(double));
+        cudaFuncSetAttribute(ds_micro_kernel<true, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(ds_micro_kernel<false, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(ds_micro_kernel<false, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        return true;
+    }();
+    (void)once;
     if (FACE) {  // one plain pass (a.redo must be null)
-        ds_micro_kernel<true, G, false><<<grid, DS_NTAB * G, 0, s>>>(a, h, sf);
+        ds_micro_kernel<true, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
     } else {     // branch-free pass, then the plain pass over the zones it flagged (normally none)
-        ds_micro_kernel<false, G, true><<<grid, DS_NTAB * G, 0, s>>>(a, h, sf);
-        ds_micro_kernel<false, G, false><<<grid, DS_NTAB * G, 0, s>>>(a, h, sf);
+        ds_micro_kernel<false, G, true><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
+        ds_micro_kernel<false, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
     }
 }
 template <bool FACE>
@@ -541,7 +550,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = b->redo.p; a.redo_count = b->redo_count.p;
-            ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->sf);
+            ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
             CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
             { const char* e = std::getenv("DSTAR_FORCE_REDO"); a.force_redo = (e && e[0] == '1') ? 1 : 0; }  // test hook
             launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
@@ -559,7 +568,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             const int sms = c->prop.multiProcessorCount;
             a.redo = nullptr; a.redo_count = nullptr;
             CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
-            ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->sf);
+            ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
             launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());

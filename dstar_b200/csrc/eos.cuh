@@ -843,7 +843,7 @@ struct DsEosRes {
 // because of the DS_PHASE barriers inside).
 template <bool FAST>
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
-                            double logT, const DsComp& c, const DsZonePre& zp, int ncharged,
+                            double logT, const DsComp& c, const DsZonePre& zp, const DsHelmZone& hz, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
                             const DsIonZ* __restrict__ ionz, const double* __restrict__ Yion, double Tns, double chi,
                             DsEosRes& o, bool& bad,
@@ -860,7 +860,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     int ierr_h = 0;
     if (!(fabs(c.Yn - 1.0) <= (double)1.1920929e-07f)) {
         DsHelmOut he;
-        ierr_h = ds_helm_electron(helm, T, logT, rho, c.A / den(1.0 - c.Yn), c.Z, he);
+        ierr_h = ds_helm_electron(helm, T, logT, hz, he);   // hz: ds_helm_zone(helm, rho, A / (1 - Yn), Z)
         if (ierr_h == 0) {
             e.u = he.eele; e.p = he.pele; e.s = he.sele; e.f = e.u - T * e.s;
             e.cv = he.deept; e.dpr = rho * he.dpepd; e.dpt = T * he.dpept;

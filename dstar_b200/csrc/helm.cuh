@@ -102,49 +102,76 @@ struct DsHelmOut {
     double eele, pele, sele, deept, dpepd, dpept, etaele;
 };
 
+// Density-direction half of the interpolation: rho*Ye, its table cell and the 16 basis-function weights depend on
+// the zone only, not on T -- computed once per zone (ds_zone_aux_kernel) and shared by its 128 temperature lanes.
+struct DsHelmZone {
+    double ye, din;
+    int i0, err;   // err = -3: rho*Ye below the table
+    dsh::W6 sd, dsd;
+    dsh::W4 cd;
+};
+DS_D DsHelmZone ds_helm_zone(const DsHelmDev& h, double rho, double abar, double zbar) {
+    using namespace dsh;
+    DsHelmZone z{};
+    const double ytot1 = 1.0 / abar;
+    z.ye = __dmul_rn(ytot1, zbar);
+    double din = __dmul_rn(z.ye, rho);
+    z.err = (din < h.denlo) ? -3 : 0;
+    if (din > h.denhi) din = h.denhi;
+    z.din = din;
+    if (z.err) return z;
+    int iat = (int)((dsm::log10(din) - h.logdlo) * h.logdstpi) + 1;
+    iat = max(1, min(iat, h.imax - 1));
+    z.i0 = iat - 1;
+    const double di = __ldg(h.d + z.i0), di1 = __ldg(h.d + z.i0 + 1);
+    // helm_alloc.f:301-326 (same operations as the *_sav arrays)
+    const Sd dd = S(di1) - S(di);
+    const Sd dd2 = dd * dd;
+    const Sd ddi = S(__ddiv_rn(1.0, dd.v));
+    Sd xd = (S(din) - S(di)) * ddi;
+    if (xd.v < 0.0) xd.v = 0.0;
+    const Sd mxd = S(1.0) - xd;
+    z.sd = W6{psi0(xd), psi1(xd) * dd, psi2(xd) * dd2, psi0(mxd), -psi1(mxd) * dd, psi2(mxd) * dd2};
+    z.dsd = W6{dpsi0(xd) * ddi, dpsi1(xd), dpsi2(xd) * dd, -dpsi0(mxd) * ddi, dpsi1(mxd), -dpsi2(mxd) * dd};
+    z.cd = W4{xpsi0(xd), xpsi1(xd) * dd, xpsi0(mxd), -xpsi1(mxd) * dd};
+    return z;
+}
+
 // returns 0 ok, -1 non-positive entropy, -2 logT < 5 (blend region, never reached by NScool),
 // -3 rho*Ye below the table
-DS_D int ds_helm_electron(const DsHelmDev& h, double T, double logT, double rho, double abar,
-                          double zbar, DsHelmOut& o) {
+DS_D int ds_helm_electron(const DsHelmDev& h, double T, double logT, const DsHelmZone& hz, DsHelmOut& o) {
     using namespace dsh;
     o = DsHelmOut{0, 0, 0, 0, 0, 0, 0};
     if (!(logT >= 5.0)) return -2;
     double temp = T, logtemp = logT;
-    double ytot1 = 1.0 / abar;
-    double ye = __dmul_rn(ytot1, zbar);
-    double din = __dmul_rn(ye, rho);
+    const double ye = hz.ye, din = hz.din;
     if (temp < h.templo) { temp = h.templo; logtemp = dsm::log10(temp); }
-    if (din < h.denlo) return -3;
+    if (hz.err) return hz.err;
     if (temp > h.temphi) { temp = h.temphi; logtemp = h.logthi; }
-    if (din > h.denhi) din = h.denhi;
 
     int jat = (int)((logtemp - h.logtlo) * h.logtstpi) + 1;
     jat = max(1, min(jat, h.jmax - 1));
-    int iat = (int)((dsm::log10(din) - h.logdlo) * h.logdstpi) + 1;
-    iat = max(1, min(iat, h.imax - 1));
-    const int j0 = jat - 1, i0 = iat - 1;
+    const int j0 = jat - 1, i0 = hz.i0;
     const double* base = h.node + (size_t)DS_HELM_REC * ((size_t)i0 + (size_t)h.imax * j0);
     Corners q{base, base + DS_HELM_REC, base + (size_t)DS_HELM_REC * h.imax,
               base + (size_t)DS_HELM_REC * h.imax + DS_HELM_REC};
 
     const double tj = __ldg(h.t + j0), tj1 = __ldg(h.t + j0 + 1);
-    const double di = __ldg(h.d + i0), di1 = __ldg(h.d + i0 + 1);
     // helm_alloc.f:301-326 (same operations as the *_sav arrays)
-    const Sd dt = S(tj1) - S(tj), dd = S(di1) - S(di);
-    const Sd dt2 = dt * dt, dd2 = dd * dd;
-    const Sd dti = S(__ddiv_rn(1.0, dt.v)), ddi = S(__ddiv_rn(1.0, dd.v));
+    const Sd dt = S(tj1) - S(tj);
+    const Sd dt2 = dt * dt;
+    const Sd dti = S(__ddiv_rn(1.0, dt.v));
     const Sd dt2i = S(__ddiv_rn(1.0, dt2.v));
 
     Sd xt = (S(temp) - S(tj)) * dti;
-    Sd xd = (S(din) - S(di)) * ddi;
     if (xt.v < 0.0) xt.v = 0.0;
-    if (xd.v < 0.0) xd.v = 0.0;
-    const Sd mxt = S(1.0) - xt, mxd = S(1.0) - xd;
+    const Sd mxt = S(1.0) - xt;
+    const W6& sd = hz.sd;
+    const W6& dsd = hz.dsd;
+    const W4& cd = hz.cd;
 
     const W6 st{psi0(xt), psi1(xt) * dt, psi2(xt) * dt2, psi0(mxt), -psi1(mxt) * dt, psi2(mxt) * dt2};
-    const W6 sd{psi0(xd), psi1(xd) * dd, psi2(xd) * dd2, psi0(mxd), -psi1(mxd) * dd, psi2(mxd) * dd2};
     const W6 dst{dpsi0(xt) * dti, dpsi1(xt), dpsi2(xt) * dt, -dpsi0(mxt) * dti, dpsi1(mxt), -dpsi2(mxt) * dt};
-    const W6 dsd{dpsi0(xd) * ddi, dpsi1(xd), dpsi2(xd) * dd, -dpsi0(mxd) * ddi, dpsi1(mxd), -dpsi2(mxd) * dd};
     const W6 ddst{ddpsi0(xt) * dt2i, ddpsi1(xt) * dti, ddpsi2(xt), ddpsi0(mxt) * dt2i, -ddpsi1(mxt) * dti, ddpsi2(mxt)};
 
     const Sd free_ = h5(q, st, sd);
@@ -154,7 +181,6 @@ DS_D int ds_helm_electron(const DsHelmDev& h, double T, double logT, double rho,
     const Sd df_dt = h5(q, dst, dsd);
 
     const W4 ct{xpsi0(xt), xpsi1(xt) * dt, xpsi0(mxt), -xpsi1(mxt) * dt};
-    const W4 cd{xpsi0(xd), xpsi1(xd) * dd, xpsi0(mxd), -xpsi1(mxd) * dd};
     Sd dpepdd_in = h3(q, 9, ct, cd);
     if (dpepdd_in.v < 1.0e-30) dpepdd_in.v = 1.0e-30;
     const Sd etaele = h3(q, 13, ct, cd);

@@ -139,7 +139,9 @@ struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 mom
     double rho, chi, Tc[3];
 };
 static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
-constexpr int DS_AUX = 5 + (int)(sizeof(DsZonePre) / sizeof(double));   // rho, chi, Tc(3), then DsZonePre
+constexpr int DS_PRE = (int)(sizeof(DsZonePre) / sizeof(double)), DS_HZ = (int)(sizeof(DsHelmZone) / sizeof(double));
+constexpr int DS_AUX = 5 + DS_PRE + DS_HZ;   // rho, chi, Tc(3), then DsZonePre, then DsHelmZone (raw 8-byte words)
+static_assert(sizeof(DsHelmZone) % sizeof(double) == 0, "DsHelmZone is copied as 8-byte words");
 constexpr int DS_YMAX = 96;   // species kept in shared memory per group (more: read from global memory)
 constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each) are kept in shared memory
 
@@ -147,7 +149,7 @@ constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each)
 // fix-up, chi, the three critical temperatures): one thread per zone, once per pass, instead of one lane per group
 // doing three binary searches through HBM while the other 127 wait at the round's first barrier.
 template <bool FACE>
-__global__ void ds_zone_aux_kernel(DsMicroArgs a, DsSfDev sf) {
+__global__ void ds_zone_aux_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.total_zones) return;
     const int star = a.zone_star[g];
@@ -162,7 +164,9 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsSfDev sf) {
     double* o = a.aux + (size_t)DS_AUX * g;
     o[0] = rho; o[1] = chi; o[2] = Tc[0]; o[3] = Tc[1]; o[4] = Tc[2];
     const DsZonePre zp = ds_zone_pre(rho, c, chi);
-    for (int q = 0; q < DS_AUX - 5; ++q) o[5 + q] = reinterpret_cast<const double*>(&zp)[q];
+    for (int q = 0; q < DS_PRE; ++q) o[5 + q] = reinterpret_cast<const double*>(&zp)[q];
+    const DsHelmZone hz = ds_helm_zone(helm, rho, c.A / (1.0 - c.Yn), c.Z);   // as ds_eval_crust_eos passes them
+    for (int q = 0; q < DS_HZ; ++q) o[5 + DS_PRE + q] = reinterpret_cast<const double*>(&hz)[q];
 }
 
 template <bool FACE, int G, bool FAST>
@@ -171,10 +175,12 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
-    __shared__ double s_Y[G][DS_YMAX];
+    extern __shared__ double s_Ydyn[];   // G * DS_YMAX abundances (dynamic: the static 48 KB are used up)
+    double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_Ydyn);
     __shared__ unsigned char s_act[G][DS_YMAX];   // indices of the zone's species above the abundance threshold
     __shared__ int s_nact[G];
     __shared__ DsZonePre s_pre[G];
+    __shared__ DsHelmZone s_hz[G];
     __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
     __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
@@ -209,7 +215,9 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         // abundances -- independent loads, one memory round trip per round
         if (it < 11) reinterpret_cast<double*>(&s_zone[grp])[it] = ((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g)[it];
         else if (it < 16) reinterpret_cast<double*>(&s_zone[grp])[it] = a.aux[(size_t)DS_AUX * g + (it - 11)];
-        else if (it < 11 + DS_AUX) reinterpret_cast<double*>(&s_pre[grp])[it - 16] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+        else if (it < 16 + DS_PRE) reinterpret_cast<double*>(&s_pre[grp])[it - 16] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+        else if (it < 16 + DS_PRE + DS_HZ)
+            reinterpret_cast<double*>(&s_hz[grp])[it - 16 - DS_PRE] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
         if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
@@ -223,6 +231,10 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         }
         const DsComp& c = s_zone[grp].c;
         const DsZonePre& zp = s_pre[grp];
+        // cells pull the 16 density weights into registers once (read through shared memory inside the biquintic
+        // sums the cell pass is 25 % slower); the face pass, which uses only two of the sums, reads them in place
+        const DsHelmZone hz_regs = FACE ? DsHelmZone{} : s_hz[grp];
+        const DsHelmZone& hz = FACE ? s_hz[grp] : hz_regs;
         const double& rho = s_zone[grp].rho;
         const double& chi = s_zone[grp].chi;
         const double* Tc = s_zone[grp].Tc;
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             DsEosRes r;
             const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
             bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, zp, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
+            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, zp, hz, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
                                     (!FACE && a.ncharged <= DS_YMAX) ? s_act[grp] : nullptr, FACE ? 0 : s_nact[grp]);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
@@ -303,12 +315,13 @@ __global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
     DsEosRes r;
     bool bad = false;
     const DsZonePre zp = ds_zone_pre(rho, c, chi);
+    const DsHelmZone hz = ds_helm_zone(helm, rho, c.A / (1.0 - c.Yn), c.Z);
     double* cp = (a.comps && live) ? a.comps + (size_t)28 * k : nullptr;
-    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, zp, a.ncharged, a.Zion, a.Aion, a.ionz,
+    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, zp, hz, a.ncharged, a.Zion, a.Aion, a.ionz,
                             a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, bad, cp);
     if (__syncthreads_or(bad)) {
         bool unused = false;
-        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, zp, a.ncharged, a.Zion, a.Aion, a.ionz,
+        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, zp, hz, a.ncharged, a.Zion, a.Aion, a.ionz,
                                  a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, unused, cp);
     }
     if (!live) return;
