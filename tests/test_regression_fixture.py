@@ -66,3 +66,32 @@ def test_cuda_reproduces_stored_tables(fx):
         assert out["rho_bar1"][0] == fx["rho_bar"][0]
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_species", [40, 120])
+def test_large_networks_take_the_global_memory_paths(fx, n_species):
+    """Networks larger than the shared-memory budgets of the coefficient pass (20 species for the per-species
+    constants, 96 for the abundances and the active-species list): padding the fixture's 18-species network with
+    zero-abundance nuclides must not change a single bit of the tables."""
+    import dstar_b200 as ds
+    nz = int(fx["nz"]); nch = int(fx["ncharged"])
+    pad = n_species - nch
+    Zion = np.concatenate([fx["Zion"], 28.0 + (np.arange(pad) % 10)])
+    Aion = np.concatenate([fx["Aion"], 60.0 + np.arange(pad)])
+
+    def widen(Y):
+        out = np.zeros((nz, n_species))
+        out[:, :nch] = Y.reshape(nz, nch)
+        return out
+    ctx = ds.Context(0, gaps=("ns", "sfb03", "t72"))
+    try:
+        b = ds.Batch(ctx, np.array([0, nz]), n_species)
+        b.upload_structure(fx["rho"], fx["rho_bar"].copy(), fx["P"], fx["P_bar"], fx["dm"], fx["ionic"], fx["ionic_bar"],
+                           widen(fx["Yion"]), widen(fx["Yion_bar"]), Zion, Aion)
+        b.micro_tables(ds.MicroCtrl.defaults(), 3)
+        out = b.download_tables()
+        for k in TABS:
+            assert np.array_equal(out[k].view(np.uint64), fx["gpu_" + k].view(np.uint64)), k
+    finally:
+        ctx.close()
