@@ -384,16 +384,32 @@ DS_D double sPh(double nn, double nion, double temperature, const DsComp& c) {
 
 // eval_conductivity.f:6-143.  lambda_imp: the zone's precomputed impurity integral, or NaN to have
 // it evaluated here; imp_ierr its status.
+// T-independent part of the conductivity of a zone (evaluated once per zone by ds_zone_aux_kernel<FACE>): log10 rho,
+// the electron density / Fermi wavenumber / Fermi energy chain (a cube root and a square root) and the whole
+// electron-impurity collision frequency, which depends on (kF, Z, A, Q) only (electron_conductivity.f:174-222).
+struct DsCondPre {
+    double lgrho, ne, kF, xF, eF, nu_eQ;
+};
+DS_D DsCondPre ds_cond_pre(const DsCondCtrl& rq, double rho, const DsComp& c) {
+    DsCondPre p;
+    p.lgrho = dsm::log10(rho);
+    p.ne = rho / amu * c.Ye;
+    p.kF = dsm::pow(threepisquare * p.ne, onethird);
+    p.xF = hbar * p.kF / Melectron / clight;
+    p.eF = sqrt(1.0 + p.xF * p.xF);
+    p.nu_eQ = (rq.eQ_fmla == 2) ? eQ_page(p.kF, c.Z, c.A, c.Q) : eQ(p.kF, c.Z, c.A, c.Q);
+    return p;
+}
+
 DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi, double Gamma,
-                          double eta, double mu_e, const DsComp& c, double Tns, double lambda_imp,
+                          double eta, double mu_e, const DsComp& c, const DsCondPre& cp, double Tns, double lambda_imp,
                           int imp_ierr, DsCond& kap) {
     const double eQ_threshold = 1.0e-8, sf_reduction_threshold = 1.0e-10;
     kap = DsCond{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const double lgrho = dsm::log10(rho);
-    const double ne = rho / amu * c.Ye;
-    const double kF = dsm::pow(threepisquare * ne, onethird);
-    const double xF = hbar * kF / Melectron / clight;
-    const double eF = sqrt(1.0 + xF * xF);
+    const double lgrho = cp.lgrho;
+    const double ne = cp.ne;
+    const double kF = cp.kF;
+    const double eF = cp.eF;
     const double Gamma_e = Gamma / c.Z53;
     const double kappa_e_pre = onethird * (pi * pi) * (boltzmann * boltzmann) * T * ne / Melectron / eF;
     double nu = 0.0, nu_c;
@@ -407,7 +423,7 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
     nu = nu + nu_c;
     if (nu_c > dbl_tiny) kap.ei = kappa_e_pre / nu_c;
     DS_PHASE();
-    nu_c = (rq.eQ_fmla == 2) ? eQ_page(kF, c.Z, c.A, c.Q) : eQ(kF, c.Z, c.A, c.Q);
+    nu_c = cp.nu_eQ;   // eQ / eQ_page(kF, Z, A, Q): zone-level, see DsCondPre
     nu = nu + nu_c;
     if (c.Q > eQ_threshold) kap.eQ = kappa_e_pre / nu_c;
     kap.electron_total = kappa_e_pre / nu;

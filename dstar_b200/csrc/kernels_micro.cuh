@@ -140,7 +140,8 @@ struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 mom
 };
 static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
 constexpr int DS_PRE = (int)(sizeof(DsZonePre) / sizeof(double)), DS_HZ = (int)(sizeof(DsHelmZone) / sizeof(double));
-constexpr int DS_AUX = 5 + DS_PRE + DS_HZ;   // rho, chi, Tc(3), then DsZonePre, then DsHelmZone (raw 8-byte words)
+constexpr int DS_CP = (int)(sizeof(dsk::DsCondPre) / sizeof(double));
+constexpr int DS_AUX = 5 + DS_PRE + DS_HZ + DS_CP;   // rho, chi, Tc(3), DsZonePre, DsHelmZone (raw 8-byte words), DsCondPre (faces)
 static_assert(sizeof(DsHelmZone) % sizeof(double) == 0, "DsHelmZone is copied as 8-byte words");
 constexpr int DS_YMAX = 96;   // species kept in shared memory per group (more: read from global memory)
 constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each) are kept in shared memory
@@ -167,6 +168,10 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     for (int q = 0; q < DS_PRE; ++q) o[5 + q] = reinterpret_cast<const double*>(&zp)[q];
     const DsHelmZone hz = ds_helm_zone(helm, rho, c.A / (1.0 - c.Yn), c.Z);   // as ds_eval_crust_eos passes them
     for (int q = 0; q < DS_HZ; ++q) o[5 + DS_PRE + q] = reinterpret_cast<const double*>(&hz)[q];
+    if (FACE) {
+        const dsk::DsCondPre cp = dsk::ds_cond_pre(a.cond, rho, c);
+        for (int q = 0; q < DS_CP; ++q) o[5 + DS_PRE + DS_HZ + q] = reinterpret_cast<const double*>(&cp)[q];
+    }
 }
 
 template <bool FACE, int G, bool FAST>
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     __shared__ int s_nact[G];
     __shared__ DsZonePre s_pre[G];
     __shared__ DsHelmZone s_hz[G];
+    __shared__ dsk::DsCondPre s_cp[FACE ? G : 1];
     __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
     __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
@@ -218,6 +224,8 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         else if (it < 16 + DS_PRE) reinterpret_cast<double*>(&s_pre[grp])[it - 16] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         else if (it < 16 + DS_PRE + DS_HZ)
             reinterpret_cast<double*>(&s_hz[grp])[it - 16 - DS_PRE] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+        else if (FACE && it < 16 + DS_PRE + DS_HZ + DS_CP)
+            reinterpret_cast<double*>(&s_cp[grp])[it - 16 - DS_PRE - DS_HZ] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
         if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                 s_v[grp][2][it] = lnenu;
             } else {
                 DsCond K;
-                dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, Tc[1], s_lam[grp],
+                dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, s_cp[FACE ? grp : 0], Tc[1], s_lam[grp],
                                      s_lam_ierr[grp], K);
                 s_v[grp][0][it] = dsm::log(K.total);
             }
@@ -367,8 +375,9 @@ __global__ void ds_eval_cond_kernel(DsEvalCondArgs a) {
     const bool live = k < a.n;
     if (!live) k = a.n - 1;
     DsCond c;
-    dsk::ds_conductivity(a.cond, a.rho[k], a.T[k], a.chi[k], a.Gamma[k], a.eta[k], a.mu_e[k],
-                         ds_load_comp(a.ionic + (size_t)11 * k), a.Tns[k], nan(""), 0, c);
+    const DsComp cc = ds_load_comp(a.ionic + (size_t)11 * k);
+    dsk::ds_conductivity(a.cond, a.rho[k], a.T[k], a.chi[k], a.Gamma[k], a.eta[k], a.mu_e[k], cc,
+                         dsk::ds_cond_pre(a.cond, a.rho[k], cc), a.Tns[k], nan(""), 0, c);
     if (!live) return;
     double* o = a.K + (size_t)10 * k;
     o[0] = c.total; o[1] = c.ee; o[2] = c.ei; o[3] = c.eQ; o[4] = c.sf; o[5] = c.nQ; o[6] = c.np; o[7] = c.kap;
