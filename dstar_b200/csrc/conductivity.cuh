@@ -50,35 +50,52 @@ DS_D double ee_PCY(double ne, double T) {
     return eefac * (plasma_theta * plasma_theta) * J / eF / be3;
 }
 
-DS_D double ee_SY06(double ne, double T) {
-    double nu_pre = 36.0 * (finestructure * finestructure) * (hbar * hbar) * clight / pi / boltzmann / Melectron;
-    double Tp_pre = ds_hc.Tp_pre;
-    double kF = dsm::pow(threepisquare * ne, onethird);
-    double xF = hbar * kF / Melectron / clight;
-    double eF = sqrt(1.0 + xF * xF);
-    double u = xF / eF;
-    double Tp = Tp_pre * sqrt(ne / eF);
-    double theta = (double)sqrtf(3.0f) * Tp / T;
-    double u2 = u * u, u3 = u * u * u, u4 = dsd::ipow<4>(u);
-    double tu = theta * u;
-    double At = 20.0 + 450.0 * u3;
-    double Ct1 = DS_R4(0.05067) + DS_R4(0.03216) * u2;
-    double Ct2 = DS_R4(0.0254) + DS_R4(0.04127) * u4;
-    double Ct = At * dsm::exp(Ct1 / Ct2);
-    double Alt = DS_R4(12.2) + DS_R4(25.2) * u3;
-    double Blt = 1.0 - 0.75 * u;
-    double Clt1 = DS_R4(0.123636) + DS_R4(0.016234) * u2;
-    double Clt2 = DS_R4(0.0762) + DS_R4(0.05714) * u4;
-    double Clt = Alt * dsm::exp(Clt1 / Clt2);
-    double Il = (1.0 / u) * (DS_R4(0.1587) - DS_R4(0.02538) / (1.0 + DS_R4(0.0435) * theta)) *
-                dsm::log(1.0 + DS_R4(128.56) / theta / (DS_R4(37.1) + theta * (DS_R4(10.83) + theta)));
-    double It = u3 * (DS_R4(2.404) / Ct + (Ct2 - DS_R4(2.404) / Ct) / (1.0 + DS_R4(0.1) * tu)) *
-                dsm::log(1.0 + Ct / tu / (At + tu));
-    double Ilt = u * (DS_R4(18.52) * u2 / Clt + (Clt2 - DS_R4(18.2) * u2 / Clt) / (1.0 + DS_R4(0.1558) * dsm::pow(theta, Blt))) *
-                 dsm::log(1.0 + Clt / (Alt * theta + DS_R4(10.83) * (tu * tu) + dsm::pow(tu, (double)(8.0f / 3.0f))));
-    double I = Il + It + Ilt;
-    return nu_pre * ne * I / eF / T;
+// ee_SY06 (electron_conductivity.f:44-92), split into the part that depends on the electron density only and the
+// part that depends on T: the first holds a cube root, two square roots, two exponentials and ~10 divisions and is
+// evaluated once per zone (DsCondPre); same operations in the same order as the one-piece form, so same bits.
+struct DsEePre {
+    double nupre_ne, eF, u, u2, u3, Tp, At, Ct2, Ct, c2404, Alt, Blt, Clt2, Clt, c1852, c182, inv_u;
+};
+DS_D DsEePre ee_SY06_pre(double ne) {
+    DsEePre p;
+    const double nu_pre = 36.0 * (finestructure * finestructure) * (hbar * hbar) * clight / pi / boltzmann / Melectron;
+    const double Tp_pre = ds_hc.Tp_pre;
+    const double kF = dsm::pow(threepisquare * ne, onethird);
+    const double xF = hbar * kF / Melectron / clight;
+    p.eF = sqrt(1.0 + xF * xF);
+    p.u = xF / p.eF;
+    p.Tp = Tp_pre * sqrt(ne / p.eF);
+    p.u2 = p.u * p.u; p.u3 = p.u * p.u * p.u;
+    const double u4 = dsd::ipow<4>(p.u);
+    p.At = 20.0 + 450.0 * p.u3;
+    const double Ct1 = DS_R4(0.05067) + DS_R4(0.03216) * p.u2;
+    p.Ct2 = DS_R4(0.0254) + DS_R4(0.04127) * u4;
+    p.Ct = p.At * dsm::exp(Ct1 / p.Ct2);
+    p.c2404 = DS_R4(2.404) / p.Ct;
+    p.Alt = DS_R4(12.2) + DS_R4(25.2) * p.u3;
+    p.Blt = 1.0 - 0.75 * p.u;
+    const double Clt1 = DS_R4(0.123636) + DS_R4(0.016234) * p.u2;
+    p.Clt2 = DS_R4(0.0762) + DS_R4(0.05714) * u4;
+    p.Clt = p.Alt * dsm::exp(Clt1 / p.Clt2);
+    p.c1852 = DS_R4(18.52) * p.u2 / p.Clt;
+    p.c182 = DS_R4(18.2) * p.u2 / p.Clt;
+    p.inv_u = 1.0 / p.u;
+    p.nupre_ne = nu_pre * ne;
+    return p;
 }
+DS_D double ee_SY06_T(const DsEePre& p, double T) {
+    const double theta = (double)sqrtf(3.0f) * p.Tp / T;
+    const double tu = theta * p.u;
+    double Il = p.inv_u * (DS_R4(0.1587) - DS_R4(0.02538) / (1.0 + DS_R4(0.0435) * theta)) *
+                dsm::log(1.0 + DS_R4(128.56) / theta / (DS_R4(37.1) + theta * (DS_R4(10.83) + theta)));
+    double It = p.u3 * (p.c2404 + (p.Ct2 - p.c2404) / (1.0 + DS_R4(0.1) * tu)) *
+                dsm::log(1.0 + p.Ct / tu / (p.At + tu));
+    double Ilt = p.u * (p.c1852 + (p.Clt2 - p.c182) / (1.0 + DS_R4(0.1558) * dsm::pow(theta, p.Blt))) *
+                 dsm::log(1.0 + p.Clt / (p.Alt * theta + DS_R4(10.83) * (tu * tu) + dsm::pow(tu, (double)(8.0f / 3.0f))));
+    double I = Il + It + Ilt;
+    return p.nupre_ne * I / p.eF / T;
+}
+DS_D double ee_SY06(double ne, double T) { return ee_SY06_T(ee_SY06_pre(ne), T); }
 
 DS_D double eone(double z) {
     const double a0 = DS_R4(0.1397), a1 = DS_R4(0.5772), a2 = DS_R4(2.2757);
@@ -86,51 +103,76 @@ DS_D double eone(double z) {
     return dsm::exp(-z4 / (z3 + a0)) * (dsm::log(1.0 + 1.0 / z) - a1 / (1.0 + a2 * z2));
 }
 
-DS_D double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z2, double Z53, double A) {
-    (void)Ye;
-    const double um1 = DS_R4(2.8), um2 = DS_R4(12.973);
+// eion (electron_conductivity.f:94-172), split the same way: what depends on (kF, composition) only -- a sixth
+// root, a square root, a logarithm, ~10 divisions -- once per zone; what depends on Gamma_e and eta per temperature.
+struct DsEiPre {
+    double kF2, v2, s, eta02, aei2, beta, gsfac, gk01, fourkF2, w1, w_num, log1, sp1, s_sp1, log2, inv_sp1, r2s, z2a,
+        eifac_eF;
+};
+DS_D DsEiPre eion_pre(double kF, double Z, double Z2, double A) {
+    DsEiPre p;
+    const double um2 = DS_R4(12.973);
     const double onesixth = (double)(1.0f / 6.0f), fourthird = 4.0 * onethird;
-    double sw_max = dbl_max_log;
-    double electroncompton = hbar / Melectron / clight;
-    double eifac = fourthird * clight * (finestructure * finestructure) / electroncompton / pi;
-    double kF2 = kF * kF;
-    double x = electroncompton * kF;
-    double eF = sqrt(1.0 + x * x);
-    double v = x / eF;
-    double v2 = v * v;
+    const double electroncompton = hbar / Melectron / clight;
+    const double eifac = fourthird * clight * (finestructure * finestructure) / electroncompton / pi;
+    p.kF2 = kF * kF;
+    const double x = electroncompton * kF;
+    const double eF = sqrt(1.0 + x * x);
+    const double v = x / eF;
+    p.v2 = v * v;
+    p.s = finestructure / pi / v;
+    p.eta02 = dsd::ipow<2>(DS_R4(0.19) / dsm::pow(Z, onesixth));
+    const double aei = ds_hc.aei_fac * kF;
+    p.aei2 = aei * aei;
+    p.beta = pi * finestructure * Z * v;
+    p.gsfac = 1.0 + DS_R4(0.122) * (p.beta * p.beta);
+    const double Gk1 = 1.0 + p.beta * dsd::ipow<3>(v);
+    const double GkZ = 1.0 - 1.0 / Z;
+    p.gk01 = DS_R4(0.0105) * GkZ * Gk1;
+    p.fourkF2 = 4.0 * p.kF2;
+    p.w1 = 1.0 + onethird * p.beta;
+    p.w_num = 4.0 * um2 * p.kF2;
+    p.log1 = dsm::log(1.0 + 1.0 / p.s);
+    p.sp1 = p.s + 1.0;
+    p.s_sp1 = p.s / (1.0 + p.s);
+    p.log2 = dsm::log((p.s + 1.0) / p.s);
+    p.inv_sp1 = 1.0 / (p.s + 1.0);
+    p.r2s = (2.0 * p.s + 1.0) / (2.0 * p.s + 2.0);
+    p.z2a = Z2 / A;
+    p.eifac_eF = eifac * eF;
+    return p;
+}
+DS_D double eion_T(const DsEiPre& p, double Gamma_e, double eta, double Z, double Z2, double Z53, double A) {
+    const double um1 = DS_R4(2.8);
+    const double sw_max = dbl_max_log;
+    const double s = p.s;
     double Gamma = Gamma_e * Z53;
-    double s = finestructure / pi / v;
-    double kTF2 = 4.0 * s * kF2;
-    double eta02 = dsd::ipow<2>(DS_R4(0.19) / dsm::pow(Z, onesixth));
-    double aei = ds_hc.aei_fac * kF;
-    double qD2 = 3.0 * Gamma_e * (aei * aei) * Z2 / Z;
-    double beta = pi * finestructure * Z * v;
-    double qi2 = qD2 * (1.0 + DS_R4(0.06) * Gamma) * dsm::exp(-sqrt(Gamma));
-    double qs2 = (qi2 + kTF2) * dsm::exp(-beta);
-    (void)qs2;
-    double Gs = eta / sqrt(eta * eta + eta02) * (1.0 + DS_R4(0.122) * (beta * beta));
+    (void)Gamma;
+    double qD2 = 3.0 * Gamma_e * p.aei2 * Z2 / Z;
+    double Gs = eta / sqrt(eta * eta + p.eta02) * p.gsfac;
     double Gk0 = 1.0 / dsm::pow(eta * eta + DS_R4(0.0081), 1.5);
-    double Gk1 = 1.0 + beta * dsd::ipow<3>(v);
-    double GkZ = 1.0 - 1.0 / Z;
-    double Gk = Gs + DS_R4(0.0105) * GkZ * Gk1 * Gk0 * eta;
-    double a0 = 4.0 * kF2 / qD2 / eta;
+    double Gk = Gs + p.gk01 * Gk0 * eta;
+    double a0 = p.fourkF2 / qD2 / eta;
     double D1 = dsm::exp(DS_R4(-9.1) * eta);
     double D = dsm::exp(-a0 * um1 * D1 * 0.25);
-    double w1 = 1.0 + onethird * beta;
-    double w = 4.0 * um2 * kF2 / qD2 * w1;
+    double w = p.w_num / qD2 * p.w1;
     double sw = s * w;
     double L1, L2;
     if (sw < sw_max) {
         double fac = dsm::exp(sw) * (eone(sw) - eone(sw + w));
-        L1 = 0.5 * (dsm::log(1.0 + 1.0 / s) + (1.0 - dsm::exp(-w)) * s / (s + 1.0) - fac * (1.0 + sw));
+        L1 = 0.5 * (p.log1 + (1.0 - dsm::exp(-w)) * s / p.sp1 - fac * (1.0 + sw));
         L2 = 0.5 * (1.0 - (1.0 - dsm::exp(-w)) / w +
-                    s * (s / (1.0 + s) * (1.0 - dsm::exp(-w)) - 2.0 * dsm::log(1.0 + 1.0 / s) + fac * (2.0 + sw)));
+                    s * (p.s_sp1 * (1.0 - dsm::exp(-w)) - 2.0 * p.log1 + fac * (2.0 + sw)));
     } else {
-        L1 = 0.5 * (dsm::log((s + 1.0) / s) - 1.0 / (s + 1.0));
-        L2 = (2.0 * s + 1.0) / (2.0 * s + 2.0) - s * dsm::log((s + 1.0) / s);
+        L1 = 0.5 * (p.log2 - p.inv_sp1);
+        L2 = p.r2s - s * p.log2;
     }
-    double Lei = (Z2 / A) * (L1 - v2 * L2) * Gk * D;
-    return eifac * eF * Lei * A / Z;
+    double Lei = p.z2a * (L1 - p.v2 * L2) * Gk * D;
+    return p.eifac_eF * Lei * A / Z;
+}
+DS_D double eion(double kF, double Gamma_e, double eta, double Ye, double Z, double Z2, double Z53, double A) {
+    (void)Ye;
+    return eion_T(eion_pre(kF, Z, Z2, A), Gamma_e, eta, Z, Z2, Z53, A);
 }
 
 DS_D double eQ(double kF, double Z, double A, double Q) {
@@ -389,6 +431,8 @@ DS_D double sPh(double nn, double nion, double temperature, const DsComp& c) {
 // electron-impurity collision frequency, which depends on (kF, Z, A, Q) only (electron_conductivity.f:174-222).
 struct DsCondPre {
     double lgrho, ne, kF, xF, eF, nu_eQ;
+    DsEePre ee;   // ee_SY06, density part
+    DsEiPre ei;   // eion, (kF, composition) part
 };
 DS_D DsCondPre ds_cond_pre(const DsCondCtrl& rq, double rho, const DsComp& c) {
     DsCondPre p;
@@ -398,6 +442,8 @@ DS_D DsCondPre ds_cond_pre(const DsCondCtrl& rq, double rho, const DsComp& c) {
     p.xF = hbar * p.kF / Melectron / clight;
     p.eF = sqrt(1.0 + p.xF * p.xF);
     p.nu_eQ = (rq.eQ_fmla == 2) ? eQ_page(p.kF, c.Z, c.A, c.Q) : eQ(p.kF, c.Z, c.A, c.Q);
+    p.ee = ee_SY06_pre(p.ne);
+    p.ei = eion_pre(p.kF, c.Z, c.Z2, c.A);
     return p;
 }
 
@@ -415,11 +461,11 @@ DS_D void ds_conductivity(const DsCondCtrl& rq, double rho, double T, double chi
     double nu = 0.0, nu_c;
 
     DS_PHASE();
-    nu_c = (rq.ee_fmla == 2) ? ee_PCY(ne, T) : ee_SY06(ne, T);
+    nu_c = (rq.ee_fmla == 2) ? ee_PCY(ne, T) : ee_SY06_T(cp.ee, T);
     nu = nu + nu_c;
     DS_PHASE();
     if (nu_c > dbl_tiny) kap.ee = kappa_e_pre / nu_c;
-    nu_c = eion(kF, Gamma_e, eta, c.Ye, c.Z, c.Z2, c.Z53, c.A);
+    nu_c = eion_T(cp.ei, Gamma_e, eta, c.Z, c.Z2, c.Z53, c.A);
     nu = nu + nu_c;
     if (nu_c > dbl_tiny) kap.ei = kappa_e_pre / nu_c;
     DS_PHASE();
