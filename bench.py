@@ -331,11 +331,11 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # DRAM bytes of one cell-pass launch from the committed ncu --set full capture of this very configuration
-    # (profiles/r01d_ncu_full_summary.md, r01i table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
+    # (profiles/r01d_ncu_full_summary.md, r01j table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
     traffic = 6.09e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
     roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>", "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                "traffic_note": "bytes per launch, ncu capture r01i (mostly register-spill frames cycling through L2); "
+                "traffic_note": "bytes per launch, ncu capture r01j (mostly register-spill frames cycling through L2); "
                                 "algorithmic bytes per launch %.3g" % alg_bytes,
                 "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
                                "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
