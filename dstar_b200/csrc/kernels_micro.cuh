@@ -200,7 +200,12 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     const double* Zn = net_in_smem ? s_ZA[0] : a.Zion;
     const double* An = net_in_smem ? s_ZA[1] : a.Aion;
     const DsIonZ* ionz = ionz_in_smem ? s_ionz : a.ionz;
-    const double T = a.tab_T[it], lgT = a.tab_lgT[it];
+    // Which 32-knot block a warp of the group works on is rotated by the group index: the warp whose knots straddle
+    // the melting line (it runs both ion branches) sits at a similar temperature in most zones, i.e. would be the
+    // same warp number in every group -- and warp number mod 4 is the SM sub-partition.  The rotation spreads those
+    // double-work warps over the four sub-partitions.  Knots stay contiguous within a warp.
+    const int kn = ((((it >> 5) + grp) & 3) << 5) | (it & 31);
+    const double T = a.tab_T[kn], lgT = a.tab_lgT[kn];
     // second pass (FAST = false with a redo list): the work items are the list entries, densely packed
     const bool redo_pass = !FAST && a.redo != nullptr;
     const int n_items = redo_pass ? *a.redo_count : a.total_zones;
@@ -264,9 +269,9 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                                     (!FACE && a.ncharged <= DS_YMAX) ? s_act[grp] : nullptr, FACE ? 0 : s_nact[grp]);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
-                s_v[grp][0][it] = dsm::log(r.Cp);
-                s_v[grp][1][it] = dsm::log(r.Gamma);
-                if (on && iz == 0 && it == 0)  // create_model.f:367-369
+                s_v[grp][0][kn] = dsm::log(r.Cp);
+                s_v[grp][1][kn] = dsm::log(r.Gamma);
+                if (on && iz == 0 && kn == 0)  // create_model.f:367-369
                     a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
                 DsNeutrino eps;
                 dsn::ds_crust_neutrino<FAST>(rho, T, c, zp, chi, Tc[1], a.nu_channels, eps, bad);
@@ -276,23 +281,23 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
                         lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
                                                      dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
                 }
-                s_v[grp][2][it] = lnenu;
+                s_v[grp][2][kn] = lnenu;
             } else {
                 DsCond K;
                 dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, s_cp[FACE ? grp : 0], Tc[1], s_lam[grp],
                                      s_lam_ierr[grp], K);
-                s_v[grp][0][it] = dsm::log(K.total);
+                s_v[grp][0][kn] = dsm::log(K.total);
             }
             if (FAST && bad) s_bad[grp] = 1;
         }
         __syncthreads();
         const size_t ob = (size_t)4 * DS_NTAB * g;
         if (!FACE) {
-            ds_group_interp_pm(on, it, s_h, s_v[grp][2], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
-            ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
-            ds_group_interp_pm(on, it, s_h, s_v[grp][1], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][2], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][1], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
         } else {
-            ds_group_interp_pm(on, it, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
         }
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
         if (FAST && on && it == 0 && (s_bad[grp] | a.force_redo)) a.redo[atomicAdd(a.redo_count, 1)] = g;
