@@ -86,9 +86,11 @@ struct dstar_batch {
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
     DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // ordering between the two streams: face inputs / evolve inputs uploaded (copy stream), last compute issued (main)
-    cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr;
+    cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr, ev_cell_in = nullptr;
+    char* h_stage = nullptr;   // pinned staging block for the small result arrays (download_results)
+    size_t stage_bytes = 0;
     double ms[3] = {0, 0, 0};
     int launches = 0;
 };
@@ -431,9 +433,11 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(b->redo.alloc(b->total)); CK(b->redo_count.alloc(1));
     CK(b->rho_bar1.alloc(n_star));
     CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
+    CK(cudaEventCreate(&b->ev2)); CK(cudaEventCreate(&b->ev3));
     CK(cudaEventCreateWithFlags(&b->ev_face_in, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_evolve_in, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_busy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_cell_in, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(st));
     *out = b;
     return DSTAR_OK;
@@ -446,8 +450,12 @@ void dstar_batch_destroy(dstar_batch* b) {
     if (b->ev_face_in) cudaEventDestroy(b->ev_face_in);
     if (b->ev_evolve_in) cudaEventDestroy(b->ev_evolve_in);
     if (b->ev_busy) cudaEventDestroy(b->ev_busy);
+    if (b->ev_cell_in) cudaEventDestroy(b->ev_cell_in);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev2) cudaEventDestroy(b->ev2);
+    if (b->ev3) cudaEventDestroy(b->ev3);
     delete b;
 }
 
@@ -478,6 +486,10 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
     b->h_rb1.resize(b->n_star);
     for (int i = 0; i < b->n_star; ++i) b->h_rb1[i] = rho_bar[b->h_zone_offset[i]];
     CK(b->rho_bar1.upload(b->h_rb1.data(), b->n_star, s));
+    // the copy stream starts only when the cell inputs have landed: copies of both streams share the host link, and
+    // interleaved they delayed the start of the cell pass by ~0.4 ms (256 stars); now they run under the cell kernel
+    CK(cudaEventRecord(b->ev_cell_in, s));
+    CK(cudaStreamWaitEvent(cs, b->ev_cell_in, 0));
     CK(b->rho_bar.upload(rho_bar, n, cs)); CK(b->ionic_bar.upload(ionic_bar, 11 * n, cs));
     CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, cs));
     if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, cs));
@@ -557,13 +569,11 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(b->ev1, s));
-        CK(cudaEventSynchronize(b->ev1));
-        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[0] = ms;
+        CK(cudaEventRecord(b->ev1, s));   // read back after the face pass has been queued: no idle gap between them
         ++b->launches;
     }
     if (which & 2) {
-        CK(cudaEventRecord(b->ev0, s));
+        CK(cudaEventRecord(b->ev2, s));
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = nullptr; a.redo_count = nullptr;
@@ -572,10 +582,14 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(b->ev1, s));
-        CK(cudaEventSynchronize(b->ev1));
-        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[1] = ms;
+        CK(cudaEventRecord(b->ev3, s));
+        CK(cudaEventSynchronize(b->ev3));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev2, b->ev3)); b->ms[1] = ms;
         ++b->launches;
+    }
+    if (which & 1) {
+        CK(cudaEventSynchronize(b->ev1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[0] = ms;
     }
     CK(cudaEventRecord(b->ev_busy, s));
     b->have_tables = true;
@@ -760,18 +774,37 @@ int dstar_batch_download_results(dstar_batch* b, double* t_monitor, double* Teff
     CK(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
     const size_t ns = b->n_star, ne = b->n_epoch;
-    if (t_monitor) CK(b->t_mon.download(t_monitor, ne * ns, s));
-    if (Teff_monitor) CK(b->Teff_mon.download(Teff_monitor, ne * ns, s));
-    if (Qb_monitor) CK(b->Qb_mon.download(Qb_monitor, ne * ns, s));
-    if (idid) CK(b->idid.download(idid, ne * ns, s));
-    if (counters) CK(b->counters.download(counters, 7 * ns, s));
+    // The monitors are a few KB each: ten copies into pageable caller memory cost a driver round trip each.  They go
+    // through one pinned staging block instead (async copies, one synchronisation, then plain memcpy to the caller).
+    struct Item { void* dst; const void* src; size_t bytes; };
+    const Item items[] = {
+        {t_monitor, b->t_mon.p, ne * ns * sizeof(double)}, {Teff_monitor, b->Teff_mon.p, ne * ns * sizeof(double)},
+        {Qb_monitor, b->Qb_mon.p, ne * ns * sizeof(double)}, {idid, b->idid.p, ne * ns * sizeof(int32_t)},
+        {counters, b->counters.p, 7 * ns * sizeof(int32_t)}, {Teff, b->Teff.p, ns * sizeof(double)},
+        {Lsurf, b->Lsurf.p, ns * sizeof(double)}, {dt, b->dt.p, ns * sizeof(double)},
+        {tsec, b->tsec.p, ns * sizeof(double)}, {model, b->model.p, ns * sizeof(int32_t)}};
+    size_t need = 0;
+    for (const Item& it : items) if (it.dst) need += (it.bytes + 15) & ~(size_t)15;
+    if (need > b->stage_bytes) {
+        if (b->h_stage) cudaFreeHost(b->h_stage);
+        b->h_stage = nullptr; b->stage_bytes = 0;
+        CK(cudaMallocHost(&b->h_stage, need));
+        b->stage_bytes = need;
+    }
+    size_t off = 0;
+    for (const Item& it : items) {
+        if (!it.dst) continue;
+        CK(cudaMemcpyAsync(b->h_stage + off, it.src, it.bytes, cudaMemcpyDeviceToHost, s));
+        off += (it.bytes + 15) & ~(size_t)15;
+    }
     if (lnT) CK(b->lnT.download(lnT, b->total, s));
-    if (Teff) CK(b->Teff.download(Teff, ns, s));
-    if (Lsurf) CK(b->Lsurf.download(Lsurf, ns, s));
-    if (dt) CK(b->dt.download(dt, ns, s));
-    if (tsec) CK(b->tsec.download(tsec, ns, s));
-    if (model) CK(b->model.download(model, ns, s));
     CK(cudaStreamSynchronize(s));
+    off = 0;
+    for (const Item& it : items) {
+        if (!it.dst) continue;
+        std::memcpy(it.dst, b->h_stage + off, it.bytes);
+        off += (it.bytes + 15) & ~(size_t)15;
+    }
     return DSTAR_OK;
 }
 
