@@ -331,17 +331,17 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # DRAM bytes of one cell-pass launch from the committed ncu --set full capture of this very configuration
-    # (profiles/r01d_ncu_full_summary.md, r01j table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
-    traffic = 6.09e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
+    # (profiles/r01d_ncu_full_summary.md, r01l table: dram__bytes_read.sum + dram__bytes_write.sum); other sizes: null
+    traffic = 6.11e9 if (args.workload == "custom_Tc_Qimp" and n_star == 256 and abs(args.resolution - 0.05) < 1e-12) else None
     roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>", "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                "traffic_note": "bytes per launch, ncu capture r01j (mostly register-spill frames cycling through L2); "
+                "traffic_note": "bytes per launch, ncu capture r01l (mostly register-spill frames cycling through L2); "
                                 "algorithmic bytes per launch %.3g" % alg_bytes,
                 "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
                                "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
                 "flops_per_eval": {"cell": FLOP_CELL, "face": FLOP_FACE},
                 "cell_plus_face": {"achieved": both_tf, "frac": both_tf / fp64_peak if fp64_peak > 0 else None},
-                "fp64_pipe_busy_ncu": {"cell": 0.41, "face": 0.50, "source": "profiles/r01d_ncu_full_summary.md"},
+                "fp64_pipe_busy_ncu": {"cell": 0.445, "face": 0.44, "source": "profiles/r01d_ncu_full_summary.md"},
                 "hbm": {"achieved_gbs": alg_bytes / (cell_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                 "kernel_ms": {"cells": tc / args.steps, "faces": tf / args.steps, "evolve": te / args.steps}}
