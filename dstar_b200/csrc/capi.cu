@@ -176,6 +176,27 @@ extern "C" {
 
 const char* dstar_last_error(void) { return g_err.c_str(); }
 
+// Local-memory window of the device.  The coefficient kernels keep ~0.7 KB of spill frame per thread, and the frames
+// of all resident threads (~90 MB) cycle through L2.  How they map onto L2 depends on the per-thread window the driver
+// lays local memory out with; that follows cudaLimitStackSize and whatever resized the pool earlier in the process.
+// Measured (256 stars, cell pass; profiles/r01_notes.md, r01m): 5.42 ms in a fresh process at the 1 KB default, but
+// 6.25 ms at the same 1 KB when torch had launched a kernel first, and 6.39 ms after NCCL had set 1872 B for its own
+// kernels (every multi-GPU run); with the limit raised to 2 / 4 / 8 / 16 KB: 5.59 / 5.44 / 5.42 / 5.39 ms in all of
+// these situations.  The library therefore raises the limit to 8 KB (never lowers it) and re-checks before every
+// coefficient pass, because NCCL resets it when a communicator is created.  Cost: 8 KB x 303 k resident threads =
+// 2.4 GB of HBM.  DSTAR_STACK_LIMIT=<bytes> overrides, 0 leaves the device alone.
+static cudaError_t ensure_stack_limit() {
+    static const size_t want = [] {
+        const char* e = std::getenv("DSTAR_STACK_LIMIT");
+        return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)8192;
+    }();
+    if (want == 0) return cudaSuccess;
+    size_t cur = 0;
+    cudaError_t e = cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+    if (e != cudaSuccess || cur >= want) return e;
+    return cudaDeviceSetLimit(cudaLimitStackSize, want);   // synchronises the device; happens once (or once per NCCL init)
+}
+
 int dstar_ctx_create(int device, dstar_ctx** out) {
     if (!out) return fail(DSTAR_ERR_ARG, "ctx == NULL");
     int ndev = 0;
@@ -184,6 +205,7 @@ int dstar_ctx_create(int device, dstar_ctx** out) {
         return fail(DSTAR_ERR_CUDA, "no CUDA device: dstar_b200 has no CPU fallback", e);
     if (device < 0 || device >= ndev) return fail(DSTAR_ERR_ARG, "device index out of range");
     CK(cudaSetDevice(device));
+    CK(ensure_stack_limit());
     dstar_ctx* c = new dstar_ctx;
     c->device = device;
     CK(cudaGetDeviceProperties(&c->prop, device));
@@ -529,6 +551,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     dstar_ctx* c = b->ctx;
     if (!c->helm_loaded) return fail(DSTAR_ERR_STATE, "HELM table not loaded (dstar_ctx_set_helm)");
     CK(cudaSetDevice(c->device));
+    CK(ensure_stack_limit());
     cudaStream_t s = c->stream;
     const size_t tsz = (size_t)4 * DS_NTAB * b->total;
     if (!b->tab_lnCp.p) {
