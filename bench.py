@@ -353,8 +353,9 @@ def run_b200(args):
     line = {"metric": METRIC, "value": evals * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %d stars/GPU x nz~%d, %d epochs, HZ90 crust, pcy97 atmosphere, rebuilt HELM/gap tables"
-                       % (args.workload, n_star, int(np.median(nz)), H["em"].shape[0]),
+            "config": {"workload": "%s: %d stars/GPU x nz~%d, %d epochs, %s crust, bc09 atmosphere (device-generated table), rebuilt HELM/gap tables"
+                       % (args.workload, n_star, int(np.median(nz)), H["em"].shape[0],
+                          "abuntime (synthetic)" if args.workload == "int16_demo" else "HZ90"),
                        "stars_per_gpu": n_star, "zones_total_per_gpu": total, "seed": 20261019,
                        "l2_policy": "inputs+tables per step %.0f MB > 126 MB L2" % ((4 * 4096.0 * total + h2d) / 1e6)},
             "curves_per_sec": n_star * world / (ms_step * 1e-3),

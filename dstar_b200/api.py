@@ -98,6 +98,26 @@ class Context:
         return ionic, Yion, n2.value
 
 
+def _atm_bc09_Teff(self, grav, Plight, Pb, lgTeff=None, with_info=False):
+    """do_get_bc09_Teff (dStar_atm/private/bc09.f:45-95) for n_tab (grav, Plight, Pb) triples on the device.
+    Returns lgTeff(nv), lgTb(n_tab, nv), lgflux(n_tab, nv), ierr(n_tab)[, info(n_tab, nv, 4)]."""
+    grav = f64(np.atleast_1d(grav)); Plight = f64(np.atleast_1d(Plight)); Pb = f64(np.atleast_1d(Pb))
+    if lgTeff is None:   # dStar_atm_def.f:4-8: 256 knots over lgTeff = 5.5 .. 7.0
+        lgTeff = 5.5 + np.arange(256) * (7.0 - 5.5) / 255.0
+    lgTeff = f64(lgTeff)
+    nt, nv = len(grav), len(lgTeff)
+    lgTb = np.zeros((nt, nv)); lgflux = np.zeros((nt, nv)); ierr = np.zeros(nt, dtype=np.int32)
+    info = np.zeros((nt, nv, 4)) if with_info else None
+    rc = self.L.dstar_atm_bc09_Teff(self.h, nt, p(grav), p(Plight), p(Pb), nv, p(lgTeff), p(lgTb), p(lgflux),
+                                    p(ierr, ip), p(info))
+    if rc <= -100:
+        check(rc, "dstar_atm_bc09_Teff")
+    return (lgTeff, lgTb, lgflux, ierr) + ((info,) if with_info else ())
+
+
+Context.atm_bc09_Teff = _atm_bc09_Teff
+
+
 def host_interp_pm(x, y):
     """MESA interp_pm on the host (setup utility of the product): returns the (n,4) coefficients."""
     x = f64(x)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/dstar_b200.h"
+#include "atm_launch.hpp"
 #include "kernels_evolve.cuh"
 #include "kernels_micro.cuh"
 #include "kernels_test.cuh"
@@ -430,6 +431,45 @@ int dstar_crust_composition_info(dstar_ctx* c, int nv, int nisos, const double* 
     CK(d_Yion.download(Yion, (size_t)nch * nz, s));
     CK(cudaStreamSynchronize(s));
     if (ncharged) *ncharged = nch;
+    return DSTAR_OK;
+}
+
+// do_get_bc09_Teff (dStar_atm/private/bc09.f:45-95) for n_tab (grav, Plight, Pb) triples at once: one thread per
+// (table, knot), kernels_atm.cuh.  lgflux = 4 lgTeff + log10(sigma_SB) (bc09.f:88) is filled here.
+int dstar_atm_bc09_Teff(dstar_ctx* c, int n_tab, const double* grav, const double* Plight, const double* Pb, int nv,
+                        const double* lgTeff, double* lgTb, double* lgflux, int32_t* ierr, double* info) {
+    if (!c || n_tab < 1 || nv < 1 || !grav || !Plight || !Pb || !lgTeff || !lgTb) return fail(DSTAR_ERR_ARG, "atm_bc09_Teff");
+    if (!c->helm_loaded) return fail(DSTAR_ERR_STATE, "HELM table not loaded (dstar_ctx_set_helm)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t tot = (size_t)n_tab * nv;
+    DevBuf<double> d_g, d_pl, d_pb, d_te, d_tb, d_info;
+    DevBuf<int> d_ie;
+    CK(d_g.upload(grav, n_tab, s)); CK(d_pl.upload(Plight, n_tab, s)); CK(d_pb.upload(Pb, n_tab, s));
+    CK(d_te.upload(lgTeff, nv, s)); CK(d_tb.alloc(tot)); CK(d_ie.alloc(tot));
+    if (info) CK(d_info.alloc(4 * tot));
+    DsHostConsts hc;
+    fill_host_consts(hc);
+    CK(ds_bc09_launch(c->helm, hc, n_tab, nv, d_g.p, d_pl.p, d_pb.p, d_te.p, d_tb.p, info ? d_info.p : nullptr, d_ie.p, s));
+    std::vector<int> h_ie(tot);
+    CK(d_tb.download(lgTb, tot, s));
+    CK(d_ie.download(h_ie.data(), tot, s));
+    if (info) CK(d_info.download(info, 4 * tot, s));
+    CK(cudaStreamSynchronize(s));
+    int worst = 0;
+    for (int t = 0; t < n_tab; ++t) {
+        int e = 0;
+        for (int i = nv - 1; i >= 0; --i)   // the reference stops at the first failing knot, hottest first (bc09.f:77-87)
+            if (h_ie[(size_t)t * nv + i] != 0) { e = h_ie[(size_t)t * nv + i]; break; }
+        if (ierr) ierr[t] = e;
+        if (e != 0) worst = e;
+    }
+    if (lgflux) {
+        const double lg_sigma = dsm::log10(dsc::sigma_SB);
+        for (int t = 0; t < n_tab; ++t)
+            for (int i = 0; i < nv; ++i) lgflux[(size_t)t * nv + i] = 4.0 * lgTeff[i] + lg_sigma;
+    }
+    if (worst != 0) return fail(worst, "bc09: envelope integration failed for at least one table (see ierr)");
     return DSTAR_OK;
 }
 

@@ -5,8 +5,9 @@
 // HZ90_comp.f), the crust table lgRho(lgP), lgEps(lgP) (dStar_crust_mod.f:74-171; the P->rho inversion
 // evaluates the EOS on the DEVICE in batched form), the crust TOV integration
 // (NScool_crust_tov.f:110-303) and zone geometry (NScool_create_model.f:138-243), the pcy97
-// atmosphere table (dStar_atm/private/pcy97.f), user hooks.  What runs on the device: composition
-// lookups, the coefficient pass, the whole thermal evolution.
+// atmosphere table (dStar_atm/private/pcy97.f), interp_pm of the atmosphere tables (dStar_atm_mod.f:97-99), user
+// hooks.  What runs on the device: composition lookups, the bc09 envelope integrations behind the default
+// atmosphere table (dStar_atm/private/bc09.f), the coefficient pass, the whole thermal evolution.
 #include <algorithm>
 #include <array>
 #include <cctype>
@@ -565,6 +566,15 @@ struct AtmTable {  // dStar_atm_def.f:11-19
     int nv = 256;
     std::vector<double> lgTb, lgTeff, lgflux;
 };
+// bc09 tables already generated in this process, keyed by the exact (grav, Plight, Pb) triple.  (The reference
+// caches them on disk under a name built from int(100*log10(.)) of the three numbers, dStar_atm_mod.f:171-181, so
+// two stars whose gravities differ by < 2 % silently share whichever table was generated first; here every distinct
+// triple gets its own table.)
+struct AtmKey {
+    double g, pl, pb;
+    bool operator<(const AtmKey& o) const { return g != o.g ? g < o.g : (pl != o.pl ? pl < o.pl : pb < o.pb); }
+};
+std::map<AtmKey, std::shared_ptr<AtmTable>> g_atm_cache;
 
 // ------------------------------------------------------------------ one star
 struct Star {
@@ -577,7 +587,7 @@ struct Star {
     std::shared_ptr<CrustTable> crust;
     AtmTable atm;
     double Lsurf = 0, dlnLsdlnT = 0, Teff = 0, Tcore = 0, Psurf = 0, Pcore = 0, Mcore = 0, Rcore = 0, ePhicore = 0,
-           Mtotal = 0, Rtotal = 0, grav = 0, tsec = 0, dt = 0;
+           Mtotal = 0, Rtotal = 0, grav = 0, tsec = 0, dt = 0, Plight = 0;
     int model = 0;
     std::map<std::string, std::vector<double>> z;  // zone arrays by name
     std::vector<double> t_monitor, Teff_monitor, Qb_monitor;
@@ -845,8 +855,10 @@ int setup_zones(Star& s) {
     s.grav = s.Mtotal * mass_g * k::Gnewton / ((s.Rtotal * 1.0e5) * (s.Rtotal * 1.0e5)) * Z["eLambda_bar"][0];
     // atmosphere table (dStar_atm_mod.f:46-106), pcy97.f:8-44
     double Plight = s.grav * std::pow(10.0, c.lg_atm_light_element_column);
-    if (c.atm_model != "pcy97") {
-        s.err = "atm_model '" + c.atm_model + "': only 'pcy97' is built so far (bc09 table generation is a next-row item, SURVEY 8f-1)";
+    s.Plight = Plight;
+    if (c.atm_model == "bc09") { s.atm.nv = 0; return 0; }   // generated for the whole batch at once: build_bc09_tables
+    if (c.atm_model != "pcy97") {   // dStar_atm_mod.f:102-104: assertion 'atmosphere prefix is okay'
+        s.err = "atm_model '" + c.atm_model + "': expected 'bc09' or 'pcy97'";
         return -1;
     }
     AtmTable& at = s.atm;
@@ -870,6 +882,46 @@ int setup_zones(Star& s) {
     }
     interp_pm(at.lgTb.data(), at.nv, at.lgTeff.data());
     interp_pm(at.lgTb.data(), at.nv, at.lgflux.data());
+    return 0;
+}
+
+// do_generate_atm_table with prefix 'bc09' (dStar_atm_mod.f:46-106) for every star of the batch that asked for it:
+// the distinct (grav, Plight, Psurf) triples not yet in the cache go to the device in ONE call (thread = table x
+// knot, kernels_atm.cuh), then interp_pm in lgTb on the host.
+int build_bc09_tables(const std::vector<Star*>& ss) {
+    std::vector<AtmKey> want;
+    for (Star* s : ss) {
+        if (s->c.atm_model != "bc09") continue;
+        const AtmKey key{s->grav, s->Plight, s->Psurf};
+        if (g_atm_cache.count(key) == 0 && std::find_if(want.begin(), want.end(), [&](const AtmKey& q) {
+                return !(q < key) && !(key < q); }) == want.end())
+            want.push_back(key);
+    }
+    if (!want.empty()) {
+        const int nt = (int)want.size(), nv = 256;   // atm_default_number_table_points, dStar_atm_def.f:4
+        std::vector<double> g(nt), pl(nt), pb(nt), lgTeff(nv), lgTb((size_t)nv * nt), lgflux((size_t)nv * nt);
+        std::vector<int32_t> ierr(nt);
+        for (int t = 0; t < nt; ++t) { g[t] = want[t].g; pl[t] = want[t].pl; pb[t] = want[t].pb; }
+        for (int i = 0; i < nv; ++i) lgTeff[i] = 5.5 + (double)i * (7.0 - 5.5) / (double)(nv - 1);   // dStar_atm_def.f:7-8
+        const int rc = dstar_atm_bc09_Teff(g_ctx, nt, g.data(), pl.data(), pb.data(), nv, lgTeff.data(), lgTb.data(),
+                                           lgflux.data(), ierr.data(), nullptr);
+        if (rc != 0) { g_err = std::string("bc09 atmosphere: ") + dstar_last_error(); return rc; }
+        for (int t = 0; t < nt; ++t) {
+            auto at = std::make_shared<AtmTable>();
+            at->nv = nv;
+            at->lgTb.assign(&lgTb[(size_t)nv * t], &lgTb[(size_t)nv * t] + nv);
+            at->lgTeff.assign(4 * nv, 0.0); at->lgflux.assign(4 * nv, 0.0);
+            for (int i = 0; i < nv; ++i) { at->lgTeff[4 * i] = lgTeff[i]; at->lgflux[4 * i] = lgflux[(size_t)nv * t + i]; }
+            // (as in the reference, nothing checks that lgTb(lgTeff) came out increasing: dop853 at rtol 1e-6 takes
+            //  steps of several e-folds in P across the opacity ramp and the melting line and an occasional knot is off
+            //  by ~1e-2 dex; the lookup's binary search is defined for any array)
+            interp_pm(at->lgTb.data(), nv, at->lgTeff.data());
+            interp_pm(at->lgTb.data(), nv, at->lgflux.data());
+            g_atm_cache[want[t]] = at;
+        }
+    }
+    for (Star* s : ss)
+        if (s->c.atm_model == "bc09") s->atm = *g_atm_cache[AtmKey{s->grav, s->Plight, s->Psurf}];
     return 0;
 }
 
@@ -974,6 +1026,7 @@ void dstar_NScool_shutdown(void) {
     g_batch.clear();
     g_stars.clear();
     g_crust_cache.clear();
+    g_atm_cache.clear();
     for (auto& s : g_loaded_gaps) s.clear();
     if (g_ctx) dstar_ctx_destroy(g_ctx);
     g_ctx = nullptr;
@@ -1043,6 +1096,7 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
         s->nisos = (int)s->crust->net.Z.size();
         s->ncharged = s->crust->net.ncharged();
     }
+    if (build_bc09_tables(ss) != 0) return -1;
     // all stars of one batch must share the nuclide network
     const Network& net = ss[0]->crust->net;
     const int nch = ss[0]->ncharged;

@@ -2,8 +2,8 @@
 
 Each builder returns a list of dstar_b200.NScool slots with their controls set exactly as the
 corresponding example inlist sets them (examples/<name>/inlist), varied per star as the sweep /
-MCMC driver would.  One deliberate difference from the shipped inlists: atm_model = 'pcy97' (the
-bc09 envelope integration is a "next" row).
+MCMC driver would -- including the outer boundary: no example inlist sets atm_model, so all of them run
+the default 'bc09' envelope (NScool/defaults/controls.defaults:149), whose table the device generates.
 """
 import numpy as np
 
@@ -11,7 +11,7 @@ from .api import NScool
 
 SEED = 20261019
 
-_COMMON = dict(atm_model="pcy97", maximum_number_of_models=10000, maximum_timestep=0.0, integration_tolerance=1.0e-4,
+_COMMON = dict(atm_model="bc09", maximum_number_of_models=10000, maximum_timestep=0.0, integration_tolerance=1.0e-4,
                min_lg_temperature_integration=7.0, max_lg_temperature_integration=9.5, core_mass=1.6,
                core_radius=11.0, lgPcrust_bot=32.5, lgPcrust_top=27.0)
 

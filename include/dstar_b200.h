@@ -83,6 +83,14 @@ int dstar_crust_composition_info(dstar_ctx* ctx, int nv, int nisos, const double
                                  const double* Ycoef, const double* Ziso, const double* Aiso, int nz,
                                  const double* lgP, double* ionic, double* Yion, int32_t* ncharged);
 
+/* do_get_bc09_Teff (dStar_atm/private/bc09.f:45-95; the default atm_model, NScool/defaults/controls.defaults:149)
+ * for n_tab independent (grav, Plight, Pb) triples: lgTeff(nv) ascending knots in, lgTb(nv,n_tab) and
+ * lgflux(nv,n_tab) out, ierr(n_tab) = the reference's ierr per table.  info: NULL or (4,nv,n_tab) = rho_ph, P_ph,
+ * kappa_ph, number of EOS evaluations.  What do_generate_atm_table (dStar_atm_mod.f:46-106) then does with the
+ * result (interp_pm in lgTb) is host work: dstar_NScool_create_model(s) in dstar_nscool.h. */
+int dstar_atm_bc09_Teff(dstar_ctx* ctx, int n_tab, const double* grav, const double* Plight, const double* Pb,
+                        int nv, const double* lgTeff, double* lgTb, double* lgflux, int32_t* ierr, double* info);
+
 /* ---- controls shared by all stars of a batch (subset of NScool/public/NScool_controls.inc) ---- */
 typedef struct dstar_micro_ctrl {
     double eos_gamma_melt_pt, eos_rsi_melt_pt, eos_nuclide_abundance_threshold; /* <= 0: defaults */

@@ -96,6 +96,28 @@ void dso_pcy97(double grav, double Plight, int n, const double* lgTb, double* lg
     pcy97_Teff(grav, Plight, n, lgTb, lgTeff, lgflux);
 }
 
+// bc09 (atm.cpp): tight != 0 selects Bc09Settings::tight(); info (6, n) = rho_ph, P_ph, kappa_ph, nstep, nfcn, n_eos
+int dso_bc09_Teff(double grav, double Plight, double Pb, int n, const double* lgTeff, int tight, double* lgTb,
+                  double* lgflux, double* info) {
+    if (!g_helm_loaded) return -100;
+    std::vector<Bc09Knot> kn(n);
+    const int ierr = bc09_Teff(g_helm, grav, Plight, Pb, n, lgTeff, lgTb, lgflux,
+                               tight ? Bc09Settings::tight() : Bc09Settings::reference(), kn.data());
+    if (info)
+        for (int i = 0; i < n; ++i) {
+            double* o = info + 6 * i;
+            o[0] = kn[i].rho_ph; o[1] = kn[i].P_ph; o[2] = kn[i].kappa_ph; o[3] = kn[i].nstep; o[4] = kn[i].nfcn;
+            o[5] = kn[i].n_eos;
+        }
+    return ierr;
+}
+int dso_bc09_table(double grav, double Plight, double Pb, int nv, int tight, double* lgTb, double* lgTeff4,
+                   double* lgflux4) {
+    if (!g_helm_loaded) return -100;
+    return bc09_table(g_helm, grav, Plight, Pb, nv, lgTb, lgTeff4, lgflux4,
+                      tight ? Bc09Settings::tight() : Bc09Settings::reference());
+}
+
 // batched EOS: for k in [0,n): rho[k], T[k], ionic[11*k..], Yion[ncharged*k..], Tcs[3*k..];
 // chi_in[k] (<0 => default nuclear size); out res[15*k..], phase[k], chi_out[k]
 int dso_eval_crust_eos_c(int n, const double* rho, const double* T, const double* ionic, int ncharged,

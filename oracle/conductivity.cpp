@@ -15,7 +15,8 @@ using namespace cst;
 #include "dop853_coef.inc"
 
 namespace {
-double hinit853(int n, OdeRhs f, void* ctx, double x, const double* y, double posneg,
+template <class F>
+double hinit853(int n, F f, double x, const double* y, double posneg,
                 const double* f0, double* f1, double* y1, int iord, double hmax, double atol,
                 double rtol) {
     double dnf = 0.0, dny = 0.0;
@@ -30,7 +31,7 @@ double hinit853(int n, OdeRhs f, void* ctx, double x, const double* y, double po
     h = std::min(h, hmax);
     h = std::copysign(h, posneg);
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * f0[i];
-    f(n, x + h, y1, f1, ctx);
+    f(n, x + h, y1, f1);
     double der2 = 0.0;
     for (int i = 0; i < n; ++i) {
         double sk = atol + rtol * std::fabs(y[i]);
@@ -46,9 +47,14 @@ double hinit853(int n, OdeRhs f, void* ctx, double x, const double* y, double po
 }
 }  // namespace
 
-// returns idid: 1 ok, -2 too many steps, -3 step too small
-int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double h0,
-           double max_step, int max_steps, double rtol, double atol, Dop853Stats* st) {
+// returns idid: 1 ok, -2 too many steps, -3 step too small, -5 the right-hand side failed at the starting point.
+// F(n, x, y, dy) returns ierr; MESA's fcn interface says "nonzero means retry with smaller timestep" (quoted at
+// dStar_atm/private/bc09.f:458): a stage whose right-hand side fails is treated as a rejected step with the largest
+// step reduction the controller knows (h / facc1), like a step with infinite error.
+namespace {
+template <class F>
+int dop853_impl(int n, F f, double& x, double* y, double xend, double h0,
+                double max_step, int max_steps, double rtol, double atol, Dop853Stats* st) {
     const double uround = 2.3e-16, safe = 0.9, fac1 = 0.333, fac2 = 6.0, beta = 0.0;
     const double expo1 = 1.0 / 8.0 - beta * 0.2;
     const double facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
@@ -60,9 +66,9 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
     double facold = 1.0e-4;
     bool last = false, reject = false;
     int nfcn = 0, nstep = 0, naccpt = 0, nrejct = 0;
-    f(n, x, y, k(0), ctx);
+    if (f(n, x, y, k(0)) != 0) return -5;
     double h = h0;
-    if (h == 0.0) h = hinit853(n, f, ctx, x, y, posneg, k(0), k(1), k(2), 8, hmax, atol, rtol);
+    if (h == 0.0) h = hinit853(n, f, x, y, posneg, k(0), k(1), k(2), 8, hmax, atol, rtol);
     nfcn += 2;
     int idid = 1;
     for (;;) {
@@ -71,7 +77,8 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
         if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
         ++nstep;
         // 12 stages
-        for (int s = 1; s < 12; ++s) {
+        bool failed = false;
+        for (int s = 1; s < 12 && !failed; ++s) {
             for (int i = 0; i < n; ++i) {
                 double acc = 0.0;
                 for (int j = 0; j < s; ++j) {
@@ -80,9 +87,16 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
                 }
                 ytmp[i] = y[i] + h * acc;
             }
-            f(n, x + dop_c[s] * h, ytmp.data(), k(s), ctx);
+            failed = f(n, x + dop_c[s] * h, ytmp.data(), k(s)) != 0;
         }
         nfcn += 11;
+        if (failed) {   // retry with a smaller step
+            h = h / facc1;
+            reject = true;
+            if (naccpt >= 1) ++nrejct;
+            last = false;
+            continue;
+        }
         double xph = x + h;
         double* k4 = k(12);
         for (int i = 0; i < n; ++i) {
@@ -110,10 +124,17 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
         double fac = fac11 / dsm::pow(facold, beta);
         fac = std::max(facc2, std::min(facc1, fac / safe));
         double hnew = h / fac;
+        if (err <= 1.0 && f(n, xph, ynew.data(), k4) != 0) {   // the new point itself is not evaluable: retry smaller
+            ++nfcn;
+            h = h / facc1;
+            reject = true;
+            if (naccpt >= 1) ++nrejct;
+            last = false;
+            continue;
+        }
         if (err <= 1.0) {
             facold = std::max(err, 1.0e-4);
             ++naccpt;
-            f(n, xph, ynew.data(), k4, ctx);
             ++nfcn;
             for (int i = 0; i < n; ++i) { k(0)[i] = k4[i]; y[i] = ynew[i]; }
             x = xph;
@@ -131,6 +152,17 @@ int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double
     }
     if (st) { st->nfcn = nfcn; st->nstep = nstep; st->naccpt = naccpt; st->nrejct = nrejct; }
     return idid;
+}
+}  // namespace
+int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double h0,
+           double max_step, int max_steps, double rtol, double atol, Dop853Stats* st) {
+    auto g = [f, ctx](int n_, double x_, const double* y_, double* dy_) { f(n_, x_, y_, dy_, ctx); return 0; };
+    return dop853_impl(n, g, x, y, xend, h0, max_step, max_steps, rtol, atol, st);
+}
+int dop853_checked(int n, OdeRhsChecked f, void* ctx, double& x, double* y, double xend, double h0,
+                   double max_step, int max_steps, double rtol, double atol, Dop853Stats* st) {
+    auto g = [f, ctx](int n_, double x_, const double* y_, double* dy_) { return f(n_, x_, y_, dy_, ctx); };
+    return dop853_impl(n, g, x, y, xend, h0, max_step, max_steps, rtol, atol, st);
 }
 
 // ---------------------------------------------------- electron scattering

@@ -12,7 +12,7 @@
 // those are data-free (see tests/test_oracle_golden.py):
 //   constants/test/sample_output.data, nucchem/test/sample_output,
 //   neutrino/test/sample_output.data (crust rows), conductivity/test/
-//   sample_output.data, dStar_atm/test/sample_output.data (pcy97 rows),
+//   sample_output.data, dStar_atm/test/sample_output.data (pcy97 and bc09 rows),
 //   dStar_eos/test/sample_output.data, superfluid/test/sample_output.data.
 // PARITY UNPINNED (no golden exists upstream): the stiff integrator (MESA
 // isolve/rodasp, not in tree) and therefore Teff(t); see DESIGN.md.
@@ -260,9 +260,45 @@ struct Dop853Stats {
 typedef void (*OdeRhs)(int n, double x, const double* y, double* dy, void* ctx);
 int dop853(int n, OdeRhs f, void* ctx, double& x, double* y, double xend, double h0,
            double max_step, int max_steps, double rtol, double atol, Dop853Stats* st = nullptr);
+// same integrator, right-hand side returning ierr (nonzero = "retry with smaller timestep", MESA's fcn contract)
+typedef int (*OdeRhsChecked)(int n, double x, const double* y, double* dy, void* ctx);
+int dop853_checked(int n, OdeRhsChecked f, void* ctx, double& x, double* y, double xend, double h0,
+                   double max_step, int max_steps, double rtol, double atol, Dop853Stats* st = nullptr);
 
 // -------------------------------------------------------------- atmosphere
 void pcy97_Teff(double grav, double Plight, int n, const double* lgTb, double* lgTeff,
                 double* lgflux);
+
+// bc09 (dStar_atm/private/bc09.f, dStar_atm_mod.f:46-106): see atm.cpp
+struct Bc09Settings {
+    bool chain_guess = true;                  // rho_ph of knot i+1 is the guess of knot i (bc09.f:77-82)
+    int max_iter_photosphere = 20;            // bc09.f:291
+    double tol_photosphere_lnrho = 1.0e-6;    // bc09.f:292
+    double tol_photosphere_condition = 1.0e-8;  // bc09.f:293
+    // bc09.f:567 passes 20; 60 here in both modes: at the melting line P(rho) of the ion mixture jumps by ~1e-3 and
+    // a wanted pressure inside the jump has no root -- bisection then needs ~40 calls to close the bracket to 1e-12
+    // (what MESA's own finder returns there is not knowable without its source; the reference's golden run got through)
+    int max_iter_density = 60;
+    double tol_density = 1.0e-12;             // bc09.f:568
+    static Bc09Settings reference() { return Bc09Settings(); }
+    static Bc09Settings tight() {   // knot-independent form used by the device kernel
+        Bc09Settings s;
+        s.chain_guess = false;
+        s.max_iter_photosphere = 200;
+        s.tol_photosphere_lnrho = 1.0e-13;
+        s.tol_photosphere_condition = 0.0;
+        s.max_iter_density = 60;
+        s.tol_density = 1.0e-13;
+        return s;
+    }
+};
+struct Bc09Knot {   // diagnostics per knot
+    double rho_ph, P_ph, kappa_ph;
+    int nstep, nfcn, n_eos;
+};
+int bc09_Teff(const HelmTable& h, double grav, double Plight, double Pb, int n, const double* lgTeff, double* lgTb,
+              double* lgflux, const Bc09Settings& st, Bc09Knot* info = nullptr);
+int bc09_table(const HelmTable& h, double grav, double Plight, double Pb, int nv, double* lgTb, double* lgTeff4,
+               double* lgflux4, const Bc09Settings& st);
 
 }  // namespace dso

@@ -152,6 +152,21 @@ class Oracle:
         self.lib.dso_pcy97(grav, Plight, len(lgTb), _ptr(lgTb), _ptr(a), _ptr(b))
         return a, b
 
+    def bc09_Teff(self, grav, Plight, Pb, lgTeff, tight=False):
+        """do_get_bc09_Teff (bc09.f:45-95): returns ierr, lgTb, lgflux, info(n,6)."""
+        lgTeff = f64(lgTeff); n = len(lgTeff)
+        lgTb = np.zeros(n); lgflux = np.zeros(n); info = np.zeros((n, 6))
+        self.lib.dso_bc09_Teff.argtypes = [C.c_double] * 3 + [C.c_int, dp, C.c_int, dp, dp, dp]
+        rc = self.lib.dso_bc09_Teff(grav, Plight, Pb, n, _ptr(lgTeff), int(tight), _ptr(lgTb), _ptr(lgflux), _ptr(info))
+        return rc, lgTb, lgflux, info
+
+    def bc09_table(self, grav, Plight, Pb, nv=256, tight=False):
+        """do_generate_atm_table('bc09') (dStar_atm_mod.f:46-106): returns ierr, lgTb(nv), lgTeff(nv,4), lgflux(nv,4)."""
+        lgTb = np.zeros(nv); a = np.zeros((nv, 4)); b = np.zeros((nv, 4))
+        self.lib.dso_bc09_table.argtypes = [C.c_double] * 3 + [C.c_int, C.c_int, dp, dp, dp]
+        rc = self.lib.dso_bc09_table(grav, Plight, Pb, nv, int(tight), _ptr(lgTb), _ptr(a), _ptr(b))
+        return rc, lgTb, a, b
+
     # ---- batched microphysics
     def eval_crust_eos(self, rho, T, ionic, Zion, Aion, Yion, Tcs, chi_in=None, eos_ctrl=None):
         rho = f64(rho); T = f64(T); ionic = f64(ionic); Yion = f64(Yion); Tcs = f64(Tcs)

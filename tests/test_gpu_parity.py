@@ -141,7 +141,7 @@ def test_conductivity_parity(ctx, oracle, neutrons):
 
 
 def _make_star(ds, **kw):
-    base = dict(atm_model="pcy97", target_resolution_lnP=0.2, number_epochs=2, basic_epoch_Mdots=[1.0e17, 0.0],
+    base = dict(target_resolution_lnP=0.2, number_epochs=2, basic_epoch_Mdots=[1.0e17, 0.0],
                 basic_epoch_boundaries=[0.0, 50.0, 1050.0], core_temperature=1.4e8,
                 atmosphere_temperature_when_accreting=2.4e8, turn_on_extra_heating=True, Q_heating_shallow=0.1,
                 lgP_min_heating_shallow=27.5, lgP_max_heating_shallow=28.5, which_neutron_1S0_gap="sfb03",
