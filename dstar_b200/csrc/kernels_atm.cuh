@@ -10,6 +10,14 @@
 // The evaluators are the same inlined device functions the coefficient pass uses (plain IEEE divisions, phase
 // barriers compiled out in this translation unit because control flow here is per thread).
 //
+// SIMT shape: the nested adaptive algorithm (layers > dop853 steps > stages > bracket search > root iterations) is
+// written as an explicit per-lane STATE MACHINE around ONE call site of the ~0.4 MB evaluator.  Every trip of the
+// kernel's single loop, all 32 lanes of a warp (32 neighbouring knots) evaluate the EOS together -- each for
+// whatever its own algorithm needs next -- and then advance their state with a few scalar operations.  Written as
+// ordinary nested loops the lanes fall out of step at the first data-dependent trip count and the compiler's
+// reconvergence points do not bring them back: ncu showed 1.25 active lanes per instruction and 3.9 s per table;
+// the state machine holds ~25 lanes per instruction (profiles/r02_notes.md).
+//
 // Departure from the reference, on purpose: the reference walks the knots from hot to cold and hands the
 // photospheric density of one knot to the next as the root finder's first guess (bc09.f:77-82), which would
 // serialise a table.  Here every knot starts from its own ideal-gas + Thomson guess and all roots are converged to
@@ -43,291 +51,398 @@ struct DsBc09Args {
 namespace dsa {
 using namespace dsc;
 
-struct Par {   // rpar / ipar of bc09.f:6-34
-    const DsHelmDev* helm;
-    const DsBc09Args* a;
-    const DsBc09Layer* L;
-    double grav, tau, Teff, pres, temp, rho, kappa;
-    int n_eos;
-};
 struct EosOut {
     double lnP, chiRho, grad_ad, Gamma, Theta, mu_e, chi;
 };
 
-// eval_crust_eos (dStar_eos_lib.f:123) at one point; never inlined so the ~0.4 MB evaluator exists once in the kernel
-__device__ __noinline__ void eos_point(const Par& p, double rho, double T, EosOut& o) {
-    const DsBc09Layer& L = *p.L;
+// eval_crust_eos (dStar_eos_lib.f:123) at one point; never inlined: the evaluator exists once in the kernel
+__device__ __noinline__ void eos_point(const DsHelmDev& helm, const DsEosCtrl& rq, const DsBc09Layer& L, double rho, double T,
+                                       EosOut& o) {
     const double chi = dse::nuclear_volume_fraction(rho, L.c, DS_DEFAULT_NUCLEAR_RADIUS);
     const DsZonePre zp = ds_zone_pre(rho, L.c, chi);
-    const DsHelmZone hz = ds_helm_zone(*p.helm, rho, L.c.A / (1.0 - L.c.Yn), L.c.Z);
+    const DsHelmZone hz = ds_helm_zone(helm, rho, L.c.A / (1.0 - L.c.Yn), L.c.Z);
     DsEosRes r;
     bool bad = false;
-    ds_eval_crust_eos<false>(*p.helm, p.a->eos, rho, T, dsm::log10(T), L.c, zp, hz, L.ncharged, L.Zion, L.Aion, L.ionz,
-                             L.Yion, 0.0, chi, r, bad);
+    ds_eval_crust_eos<false>(helm, rq, rho, T, dsm::log10(T), L.c, zp, hz, L.ncharged, L.Zion, L.Aion, L.ionz, L.Yion, 0.0,
+                             chi, r, bad);
     o.lnP = r.lnP; o.chiRho = r.chiRho; o.grad_ad = r.grad_ad; o.Gamma = r.Gamma; o.Theta = r.Theta; o.mu_e = r.mu_e;
     o.chi = chi;
 }
 // kappa = 4/3 a c T^3 / rho / K_total (bc09.f:437, :549)
-__device__ __noinline__ double opacity_point(const Par& p, double rho, double T, const EosOut& e) {
+__device__ __noinline__ double opacity_point(const DsCondCtrl& rq, const DsBc09Layer& L, double rho, double T, const EosOut& e) {
     DsCond K;
-    dsk::ds_conductivity(p.a->cond, rho, T, e.chi, e.Gamma, e.Theta, e.mu_e, p.L->c, dsk::ds_cond_pre(p.a->cond, rho, p.L->c),
-                         0.0, nan(""), 0, K);
+    dsk::ds_conductivity(rq, rho, T, e.chi, e.Gamma, e.Theta, e.mu_e, L.c, dsk::ds_cond_pre(rq, rho, L.c), 0.0, nan(""), 0, K);
     return 4.0 * onethird * arad * clight * dsd::ipow<3>(T) / rho / K.total;
 }
 
-// WHICH = 0: photosphere (bc09.f:373-443), 1: eval_pressure (bc09.f:607-666)
-template <int WHICH>
-DS_D double root_fn(Par& p, double lnrho, double& dfdx, int& ierr) {
+enum {   // program counter of a lane: where its algorithm continues once the pending evaluation has come back
+    PC_PH_START,                                                    // find_photospheric_pressure, bc09.f:284-371
+    PC_ROOT_BEGIN, PC_RB1, PC_RB3, PC_RBCHECK, PC_RBX1, PC_RBX3,    // look_for_brackets
+    PC_RSTART, PC_RIT,                                              // safe_root_with_initial_guess
+    PC_PH_FINAL,                                                    // photosphere evaluated at the returned root
+    PC_DERIV_ROOTED, PC_DERIV_FINAL,                                // get_coefficients, bc09.f:485-551
+    PC_DOP_GOT, PC_STEP_BEGIN, PC_STAGE_ISSUE, PC_STEP_ERR, PC_LAYER_DONE   // dop853, bc09.f:202-259
+};
+
+struct Lane {
+    int pc, ierr;
+    bool done;
+    // rpar / ipar of bc09.f:6-34
+    const DsBc09Layer* L;
+    double grav, tau, Teff, pres, temp, rho, kappa;
+    int n_eos;
+    double lgTeff, lgyb, lgy_light, lg_grav, lgTb;
+    double rho_ph, P_ph, kappa_ph, lnrho_ph;
+    // the pending evaluation
+    double q_rho, q_T;
+    bool q_opac;
+    // root finder: which = 0 photosphere (bc09.f:373-443), 1 eval_pressure (bc09.f:607-666)
+    int which, it, imax;
+    double xg, dx, x1, x3, y1, y3, x, epsx, epsy;
+    // deriv (bc09.f:445-483)
+    double d_lnT4, d_P, d_T, d_rho, d_val;
+    int d_ierr;
+    // dop853
+    int layer, stage, nstep;
+    bool last, reject;
+    double X, Y, xend, h, hmax, posneg, facold, xph, ynew, err, hnew;
+    double k[13];
+};
+
+DS_D void request_root_eval(Lane& z, double lnrho) {
+    z.q_rho = dsm::exp(lnrho);
+    z.q_T = (z.which == 0) ? z.Teff : z.temp;
+    z.q_opac = (z.which == 0);
+    ++z.n_eos;
+}
+// value of the root function from the evaluation that just came back
+DS_D double root_value(Lane& z, const EosOut& e, double kap, double& dfdx, int& ierr) {
     ierr = 0;
-    const double rho = dsm::exp(lnrho);
-    EosOut e;
-    ++p.n_eos;
-    if (WHICH == 0) {
-        eos_point(p, rho, p.Teff, e);
+    if (z.which == 0) {
         const double P = dsm::exp(e.lnP);
-        const double kappa = opacity_point(p, rho, p.Teff, e);
-        p.kappa = kappa;
-        p.pres = P;
+        z.kappa = kap;
+        z.pres = P;
         dfdx = 0.0;
-        return P - p.tau * p.grav / kappa;
+        return P - z.tau * z.grav / kap;
     }
-    eos_point(p, rho, p.temp, e);
-    if (!isfinite(e.lnP)) { ierr = -9; return 0.0; }
+    if (!isfinite(e.lnP)) { ierr = -9; dfdx = 0.0; return 0.0; }
     dfdx = e.chiRho;
-    return e.lnP - dsm::log(p.pres);
+    return e.lnP - dsm::log(z.pres);
 }
-
-// MESA num_lib look_for_brackets / safe_root_with_initial_guess, restated from their documented contract: bracket
-// search by a doubling increment around the guess; Newton step when a derivative is supplied and it stays inside the
-// bracket, bisection otherwise; stop on |dx| <= epsx or |f| <= epsy
-template <int WHICH>
-DS_D int look_for_brackets(Par& p, double x, double dx, double& x1, double& x3, double& y1, double& y3, int imax) {
-    int ierr = 0;
-    double dfdx;
-    x1 = x - dx;
-    x3 = x + dx;
-    y1 = root_fn<WHICH>(p, x1, dfdx, ierr);
-    if (ierr != 0) return ierr;
-    y3 = root_fn<WHICH>(p, x3, dfdx, ierr);
-    if (ierr != 0) return ierr;
-    for (int i = 0; i < imax; ++i) {
-        if (!(y1 * y3 > 0.0)) return (y1 * y3 <= 0.0) ? 0 : -1;
-        dx = 2.0 * dx;
-        if (fabs(y1) < fabs(y3)) {
-            x3 = x1; y3 = y1;
-            x1 = x1 - dx;
-            y1 = root_fn<WHICH>(p, x1, dfdx, ierr);
-        } else {
-            x1 = x3; y1 = y3;
-            x3 = x3 + dx;
-            y3 = root_fn<WHICH>(p, x3, dfdx, ierr);
-        }
-        if (ierr != 0) return ierr;
-    }
-    return (y1 * y3 <= 0.0) ? 0 : -1;
-}
-template <int WHICH>
-DS_D double safe_root(Par& p, double x_guess, double x1, double x3, double y1, double y3, int imax, double epsx,
-                      double epsy, int& ierr) {
-    ierr = 0;
-    if (y1 == 0.0) return x1;
-    if (y3 == 0.0) return x3;
-    double x = x_guess;
-    if (!(x > x1 && x < x3)) x = 0.5 * (x1 + x3);
-    for (int i = 0; i < imax; ++i) {
-        double dfdx = 0.0;
-        const double y = root_fn<WHICH>(p, x, dfdx, ierr);
-        if (ierr != 0) return x;
-        if (fabs(y) <= epsy) return x;
-        if ((y > 0.0) == (y1 > 0.0)) { x1 = x; y1 = y; } else { x3 = x; y3 = y; }
-        double xn = 0.5 * (x1 + x3);
-        if (dfdx != 0.0) {
-            const double xt = x - y / dfdx;
-            if (xt > x1 && xt < x3) xn = xt;
-        }
-        if (fabs(xn - x) <= epsx) return xn;
-        x = xn;
-    }
-    ierr = -1;
-    return x;
-}
-
-// deriv + get_coefficients + get_lnrho_from_PT (bc09.f:445-605); returns ierr
-DS_D int deriv(Par& p, double lnP, double lnT4, double& dlnT4dlnP) {
-    double rho = p.rho;
+DS_D void lane_fail(Lane& z, int ierr) { z.ierr = ierr; z.done = true; }
+// deriv (bc09.f:445-483) at (lnP, lnT4): starts get_lnrho_from_PT (bc09.f:553-605)
+DS_D void deriv_call(Lane& z, const DsBc09Args& a, double lnP, double lnT4) {
+    z.d_lnT4 = lnT4;
     const double P = dsm::exp(lnP);
-    const double T = p.Teff * dsm::exp(0.25 * lnT4);
-    // get_lnrho_from_PT
-    p.temp = T;
-    p.pres = P;
-    const double lnrho_guess = dsm::log(rho);
-    double x1, x3, y1, y3;
-    int ierr = look_for_brackets<1>(p, lnrho_guess, 0.5, x1, x3, y1, y3, p.a->max_iter_density);
-    if (ierr != 0) return ierr;
-    const double lnrho = safe_root<1>(p, lnrho_guess, x1, x3, y1, y3, p.a->max_iter_density, p.a->tol_density,
-                                      p.a->tol_density, ierr);
-    if (ierr != 0) return ierr;
-    rho = dsm::exp(lnrho);
-    EosOut e;
-    ++p.n_eos;
-    eos_point(p, rho, T, e);
-    if (!(fabs(dsm::exp(e.lnP) - P) < 1.0e-3 * P)) return -10;   // assertion "EOS is behaving", bc09.f:536
-    const double kappa = opacity_point(p, rho, T, e);
-    const double v = 0.75 * kappa * P / p.grav / dsm::exp(lnT4);
-    dlnT4dlnP = fmin(v, 4.0 * e.grad_ad);
-    p.rho = rho;   // the new anchor point (bc09.f:481)
-    return 0;
+    const double T = z.Teff * dsm::exp(0.25 * lnT4);
+    z.temp = T;
+    z.pres = P;
+    z.d_P = P; z.d_T = T;
+    z.which = 1;
+    z.xg = dsm::log(z.rho);
+    z.dx = 0.5;
+    z.imax = a.max_iter_density;
+    z.epsx = a.tol_density; z.epsy = a.tol_density;
+    z.pc = PC_ROOT_BEGIN;
+}
+DS_D void dop_start(Lane& z, double x, double y, double xend) {
+    z.X = x; z.Y = y; z.xend = xend;
+    z.hmax = fabs(xend - x);
+    z.posneg = copysign(1.0, xend - x);
+    z.facold = 1.0e-4;
+    z.last = false; z.reject = false;
+    z.nstep = 0;
+    z.stage = 0;
 }
 
-// Scalar DOP853 (Hairer, Norsett & Wanner; MESA num_lib dop853 as bc09.f:202,224 calls it): one equation, scalar
-// tolerances, given first step, no dense output.  A right-hand side that fails (ierr /= 0: "retry with smaller
-// timestep", bc09.f:458 -- e.g. a trial stage at a temperature whose radiation pressure alone exceeds P, where no
-// density solves the EOS) rejects the step with the controller's largest reduction, h / facc1.
-DS_D int dop853_scalar(Par& p, double& x, double& y, double xend, double h0, int max_steps, double rtol, double atol) {
+// Consume the evaluation (e, kap) the lane asked for and run its algorithm up to the next evaluation request
+// (or to the end).  Same operations in the same order as the nested-loop form.
+DS_D void advance(Lane& z, const DsBc09Args& a, const EosOut& e, double kap) {
     const double uround = 2.3e-16, safe = 0.9, fac1 = 0.333, fac2 = 6.0;
     const double facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
-    const double hmax = fabs(xend - x);
-    const double posneg = copysign(1.0, xend - x);
-    double k[13];
-    double facold = 1.0e-4;
-    bool last = false, reject = false;
-    int nstep = 0;
-    if (deriv(p, x, y, k[0]) != 0) return -5;
-    double h = h0;
-    int idid = 1;
     for (;;) {
-        if (nstep > max_steps) { idid = -2; break; }
-        if (0.1 * fabs(h) <= fabs(x) * uround) { idid = -3; break; }
-        if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = true; }
-        ++nstep;
-        bool failed = false;
-#pragma unroll 1
-        for (int s = 1; s < 12 && !failed; ++s) {
-            double acc = 0.0;
-            for (int j = 0; j < s; ++j) {
-                const double a = dop_a[s][j];
-                if (a != 0.0) acc += a * k[j];
+        switch (z.pc) {
+            case PC_PH_START: {
+                z.L = &a.layer[0];
+                z.Teff = dsd::dexp10(z.lgTeff);
+                z.tau = twothird;
+                const double kappa_Th = Thomson * avogadro * z.L->c.Ye;
+                const double eps_ph = a.tol_photosphere_condition * z.tau * z.grav / kappa_Th;
+                const double Pgas = z.tau * z.grav / kappa_Th - onethird * arad * dsd::ipow<4>(z.Teff);
+                if (Pgas < 0.0) {   // negative_photosphere_gas_pressure, bc09.f:324-330
+                    z.P_ph = 2.0 * onethird * arad * dsd::ipow<4>(z.Teff); z.kappa_ph = kappa_Th; z.rho_ph = -1.0;
+                    lane_fail(z, -2);
+                    return;
+                }
+                z.which = 0;
+                z.xg = dsm::log(Pgas * amu * z.L->c.A / (z.L->c.Z + 1.0) / boltzmann / z.Teff);
+                z.dx = 0.1;
+                z.imax = a.max_iter_photosphere;
+                z.epsx = a.tol_photosphere_lnrho; z.epsy = eps_ph;
+                z.pc = PC_ROOT_BEGIN;
+                break;
             }
-            failed = deriv(p, x + dop_c[s] * h, y + h * acc, k[s]) != 0;
+            // ---- look_for_brackets
+            case PC_ROOT_BEGIN:
+                z.x1 = z.xg - z.dx;
+                z.x3 = z.xg + z.dx;
+                request_root_eval(z, z.x1);
+                z.pc = PC_RB1;
+                return;
+            case PC_RB1: case PC_RB3: case PC_RBX1: case PC_RBX3: {
+                double dfdx;
+                int ierr;
+                const double y = root_value(z, e, kap, dfdx, ierr);
+                if (z.pc == PC_RB1 || z.pc == PC_RBX1) z.y1 = y; else z.y3 = y;
+                if (ierr != 0) { z.d_ierr = ierr; z.pc = -1; break; }
+                if (z.pc == PC_RB1) { request_root_eval(z, z.x3); z.pc = PC_RB3; return; }
+                if (z.pc == PC_RB3) z.it = 0; else ++z.it;
+                z.pc = PC_RBCHECK;
+                break;
+            }
+            case PC_RBCHECK: {
+                if (z.it >= z.imax || !(z.y1 * z.y3 > 0.0)) {
+                    if (z.y1 * z.y3 <= 0.0) { z.pc = PC_RSTART; break; }
+                    z.d_ierr = -1; z.pc = -1;
+                    break;
+                }
+                z.dx = 2.0 * z.dx;
+                if (fabs(z.y1) < fabs(z.y3)) {
+                    z.x3 = z.x1; z.y3 = z.y1;
+                    z.x1 = z.x1 - z.dx;
+                    request_root_eval(z, z.x1);
+                    z.pc = PC_RBX1;
+                } else {
+                    z.x1 = z.x3; z.y1 = z.y3;
+                    z.x3 = z.x3 + z.dx;
+                    request_root_eval(z, z.x3);
+                    z.pc = PC_RBX3;
+                }
+                return;
+            }
+            // ---- safe_root_with_initial_guess
+            case PC_RSTART: {
+                double xr;
+                bool have = false;
+                if (z.y1 == 0.0) { xr = z.x1; have = true; }
+                else if (z.y3 == 0.0) { xr = z.x3; have = true; }
+                if (have) { z.x = xr; z.pc = -2; break; }
+                z.x = z.xg;
+                if (!(z.x > z.x1 && z.x < z.x3)) z.x = 0.5 * (z.x1 + z.x3);
+                z.it = 0;
+                request_root_eval(z, z.x);
+                z.pc = PC_RIT;
+                return;
+            }
+            case PC_RIT: {
+                double dfdx;
+                int ierr;
+                const double y = root_value(z, e, kap, dfdx, ierr);
+                if (ierr != 0) { z.d_ierr = ierr; z.pc = -1; break; }
+                if (fabs(y) <= z.epsy) { z.pc = -2; break; }
+                if ((y > 0.0) == (z.y1 > 0.0)) { z.x1 = z.x; z.y1 = y; } else { z.x3 = z.x; z.y3 = y; }
+                double xn = 0.5 * (z.x1 + z.x3);
+                if (dfdx != 0.0) {
+                    const double xt = z.x - y / dfdx;
+                    if (xt > z.x1 && xt < z.x3) xn = xt;
+                }
+                if (fabs(xn - z.x) <= z.epsx) { z.x = xn; z.pc = -2; break; }
+                z.x = xn;
+                ++z.it;
+                if (z.it >= z.imax) { z.d_ierr = -1; z.pc = -1; break; }
+                request_root_eval(z, z.x);
+                return;
+            }
+            case -1:   // the root finder failed with z.d_ierr
+                if (z.which == 0) {   // bc09.f:349-366: fall-back photosphere, then the failure is raised
+                    z.P_ph = 2.0 * onethird * arad * dsd::ipow<4>(z.Teff); z.rho_ph = dsm::exp(z.xg); z.kappa_ph = z.kappa;
+                    lane_fail(z, z.d_ierr);
+                    return;
+                }
+                z.d_val = 0.0;
+                z.pc = PC_DOP_GOT;   // deriv returns ierr /= 0
+                break;
+            case -2:   // the root finder returned z.x
+                if (z.which == 0) {   // P and kappa at the returned root itself
+                    z.lnrho_ph = z.x;
+                    request_root_eval(z, z.x);
+                    z.pc = PC_PH_FINAL;
+                    return;
+                }
+                z.pc = PC_DERIV_ROOTED;
+                break;
+            case PC_PH_FINAL: {   // do_integrate_bc09_atm, bc09.f:179-225
+                double dfdx;
+                int ierr;
+                root_value(z, e, kap, dfdx, ierr);
+                z.P_ph = z.pres; z.rho_ph = dsm::exp(z.lnrho_ph); z.kappa_ph = z.kappa;
+                z.rho = z.rho_ph; z.temp = z.Teff;
+                const double lnP = dsm::log(z.P_ph);
+                double lnPend = fmax(ln10 * (z.lgy_light + z.lg_grav), lnP + ln10);
+                lnPend = fmin(lnPend, ln10 * (z.lgyb + z.lg_grav));
+                z.layer = 0;
+                dop_start(z, lnP, 0.0, lnPend);
+                deriv_call(z, a, z.X, z.Y);
+                break;
+            }
+            // ---- get_coefficients after the density inversion
+            case PC_DERIV_ROOTED:
+                z.d_rho = dsm::exp(z.x);
+                z.q_rho = z.d_rho; z.q_T = z.d_T; z.q_opac = true;
+                ++z.n_eos;
+                z.pc = PC_DERIV_FINAL;
+                return;
+            case PC_DERIV_FINAL: {
+                if (!(fabs(dsm::exp(e.lnP) - z.d_P) < 1.0e-3 * z.d_P)) { z.d_ierr = -10; z.d_val = 0.0; z.pc = PC_DOP_GOT; break; }   // bc09.f:536
+                const double v = 0.75 * kap * z.d_P / z.grav / dsm::exp(z.d_lnT4);
+                z.d_val = fmin(v, 4.0 * e.grad_ad);
+                z.rho = z.d_rho;   // the new anchor point (bc09.f:481)
+                z.d_ierr = 0;
+                z.pc = PC_DOP_GOT;
+                break;
+            }
+            // ---- dop853 (Hairer, Norsett & Wanner; MESA num_lib): one equation, scalar tolerances, h0 = 1e-3.  A failing
+            // right-hand side ("retry with smaller timestep", bc09.f:458) rejects the step with the largest reduction.
+            case PC_DOP_GOT: {
+                if (z.stage == 0) {
+                    if (z.d_ierr != 0) { lane_fail(z, -5); return; }
+                    z.k[0] = z.d_val;
+                    z.h = 0.001;
+                    z.pc = PC_STEP_BEGIN;
+                    break;
+                }
+                if (z.d_ierr != 0) {
+                    z.h = z.h / facc1;
+                    z.reject = true;
+                    z.last = false;
+                    z.pc = PC_STEP_BEGIN;
+                    break;
+                }
+                if (z.stage < 12) {
+                    z.k[z.stage] = z.d_val;
+                    ++z.stage;
+                    z.pc = (z.stage < 12) ? PC_STAGE_ISSUE : PC_STEP_ERR;
+                    break;
+                }
+                // accepted step
+                z.facold = fmax(z.err, 1.0e-4);
+                z.k[0] = z.d_val;
+                z.Y = z.ynew;
+                z.X = z.xph;
+                if (z.last) { z.pc = PC_LAYER_DONE; break; }
+                double hnew = z.hnew;
+                if (fabs(hnew) > z.hmax) hnew = z.posneg * z.hmax;
+                if (z.reject) hnew = z.posneg * fmin(fabs(hnew), fabs(z.h));
+                z.reject = false;
+                z.h = hnew;
+                z.pc = PC_STEP_BEGIN;
+                break;
+            }
+            case PC_STEP_BEGIN:
+                if (z.nstep > 10000) { lane_fail(z, -2); return; }
+                if (0.1 * fabs(z.h) <= fabs(z.X) * uround) { lane_fail(z, -3); return; }
+                if ((z.X + 1.01 * z.h - z.xend) * z.posneg > 0.0) { z.h = z.xend - z.X; z.last = true; }
+                ++z.nstep;
+                z.stage = 1;
+                z.pc = PC_STAGE_ISSUE;
+                break;
+            case PC_STAGE_ISSUE: {
+                const int s = z.stage;
+                double acc = 0.0;
+                for (int j = 0; j < s; ++j) {
+                    const double aa = dop_a[s][j];
+                    if (aa != 0.0) acc += aa * z.k[j];
+                }
+                deriv_call(z, a, z.X + dop_c[s] * z.h, z.Y + z.h * acc);
+                break;
+            }
+            case PC_STEP_ERR: {
+                const double h = z.h, y = z.Y;
+                z.xph = z.X + h;
+                double k4 = 0.0;
+                for (int j = 0; j < 12; ++j)
+                    if (dop_b[j] != 0.0) k4 += dop_b[j] * z.k[j];
+                z.ynew = y + h * k4;
+                const double sk = 1.0e-6 + 1.0e-6 * fmax(fabs(y), fabs(z.ynew));
+                double e3 = 0.0, e5 = 0.0;
+                for (int j = 0; j < 12; ++j) {
+                    if (dop_e3[j] != 0.0) e3 += dop_e3[j] * z.k[j];
+                    if (dop_e5[j] != 0.0) e5 += dop_e5[j] * z.k[j];
+                }
+                const double err2 = (e3 / sk) * (e3 / sk);
+                double err = (e5 / sk) * (e5 / sk);
+                double deno = err + 0.01 * err2;
+                if (deno <= 0.0) deno = 1.0;
+                err = fabs(h) * err * sqrt(1.0 / (1 * deno));
+                const double fac11 = dsm::pow(err, 1.0 / 8.0);
+                double fac = fac11 / dsm::pow(z.facold, 0.0);
+                fac = fmax(facc2, fmin(facc1, fac / safe));
+                z.err = err;
+                z.hnew = h / fac;
+                if (err <= 1.0) {
+                    z.stage = 12;
+                    deriv_call(z, a, z.xph, z.ynew);
+                } else {
+                    z.h = h / fmin(facc1, fac11 / safe);
+                    z.reject = true;
+                    z.last = false;
+                    z.pc = PC_STEP_BEGIN;
+                }
+                break;
+            }
+            case PC_LAYER_DONE: {
+                if (z.layer == 0) {   // the heavy layer, bc09.f:227-265
+                    z.L = &a.layer[1];
+                    z.layer = 1;
+                    const double lnPend = ln10 * (z.lgyb + z.lg_grav);
+                    if (z.X < lnPend) {
+                        dop_start(z, z.X, z.Y, lnPend);
+                        deriv_call(z, a, z.X, z.Y);
+                        break;
+                    }
+                }
+                z.lgTb = 0.25 * z.Y / ln10 + z.lgTeff;
+                z.ierr = 0;
+                z.done = true;
+                return;
+            }
         }
-        if (failed) {
-            h = h / facc1;
-            reject = true;
-            last = false;
-            continue;
-        }
-        const double xph = x + h;
-        double k4 = 0.0;
-        for (int j = 0; j < 12; ++j)
-            if (dop_b[j] != 0.0) k4 += dop_b[j] * k[j];
-        const double ynew = y + h * k4;
-        const double sk = atol + rtol * fmax(fabs(y), fabs(ynew));
-        double e3 = 0.0, e5 = 0.0;
-        for (int j = 0; j < 12; ++j) {
-            if (dop_e3[j] != 0.0) e3 += dop_e3[j] * k[j];
-            if (dop_e5[j] != 0.0) e5 += dop_e5[j] * k[j];
-        }
-        const double err2 = (e3 / sk) * (e3 / sk);
-        double err = (e5 / sk) * (e5 / sk);
-        double deno = err + 0.01 * err2;
-        if (deno <= 0.0) deno = 1.0;
-        err = fabs(h) * err * sqrt(1.0 / (1 * deno));
-        const double fac11 = dsm::pow(err, 1.0 / 8.0);
-        double fac = fac11 / dsm::pow(facold, 0.0);
-        fac = fmax(facc2, fmin(facc1, fac / safe));
-        double hnew = h / fac;
-        if (err <= 1.0 && deriv(p, xph, ynew, k[12]) != 0) {   // the new point itself cannot be evaluated
-            h = h / facc1;
-            reject = true;
-            last = false;
-            continue;
-        }
-        if (err <= 1.0) {
-            facold = fmax(err, 1.0e-4);
-            k[0] = k[12];
-            y = ynew;
-            x = xph;
-            if (last) { idid = 1; break; }
-            if (fabs(hnew) > hmax) hnew = posneg * hmax;
-            if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
-            reject = false;
-        } else {
-            hnew = h / fmin(facc1, fac11 / safe);
-            reject = true;
-            last = false;
-        }
-        h = hnew;
     }
-    return idid;
-}
-
-// find_photospheric_pressure (bc09.f:284-371) with the ideal-gas + Thomson first guess (:322-333)
-DS_D int find_photospheric_pressure(Par& p, double& rho_ph, double& P_ph, double& kappa) {
-    const double Teff = p.Teff;
-    const double fallback_Pphoto = 2.0 * onethird * arad * dsd::ipow<4>(Teff);
-    const double kappa_Th = Thomson * avogadro * p.L->c.Ye;
-    const double eps_ph = p.a->tol_photosphere_condition * p.tau * p.grav / kappa_Th;
-    const double Pgas = p.tau * p.grav / kappa_Th - onethird * arad * dsd::ipow<4>(Teff);
-    if (Pgas < 0.0) { P_ph = fallback_Pphoto; kappa = kappa_Th; return -2; }
-    const double lnrho_guess = dsm::log(Pgas * amu * p.L->c.A / (p.L->c.Z + 1.0) / boltzmann / Teff);
-    double x1, x3, y1, y3;
-    int ierr = look_for_brackets<0>(p, lnrho_guess, 0.1, x1, x3, y1, y3, p.a->max_iter_photosphere);
-    if (ierr != 0) { P_ph = fallback_Pphoto; rho_ph = dsm::exp(lnrho_guess); kappa = p.kappa; return ierr; }
-    const double lnrho_ph = safe_root<0>(p, lnrho_guess, x1, x3, y1, y3, p.a->max_iter_photosphere,
-                                         p.a->tol_photosphere_lnrho, eps_ph, ierr);
-    if (ierr != 0) { P_ph = fallback_Pphoto; rho_ph = dsm::exp(lnrho_guess); kappa = p.kappa; return ierr; }
-    double dummy;
-    root_fn<0>(p, lnrho_ph, dummy, ierr);
-    P_ph = p.pres;
-    rho_ph = dsm::exp(lnrho_ph);
-    kappa = p.kappa;
-    return 0;
-}
-
-// do_integrate_bc09_atm (bc09.f:97-282)
-DS_D int integrate_bc09_atm(Par& p, double lgyb, double lgy_light, double lgTeff, double& lgTb, double* info) {
-    p.Teff = dsd::dexp10(lgTeff);
-    p.tau = twothird;
-    p.L = &p.a->layer[0];
-    double rho = -1.0, P = 0.0, kappa = 0.0;
-    int ierr = find_photospheric_pressure(p, rho, P, kappa);
-    if (info) { info[0] = rho; info[1] = P; info[2] = kappa; }
-    if (ierr != 0) return ierr;
-    p.rho = rho; p.temp = p.Teff; p.pres = P; p.kappa = kappa;
-    double lnP = dsm::log(P);
-    double lnT4 = 0.0;
-    const double lg_grav = dsm::log10(p.grav);
-    double lnPend = fmax(ln10 * (lgy_light + lg_grav), lnP + ln10);
-    lnPend = fmin(lnPend, ln10 * (lgyb + lg_grav));
-    int idid = dop853_scalar(p, lnP, lnT4, lnPend, 0.001, 10000, 1.0e-6, 1.0e-6);
-    if (idid < 0) return idid;
-    p.L = &p.a->layer[1];
-    lnPend = ln10 * (lgyb + lg_grav);
-    if (lnP < lnPend) {
-        idid = dop853_scalar(p, lnP, lnT4, lnPend, 0.001, 10000, 1.0e-6, 1.0e-6);
-        if (idid < 0) return idid;
-    }
-    lgTb = 0.25 * lnT4 / ln10 + lgTeff;
-    return 0;
 }
 }  // namespace dsa
 
 // thread = (table, knot); 32-thread CTAs so that the 8 warps of one table land on 8 different SMs
 __global__ void __launch_bounds__(32) ds_bc09_kernel(DsBc09Args a, DsHelmDev helm) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= a.n_tab * a.nv) return;
-    const int t = gid / a.nv, i = gid % a.nv;
-    dsa::Par p;
-    p.helm = &helm;
-    p.a = &a;
-    p.grav = a.grav[t];
-    p.n_eos = 0;
-    const double lgyb = dsm::log10(a.Pb[t] / p.grav);
-    const double lgy_light = dsm::log10(a.Plight[t] / p.grav);
-    double lgTb = 0.0;
-    double* info = a.info ? a.info + (size_t)4 * gid : nullptr;
-    const int ierr = dsa::integrate_bc09_atm(p, lgyb, lgy_light, a.lgTeff[i], lgTb, info);
-    if (info) info[3] = (double)p.n_eos;
-    a.lgTb[gid] = lgTb;
-    a.ierr[gid] = ierr;
+    dsa::Lane z;
+    z.done = gid >= a.n_tab * a.nv;
+    z.ierr = 0; z.n_eos = 0; z.lgTb = 0.0;
+    z.rho_ph = z.P_ph = z.kappa_ph = 0.0;
+    dsa::EosOut e{};
+    if (!z.done) {
+        const int t = gid / a.nv, i = gid % a.nv;
+        z.grav = a.grav[t];
+        z.lgTeff = a.lgTeff[i];
+        z.lgyb = dsm::log10(a.Pb[t] / z.grav);
+        z.lgy_light = dsm::log10(a.Plight[t] / z.grav);
+        z.lg_grav = dsm::log10(z.grav);
+        z.pc = dsa::PC_PH_START;
+        dsa::advance(z, a, e, 0.0);
+    }
+    while (__any_sync(0xffffffffu, !z.done)) {   // all 32 lanes arrive here together, every trip
+        if (!z.done) {
+            dsa::eos_point(helm, a.eos, *z.L, z.q_rho, z.q_T, e);
+            double kap = 0.0;
+            if (z.q_opac) kap = dsa::opacity_point(a.cond, *z.L, z.q_rho, z.q_T, e);
+            dsa::advance(z, a, e, kap);
+        }
+    }
+    if (gid < a.n_tab * a.nv) {
+        if (a.info) {
+            double* info = a.info + (size_t)4 * gid;
+            info[0] = z.rho_ph; info[1] = z.P_ph; info[2] = z.kappa_ph; info[3] = (double)z.n_eos;
+        }
+        a.lgTb[gid] = z.lgTb;
+        a.ierr[gid] = z.ierr;
+    }
 }
