@@ -13,8 +13,12 @@
 #include "../../include/dstar_b200.h"
 #include "atm_launch.hpp"
 #include "kernels_evolve.cuh"
+#include "kernels_evolve_warp.cuh"
 #include "kernels_micro.cuh"
 #include "kernels_test.cuh"
+
+constexpr int DS_N_EVOLVE_CLASS = 6;
+constexpr int DS_EVOLVE_Z[DS_N_EVOLVE_CLASS] = {2, 4, 6, 8, 9, 10};   // zones per lane: nz <= 64, 128, 192, 256, 288, 320
 
 namespace {
 thread_local std::string g_err;
@@ -94,6 +98,11 @@ struct dstar_batch {
     size_t stage_bytes = 0;
     double ms[3] = {0, 0, 0};
     int launches = 0;
+    // evolve launch plan: stars grouped by zones-per-lane class of the warp kernel (kernels_evolve_warp.cuh); the last
+    // entry (Z = 0) is the CTA-per-star fallback for stars with more than 320 zones
+    struct EvolveClass { int Z = 0, count = 0, max_nz = 0; DevBuf<int> list; };
+    EvolveClass ev_class[DS_N_EVOLVE_CLASS + 1];
+    int evolve_mapping = 0;   // dstar_batch_set_evolve_mapping: 0 = automatic, 1 = CTA per star, 2 = warp per star
 };
 
 namespace {
@@ -120,29 +129,35 @@ void fill_host_consts(DsHostConsts& h) {
     h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
 }
 template <bool FACE, int G>
-void launch_micro_g(int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+cudaError_t launch_micro_g(int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+    static_assert(16 + DS_PRE + DS_HZ + DS_CP <= DS_NTAB, "the prologue fetches the zone-level inputs with one lane each");
     const int grid = std::min(sms, (total + G - 1) / G);
     const size_t dyn = (size_t)G * DS_YMAX * sizeof(double);   // per-group abundances (kernels_micro.cuh: s_Y)
-    static bool once = [] {   // static + dynamic shared memory exceed 48 KB: opt in
-        const int bytes = (int)((size_t)G * DS_YMAX * sizeof(double));
-        cudaFuncSetAttribute(ds_micro_kernel<true, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        cudaFuncSetAttribute(ds_micro_kernel<false, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        cudaFuncSetAttribute(ds_micro_kernel<false, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        return true;
-    }();
-    (void)once;
+    // static + dynamic shared memory exceed 48 KB: opt in, once per DEVICE (the attribute is per device and one process
+    // may hold contexts on several)
+    static bool once[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!once[dev & 63]) {
+        if ((e = cudaFuncSetAttribute(ds_micro_kernel<true, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ds_micro_kernel<false, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ds_micro_kernel<false, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        once[dev & 63] = true;
+    }
     if (FACE) {  // one plain pass (a.redo must be null)
         ds_micro_kernel<true, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
     } else {     // branch-free pass, then the plain pass over the zones it flagged (normally none)
         ds_micro_kernel<false, G, true><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
         ds_micro_kernel<false, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
     }
+    return cudaGetLastError();
 }
 template <bool FACE>
-void launch_micro(int G, int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+cudaError_t launch_micro(int G, int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
     switch (G) {
-        case 6: launch_micro_g<FACE, 6>(sms, total, s, a, h, sf); break;
-        default: launch_micro_g<FACE, 7>(sms, total, s, a, h, sf); break;
+        case 6: return launch_micro_g<FACE, 6>(sms, total, s, a, h, sf);
+        default: return launch_micro_g<FACE, 7>(sms, total, s, a, h, sf);
     }
 }
 int micro_minb() {  // zone groups (of 128 lanes) per persistent CTA: 7 (default, 72 regs) or 6 (80 regs).
@@ -171,11 +186,31 @@ DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
     }
     return k;
 }
+// warp-per-star evolve kernel for one zones-per-lane class: one star per 32-thread CTA, as many CTAs per SM as their
+// shared memory allows (6 at Z = 8), so a small batch still spreads over all SMs
+template <int Z>
+cudaError_t launch_evolve_warp(const DsEvolveArgs& a, const int* list, int count, cudaStream_t s) {
+    constexpr int S = 1;
+    const size_t bytes = (DS_NTAB + (size_t)S * dsw::Lay<Z>::TOTAL) * sizeof(double);
+    static bool once[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!once[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(ds_evolve_warp_kernel<Z, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        once[dev & 63] = true;
+    }
+    ds_evolve_warp_kernel<Z, S><<<(count + S - 1) / S, 32 * S, bytes, s>>>(a, list, count);
+    return cudaGetLastError();
+}
 }  // namespace
+
+static int g_force_redo = 0;
 
 extern "C" {
 
 const char* dstar_last_error(void) { return g_err.c_str(); }
+void dstar_debug_force_redo(int on) { g_force_redo = on ? 1 : 0; }
 
 // Local-memory window of the device.  The coefficient kernels keep ~0.7 KB of spill frame per thread, and the frames
 // of all resident threads (~90 MB) cycle through L2.  How they map onto L2 depends on the per-thread window the driver
@@ -494,6 +529,22 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(b->status.alloc(n_star)); CK(cudaMemsetAsync(b->status.p, 0, n_star * sizeof(int), st));
     CK(b->redo.alloc(b->total)); CK(b->redo_count.alloc(1));
     CK(b->rho_bar1.alloc(n_star));
+    {   // evolve launch plan (see dstar_batch::ev_class)
+        std::vector<int> lists[DS_N_EVOLVE_CLASS + 1];
+        for (int s = 0; s < n_star; ++s) {
+            const int nz = zone_offset[s + 1] - zone_offset[s];
+            int cls = DS_N_EVOLVE_CLASS;
+            for (int q = 0; q < DS_N_EVOLVE_CLASS; ++q)
+                if (nz <= 32 * DS_EVOLVE_Z[q]) { cls = q; break; }
+            lists[cls].push_back(s);
+            b->ev_class[cls].max_nz = std::max(b->ev_class[cls].max_nz, nz);
+        }
+        for (int q = 0; q <= DS_N_EVOLVE_CLASS; ++q) {
+            b->ev_class[q].Z = q < DS_N_EVOLVE_CLASS ? DS_EVOLVE_Z[q] : 0;
+            b->ev_class[q].count = (int)lists[q].size();
+            if (!lists[q].empty()) CK(b->ev_class[q].list.upload(lists[q].data(), lists[q].size(), st));
+        }
+    }
     CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
     CK(cudaEventCreate(&b->ev2)); CK(cudaEventCreate(&b->ev3));
     CK(cudaEventCreateWithFlags(&b->ev_face_in, cudaEventDisableTiming));
@@ -627,8 +678,8 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             a.redo = b->redo.p; a.redo_count = b->redo_count.p;
             ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
             CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
-            { const char* e = std::getenv("DSTAR_FORCE_REDO"); a.force_redo = (e && e[0] == '1') ? 1 : 0; }  // test hook
-            launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
+            a.force_redo = g_force_redo;   // test hook (dstar_debug_force_redo)
+            CK(launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf));
             ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
         }
         CK(cudaGetLastError());
@@ -642,7 +693,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             a.redo = nullptr; a.redo_count = nullptr;
             CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
             ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
-            launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf);
+            CK(launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev3, s));
@@ -745,6 +796,13 @@ int dstar_batch_reset_state(dstar_batch* b) {
     return DSTAR_OK;
 }
 
+int dstar_batch_set_evolve_mapping(dstar_batch* b, int mapping) {
+    if (!b) return fail(DSTAR_ERR_ARG, "batch == NULL");
+    if (mapping < 0 || mapping > 2) return fail(DSTAR_ERR_ARG, "evolve mapping: 0 automatic, 1 CTA per star, 2 warp per star");
+    b->evolve_mapping = mapping;
+    return DSTAR_OK;
+}
+
 int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
     if (!b || !ctrl) return fail(DSTAR_ERR_ARG, "batch_evolve");
     if (!b->have_evolve || !b->have_tables) return fail(DSTAR_ERR_STATE, "evolve inputs / tables missing");
@@ -790,15 +848,42 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     // (the evolve kernel never reads face 0's rho_bar, L(1) comes from the atmosphere; kept for symmetry)
     CK(cudaStreamWaitEvent(s, b->ev_evolve_in, 0));   // evolve inputs were uploaded on the copy stream
     CK(cudaEventRecord(b->ev0, s));
-    const int threads = ((b->max_nz + 31) / 32) * 32;
-    if (threads <= 256) ds_evolve_kernel<256><<<b->n_star, threads, 0, s>>>(a);
-    else ds_evolve_kernel<512><<<b->n_star, threads, 0, s>>>(a);
-    CK(cudaGetLastError());
+    int launches = 0;
+    // Mapping (dstar_batch_set_evolve_mapping).  Measured on B200 (profiles/r02_notes.md, r02d): the CTA-per-star form
+    // is faster at every batch size tried (64 / 256 / 1024 stars of 253 zones: 2.2 / 2.6 / 9.6 ms against 6.6 / 10.2 /
+    // 17.6 ms), so "automatic" is the CTA form; the warp form stays selectable.
+    const bool warp_form = b->evolve_mapping == 2;
+    if (!warp_form) {
+        const int threads = ((b->max_nz + 31) / 32) * 32;
+        if (threads <= 256) ds_evolve_kernel<256><<<b->n_star, threads, 0, s>>>(a, nullptr);
+        else ds_evolve_kernel<512><<<b->n_star, threads, 0, s>>>(a, nullptr);
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    for (int q = 0; warp_form && q <= DS_N_EVOLVE_CLASS; ++q) {
+        const dstar_batch::EvolveClass& ec = b->ev_class[q];
+        if (ec.count == 0) continue;
+        switch (ec.Z) {
+            case 2: CK(launch_evolve_warp<2>(a, ec.list.p, ec.count, s)); break;
+            case 4: CK(launch_evolve_warp<4>(a, ec.list.p, ec.count, s)); break;
+            case 6: CK(launch_evolve_warp<6>(a, ec.list.p, ec.count, s)); break;
+            case 8: CK(launch_evolve_warp<8>(a, ec.list.p, ec.count, s)); break;
+            case 9: CK(launch_evolve_warp<9>(a, ec.list.p, ec.count, s)); break;
+            case 10: CK(launch_evolve_warp<10>(a, ec.list.p, ec.count, s)); break;
+            default: {   // more than 320 zones: CTA-per-star form
+                const int threads = ((ec.max_nz + 31) / 32) * 32;
+                if (threads <= 256) ds_evolve_kernel<256><<<ec.count, threads, 0, s>>>(a, ec.list.p);
+                else ds_evolve_kernel<512><<<ec.count, threads, 0, s>>>(a, ec.list.p);
+            }
+        }
+        CK(cudaGetLastError());
+        ++launches;
+    }
     CK(cudaEventRecord(b->ev1, s));
     CK(cudaEventSynchronize(b->ev1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[2] = ms;
     CK(cudaEventRecord(b->ev_busy, s));
-    b->launches = 1;
+    b->launches = launches;
     return DSTAR_OK;
 }
 

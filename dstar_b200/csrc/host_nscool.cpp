@@ -951,6 +951,47 @@ dstar_evolve_ctrl evolve_ctrl_of(const Controls& c) {
     return e;
 }
 
+// The coefficient pass and the evolve kernel take these settings once per batch (kernel arguments), and the gap tables
+// and their scales live in the context: a batch whose stars disagree on any of them is refused, as it is for the
+// nuclide network.  (Per-star quantities -- core temperature, Qimp, heating windows, epochs, atmosphere -- are arrays.)
+int check_batch_controls(const std::vector<Star*>& ss, bool micro, bool evolve) {
+    const Controls& c0 = ss[0]->c;
+    const dstar_micro_ctrl m0 = micro_ctrl_of(c0);
+    const dstar_evolve_ctrl e0 = evolve_ctrl_of(c0);
+    for (size_t i = 1; i < ss.size(); ++i) {
+        const Controls& c = ss[i]->c;
+        if (micro) {
+            const dstar_micro_ctrl m = micro_ctrl_of(c);
+            if (std::memcmp(&m, &m0, sizeof m) != 0) {
+                g_err = "stars of one batch must share the EOS, conductivity and neutrino controls (differs in star " + std::to_string(i + 1) + ")";
+                return -1;
+            }
+            if (c.which_proton_1S0_gap != c0.which_proton_1S0_gap || c.which_neutron_1S0_gap != c0.which_neutron_1S0_gap ||
+                c.which_neutron_3P2_gap != c0.which_neutron_3P2_gap ||
+                c.scale_sf_critical_temperatures != c0.scale_sf_critical_temperatures) {
+                g_err = "stars of one batch must share the superfluid gap tables and their scale factors (differs in star " +
+                        std::to_string(i + 1) + "); per-star critical temperatures go through other_sf_get_results";
+                return -1;
+            }
+        }
+        if (evolve) {
+            const dstar_evolve_ctrl e = evolve_ctrl_of(c);
+            if (std::memcmp(&e, &e0, sizeof e) != 0) {
+                g_err = "stars of one batch must share the integration and boundary controls (differs in star " + std::to_string(i + 1) + ")";
+                return -1;
+            }
+            if (c.trace_capacity != c0.trace_capacity || c.profile_capacity != c0.profile_capacity ||
+                c.write_interval_for_profile != c0.write_interval_for_profile) {
+                g_err = "stars of one batch must share the history/profile capture settings";
+                return -1;
+            }
+        }
+    }
+    return 0;
+}
+
+int g_evolve_mapping = 0;   // dstar_NScool_set_evolve_mapping
+
 // cached device batch shared by create_models -> evolve_models on the same id list
 struct BatchCache {
     std::vector<int> ids;
@@ -1080,6 +1121,7 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
     std::vector<Star*> ss;
     for (int i = 0; i < n; ++i) { Star* s = get(ids[i]); if (!s || !s->setup) { g_err = "bad NScool id"; return -1; } ss.push_back(s); }
     g_batch.clear();
+    if (n > 1 && check_batch_controls(ss, true, false) != 0) return -1;
     // store_controls: epochs (NScool_ctrls_io.f:244-256), startup microphysics, zones
     for (Star* s : ss) {
         Controls& c = s->c;
@@ -1208,6 +1250,7 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     for (int i = 0; i < n; ++i) { Star* s = get(ids[i]); if (!s || !s->created) { g_err = "model not created"; return -1; } ss.push_back(s); }
     const int ne = ss[0]->number_epochs;
     for (Star* s : ss) if (s->number_epochs != ne) { g_err = "stars of one batch must have the same number of epochs"; return -1; }
+    if (n > 1 && check_batch_controls(ss, false, true) != 0) return -1;
     std::vector<int32_t> zoff(n + 1, 0);
     for (int i = 0; i < n; ++i) zoff[i + 1] = zoff[i] + ss[i]->nz;
     const int total = zoff[n];
@@ -1261,6 +1304,7 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     if (pcap < 0) pcap = (n <= 64) ? 512 : 0;
     const int pint = std::max(1, ss[0]->c.write_interval_for_profile);
     if (rc == 0) rc = dstar_batch_set_profile_capture(b, pcap > 0 ? pint : 0, pcap);
+    if (rc == 0) rc = dstar_batch_set_evolve_mapping(b, g_evolve_mapping);
     if (rc == 0) rc = dstar_batch_evolve(b, &ec, cap);
     if (rc == 0) g_ms[2] = dstar_batch_last_kernel_ms(b, 2);
     std::vector<double> tm((size_t)ne * n), Tm(tm.size()), Qm(tm.size()), lnT(total), Teff(n), Lsurf(n), dt(n), tsec(n);
@@ -1323,6 +1367,12 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
 }
 
 int dstar_NScool_evolve_model(int id) { int32_t i = id; return dstar_NScool_evolve_models(1, &i); }
+
+int dstar_NScool_set_evolve_mapping(int mapping) {
+    if (mapping < 0 || mapping > 2) { g_err = "evolve mapping: 0 automatic, 1 CTA per star, 2 warp per star"; return -1; }
+    g_evolve_mapping = mapping;
+    return 0;
+}
 
 int dstar_NScool_get_int(int id, const char* name, int32_t* v) {
     Star* s = get(id);

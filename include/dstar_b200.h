@@ -162,6 +162,11 @@ int dstar_batch_reset_state(dstar_batch* b);
 /* seam B: every star through all its epochs in ONE launch.  trace_cap > 0 keeps that many
  * history rows per star. */
 int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap);
+/* thread mapping of seam B: 0 = automatic (default), 1 = one CTA per star, one thread per zone, cyclic reduction through
+ * shared memory (any nz <= 512), 2 = one warp per star, nz/32 zones per lane, partitioned solve with cyclic reduction
+ * over warp shuffles (nz <= 320; larger stars fall back to 1).  Same formulas and driver, so the same light curves;
+ * the CTA form is the faster one on B200 at every batch size measured (profiles/r02_notes.md) and is what 0 selects. */
+int dstar_batch_set_evolve_mapping(dstar_batch* b, int mapping);
 /* D2H: monitors (n_epoch,n_star) as NScool_def.f:136-144; idid (n_epoch,n_star); counters (7,n_star) =
  * nfcn, njac, nstep, naccpt, nrejct, ndec, nsol (isolve iwork(14:20)); lnT(total_zones); Teff, Lsurf,
  * dt, tsec (n_star); model(n_star).  Any pointer may be NULL. */
@@ -197,6 +202,9 @@ int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, i
  * 5 cos, 6 sinh, 7 cosh, 8 atan; 9-13 exercise the branch-free division and square root of dconst.cuh); dsmath is the deterministic elementary-function layer that plays the
  * role of MESA's math_lib for this implementation (dstar_b200/csrc/dsmath.cuh) ---- */
 int dstar_dsmath_eval(dstar_ctx* ctx, int fn, int n, const double* x, const double* y, double* out);
+/* test support: send every zone of the cell loop through the plain-division second pass as well (the pass that normally
+ * re-evaluates only the zones whose branch-free divisions left their safe operand range) */
+void dstar_debug_force_redo(int on);
 
 /* ---- measurement helpers ---- */
 /* FP64 DFMA-chain throughput of the device in TFLOP/s (the FP64 roofline denominator) */

@@ -51,6 +51,9 @@ int dstar_NScool_evolve_model(int id);
  * one evolve launch for all of them */
 int dstar_NScool_create_models(int n, const int32_t* ids);
 int dstar_NScool_evolve_models(int n, const int32_t* ids);
+/* thread mapping of the evolve kernel for the following evolve calls (dstar_batch_set_evolve_mapping, dstar_b200.h):
+ * 0 automatic, 1 CTA per star, 2 warp per star.  Not a reference control: the results do not depend on it. */
+int dstar_NScool_set_evolve_mapping(int mapping);
 /* hooks (NScool_def.f:148-155), evaluated on the host before upload:
  *   other_set_Qimp(id): may rewrite ionic_bar%Q via dstar_NScool_set_zone_array(id,"Qimp_bar",...)
  *   other_sf_get_results(id,kp,kn,Tc): called per zone for cells and faces */

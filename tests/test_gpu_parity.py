@@ -64,7 +64,7 @@ def rel(a, b):
 
 def test_device_present(ctx):
     info = ctx.device_info()
-    assert info["cc"][0] >= 9, info
+    assert info["cc"][0] == 10, info   # the library is built for sm_100a only
     tf = ctx.fp64_peak_tflops()
     assert tf > 1.0, tf
 
@@ -83,6 +83,7 @@ def test_eos_parity(ctx, oracle):
     ie_g, res_g, ph_g, chi_g = ctx.eval_crust_eos(rho, T, ionic, NET_Z, NET_A, Yion, Tcs)
     assert ie_o == 0 and not ie_g.any()
     assert np.array_equal(ph_o, ph_g)
+    assert rel(chi_g, chi_o) < 1e-13 and rel(chi_g, chi) < 1e-12   # nuclear volume fraction (dStar_eos_lib.f:123 out arg)
     names = ["lnP", "lnE", "lnS", "grad_ad", "chiRho", "chiT", "Cp", "Cv", "Chi", "Gamma", "Theta", "mu_e", "mu_n",
              "Gamma1", "Gamma3"]
     worst = {}
@@ -239,6 +240,40 @@ def test_evolve_batch_matches_single_and_oracle(nscool, oracle):
         s.free()
 
 
+def test_evolve_warp_mapping_matches_cta_mapping(nscool, oracle):
+    """The warp-per-star form of the evolve kernel (zones in registers, partitioned solve with cyclic reduction over
+    warp shuffles) runs the same RODASP driver on the same right-hand side as the CTA-per-star form; only the
+    elimination order of the tridiagonal solve differs, so light curves agree far below the integration tolerance and
+    the solver statistics are identical.  Ragged batch: 2, 4 and 8 zones per lane in one call."""
+    ds = nscool
+    from dstar_b200._capi import lib
+    out = {}
+    for mapping in (1, 2):
+        assert lib().dstar_NScool_set_evolve_mapping(mapping) == 0
+        try:
+            stars = [_make_star(ds, target_resolution_lnP=r, core_temperature=Tc, number_epochs=3,
+                                basic_epoch_Mdots=[2.0e17, 0.0, 0.0], basic_epoch_boundaries=[-400.0, 0.0, 100.0, 2000.0])
+                     for r, Tc in ((0.6, 5e7), (0.3, 9.2e7), (0.12, 2e8))]
+            ds.create_models(stars)
+            lnT0 = [s.array("lnT").copy() for s in stars]
+            ds.evolve_models(stars)
+            out[mapping] = [(s.monitors(), s.counters().copy(), s.array("lnT").copy(), s.get_int("nz")) for s in stars]
+            if mapping == 2:
+                ref = oracle_evolve_star(oracle, stars[2], lnT0[2], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.5, 28.5, 0.1],
+                                         T_atm=2.4e8, ctrl=dict(turn_on_extra_heating=1))
+                assert rel(stars[2].monitors()[1], ref["Teff_monitor"]) < 1e-6
+                np.testing.assert_array_equal(stars[2].counters(), ref["counters"])
+            for s in stars:
+                s.free()
+        finally:
+            lib().dstar_NScool_set_evolve_mapping(0)
+    for (m1, c1, y1, nz), (m2, c2, y2, _) in zip(out[1], out[2]):
+        assert rel(m2[1], m1[1]) < 1e-9, (nz, m1[1], m2[1])
+        assert np.max(np.abs(y1 - y2)) < 1e-9
+        np.testing.assert_array_equal(c1, c2)
+    print("zones per star:", [o[3] for o in out[1]])
+
+
 def test_crust_composition_lookup_parity(ctx, oracle):
     """north_star (b): composition lookups on a device-resident table vs dStar_crust_get_composition_info."""
     import dstar_b200 as ds
@@ -281,7 +316,7 @@ def test_call_order_errors(ctx):
 
 
 @pytest.mark.gpu
-def test_micro_tables_redo_pass_matches(nscool, monkeypatch):
+def test_micro_tables_redo_pass_matches(nscool):
     """The coefficient pass evaluates the cell EOS with branch-free divisions and re-evaluates flagged zones
     with plain IEEE divisions in a second launch; forcing every zone through that second pass must reproduce
     the tables bit for bit (the two division forms are the same arithmetic)."""
@@ -289,9 +324,13 @@ def test_micro_tables_redo_pass_matches(nscool, monkeypatch):
     s.create_model()
     ref = {k: s.array(k).copy() for k in ("tab_lnCp", "tab_lnGamma", "tab_lnEnu", "tab_lnK")}
     s.free()
-    monkeypatch.setenv("DSTAR_FORCE_REDO", "1")
-    s2 = _make_star(nscool)
-    s2.create_model()
-    for k, v in ref.items():
-        assert np.array_equal(s2.array(k).view(np.uint64), v.view(np.uint64)), k
-    s2.free()
+    from dstar_b200._capi import lib
+    lib().dstar_debug_force_redo(1)
+    try:
+        s2 = _make_star(nscool)
+        s2.create_model()
+        for k, v in ref.items():
+            assert np.array_equal(s2.array(k).view(np.uint64), v.view(np.uint64)), k
+        s2.free()
+    finally:
+        lib().dstar_debug_force_redo(0)
