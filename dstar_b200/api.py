@@ -219,6 +219,18 @@ class Batch:
         self.trace_cap = trace_cap
         check(self.L.dstar_batch_evolve(self.h, C.byref(ctrl), int(trace_cap)), "dstar_batch_evolve")
 
+    def set_evolve_mapping(self, mapping):
+        """0 automatic, 1 CTA per star, 2 warp per star (dstar_batch_set_evolve_mapping)."""
+        check(self.L.dstar_batch_set_evolve_mapping(self.h, int(mapping)), "dstar_batch_set_evolve_mapping")
+
+    def eval_rhs(self, epoch, ctrl=None):
+        """get_derivatives and the rows of get_jacobian at the batch's current ln T (dstar_batch_eval_rhs)."""
+        ctrl = ctrl or EvolveCtrl.defaults()
+        f = np.zeros(self.total); jac = np.zeros((self.total, 3)); surf = np.zeros((self.n_star, 3))
+        check(self.L.dstar_batch_eval_rhs(self.h, C.byref(ctrl), int(epoch), p(f), p(jac), p(surf)), "dstar_batch_eval_rhs")
+        return {"f": f, "lo": jac[:, 0].copy(), "di": jac[:, 1].copy(), "up": jac[:, 2].copy(), "Lsurf": surf[:, 0].copy(),
+                "dlnLsdlnT": surf[:, 1].copy(), "Teff": surf[:, 2].copy()}
+
     def download_results(self, full=True):
         ne, ns = self.n_epoch, self.n_star
         t = np.zeros((ne, ns)); Te = np.zeros((ne, ns)); Qb = np.zeros((ne, ns))
@@ -369,7 +381,21 @@ class NScool:
         return out
 
     def write_history(self, path):
-        _nerr(self.L.dstar_NScool_write_history(self.id, path.encode()), "write_history")
+        """Returns 0, or 1 when the file was truncated at the trace capacity."""
+        return _nerr(self.L.dstar_NScool_write_history(self.id, path.encode()), "write_history")
+
+    def write_terminal(self, path=None):
+        return _nerr(self.L.dstar_NScool_write_terminal(self.id, None if path is None else path.encode()), "write_terminal")
+
+    def terminal(self):
+        cap = 8192
+        model = np.zeros(cap, dtype=np.int32)
+        cols = [np.zeros(cap) for _ in range(6)]
+        n = _nerr(self.L.dstar_NScool_get_terminal(self.id, cap, p(model, ip), *[p(x) for x in cols]), "get_terminal")
+        names = ["tsec", "dt", "lgTmax", "lgP_Tmax", "lgTmin", "lgP_Tmin"]
+        out = {"model": model[:n]}
+        out.update({k: v[:n] for k, v in zip(names, cols)})
+        return out
 
     PROFILE_COLUMNS = ("zone", "mass", "dm", "area", "gravity", "eLambda", "ePhi", "temperature", "luminosity", "pressure",
                        "density", "zbar", "abar", "Xn", "Qimp", "Gamma", "cp", "eps_nu", "eps_nuc", "K")

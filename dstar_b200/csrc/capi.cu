@@ -90,7 +90,7 @@ struct dstar_batch {
     DevBuf<double> rho_bar1, tab_lnCp, tab_lnGamma, tab_lnEnu, tab_lnK;
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
-    DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot;
+    DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot, tr_ext;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // ordering between the two streams: face inputs / evolve inputs uploaded (copy stream), last compute issued (main)
     cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr, ev_cell_in = nullptr;
@@ -796,28 +796,8 @@ int dstar_batch_reset_state(dstar_batch* b) {
     return DSTAR_OK;
 }
 
-int dstar_batch_set_evolve_mapping(dstar_batch* b, int mapping) {
-    if (!b) return fail(DSTAR_ERR_ARG, "batch == NULL");
-    if (mapping < 0 || mapping > 2) return fail(DSTAR_ERR_ARG, "evolve mapping: 0 automatic, 1 CTA per star, 2 warp per star");
-    b->evolve_mapping = mapping;
-    return DSTAR_OK;
-}
-
-int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
-    if (!b || !ctrl) return fail(DSTAR_ERR_ARG, "batch_evolve");
-    if (!b->have_evolve || !b->have_tables) return fail(DSTAR_ERR_STATE, "evolve inputs / tables missing");
+static DsEvolveArgs fill_evolve_args(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
     dstar_ctx* c = b->ctx;
-    CK(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    const size_t ns = b->n_star;
-    if (trace_cap < 0) trace_cap = 0;
-    if (trace_cap != b->trace_cap || (trace_cap > 0 && !b->trace_model.p)) {
-        const size_t tn = (size_t)trace_cap * ns;
-        CK(b->trace_count.alloc(ns)); CK(b->trace_model.alloc(tn)); CK(b->tr_tsec.alloc(tn)); CK(b->tr_dt.alloc(tn));
-        CK(b->tr_Teff.alloc(tn)); CK(b->tr_Lsurf.alloc(tn)); CK(b->tr_Lnu.alloc(tn)); CK(b->tr_Lnuc.alloc(tn));
-        CK(b->tr_Mdot.alloc(tn));
-        b->trace_cap = trace_cap;
-    }
     DsEvolveArgs a{};
     a.n_star = b->n_star; a.n_epoch = b->n_epoch; a.n_tab = DS_NTAB; a.zone_offset = b->zone_offset.p;
     a.tab_lnT = c->tab_lnT.p; a.tab_lnK = b->tab_lnK.p; a.tab_lnCp = b->tab_lnCp.p; a.tab_lnGamma = b->tab_lnGamma.p;
@@ -840,10 +820,36 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     a.Lsurf = b->Lsurf.p; a.idid = b->idid.p; a.counters = b->counters.p;
     a.trace_cap = trace_cap; a.trace_count = trace_cap ? b->trace_count.p : nullptr; a.trace_model = b->trace_model.p;
     a.trace_tsec = b->tr_tsec.p; a.trace_dt = b->tr_dt.p; a.trace_Teff = b->tr_Teff.p; a.trace_Lsurf = b->tr_Lsurf.p;
-    a.trace_Lnu = b->tr_Lnu.p; a.trace_Lnuc = b->tr_Lnuc.p; a.trace_Mdot = b->tr_Mdot.p;
+    a.trace_Lnu = b->tr_Lnu.p; a.trace_Lnuc = b->tr_Lnuc.p; a.trace_Mdot = b->tr_Mdot.p; a.trace_ext = b->tr_ext.p;
     a.prof_interval = b->prof_interval; a.prof_cap = b->prof_cap; a.total_zones = b->total;
     a.prof_count = b->prof_cap ? b->prof_count.p : nullptr; a.prof_model = b->prof_model.p; a.prof_tsec = b->prof_tsec.p;
     a.prof_Mdot = b->prof_Mdot.p; a.prof_lnT = b->prof_lnT.p;
+    return a;
+}
+
+int dstar_batch_set_evolve_mapping(dstar_batch* b, int mapping) {
+    if (!b) return fail(DSTAR_ERR_ARG, "batch == NULL");
+    if (mapping < 0 || mapping > 2) return fail(DSTAR_ERR_ARG, "evolve mapping: 0 automatic, 1 CTA per star, 2 warp per star");
+    b->evolve_mapping = mapping;
+    return DSTAR_OK;
+}
+
+int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
+    if (!b || !ctrl) return fail(DSTAR_ERR_ARG, "batch_evolve");
+    if (!b->have_evolve || !b->have_tables) return fail(DSTAR_ERR_STATE, "evolve inputs / tables missing");
+    dstar_ctx* c = b->ctx;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t ns = b->n_star;
+    if (trace_cap < 0) trace_cap = 0;
+    if (trace_cap != b->trace_cap || (trace_cap > 0 && !b->trace_model.p)) {
+        const size_t tn = (size_t)trace_cap * ns;
+        CK(b->trace_count.alloc(ns)); CK(b->trace_model.alloc(tn)); CK(b->tr_tsec.alloc(tn)); CK(b->tr_dt.alloc(tn));
+        CK(b->tr_Teff.alloc(tn)); CK(b->tr_Lsurf.alloc(tn)); CK(b->tr_Lnu.alloc(tn)); CK(b->tr_Lnuc.alloc(tn));
+        CK(b->tr_Mdot.alloc(tn)); CK(b->tr_ext.alloc(4 * tn));
+        b->trace_cap = trace_cap;
+    }
+    const DsEvolveArgs a = fill_evolve_args(b, ctrl, trace_cap);
     // the star's rho_bar(1) is the fixed-up one (create_model.f:367-369): patch it into rho_bar
     // (the evolve kernel never reads face 0's rho_bar, L(1) comes from the atmosphere; kept for symmetry)
     CK(cudaStreamWaitEvent(s, b->ev_evolve_in, 0));   // evolve inputs were uploaded on the copy stream
@@ -884,6 +890,28 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[2] = ms;
     CK(cudaEventRecord(b->ev_busy, s));
     b->launches = launches;
+    return DSTAR_OK;
+}
+
+int dstar_batch_eval_rhs(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int epoch, double* f, double* jac, double* surf) {
+    if (!b || !ctrl) return fail(DSTAR_ERR_ARG, "batch_eval_rhs");
+    if (!b->have_evolve || !b->have_tables) return fail(DSTAR_ERR_STATE, "evolve inputs / tables missing");
+    if (epoch < 0 || epoch >= b->n_epoch) return fail(DSTAR_ERR_ARG, "epoch out of range");
+    dstar_ctx* c = b->ctx;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const DsEvolveArgs a = fill_evolve_args(b, ctrl, 0);
+    DevBuf<double> d_f, d_jac, d_surf;
+    CK(d_f.alloc(b->total)); CK(d_jac.alloc((size_t)3 * b->total)); CK(d_surf.alloc((size_t)3 * b->n_star));
+    CK(cudaStreamWaitEvent(s, b->ev_evolve_in, 0));
+    const int threads = ((b->max_nz + 31) / 32) * 32;
+    if (threads <= 256) ds_evolve_rhs_test_kernel<256><<<b->n_star, threads, 0, s>>>(a, epoch, d_f.p, d_jac.p, d_surf.p);
+    else ds_evolve_rhs_test_kernel<512><<<b->n_star, threads, 0, s>>>(a, epoch, d_f.p, d_jac.p, d_surf.p);
+    CK(cudaGetLastError());
+    if (f) CK(d_f.download(f, b->total, s));
+    if (jac) CK(d_jac.download(jac, (size_t)3 * b->total, s));
+    if (surf) CK(d_surf.download(surf, (size_t)3 * b->n_star, s));
+    CK(cudaStreamSynchronize(s));
     return DSTAR_OK;
 }
 
@@ -971,6 +999,16 @@ int dstar_batch_download_trace(dstar_batch* b, int32_t* count, int32_t* model, d
     if (Lnu) CK(b->tr_Lnu.download(Lnu, tn, s));
     if (Lnuc) CK(b->tr_Lnuc.download(Lnuc, tn, s));
     if (Mdot) CK(b->tr_Mdot.download(Mdot, tn, s));
+    CK(cudaStreamSynchronize(s));
+    return DSTAR_OK;
+}
+
+int dstar_batch_download_trace_extrema(dstar_batch* b, double* ext) {
+    if (!b || b->trace_cap <= 0) return fail(DSTAR_ERR_STATE, "no trace kept");
+    if (!ext) return fail(DSTAR_ERR_ARG, "ext == NULL");
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    CK(b->tr_ext.download(ext, (size_t)4 * b->trace_cap * b->n_star, s));
     CK(cudaStreamSynchronize(s));
     return DSTAR_OK;
 }

@@ -595,7 +595,8 @@ struct Star {
     std::vector<int> idid;
     // history rows
     std::vector<int> h_model;
-    std::vector<double> h_tsec, h_Mdot, h_Teff, h_Lsurf, h_Lnu, h_Lnuc;
+    std::vector<double> h_tsec, h_Mdot, h_Teff, h_Lsurf, h_Lnu, h_Lnuc, h_dt, h_lnTmax, h_PTmax, h_lnTmin, h_PTmin;
+    int h_total = 0;  // history rows the run produced (>= kept ones)
     // captured profiles: model number, time, accretion rate and ln T (nz each)
     std::vector<int> p_model;
     std::vector<double> p_tsec, p_Mdot, p_lnT;
@@ -1312,13 +1313,15 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     if (rc == 0) rc = dstar_batch_download_results(b, tm.data(), Tm.data(), Qm.data(), idid.data(), cnt.data(), lnT.data(),
                                                    Teff.data(), Lsurf.data(), dt.data(), tsec.data(), model.data());
     std::vector<int32_t> tc, tmodel;
-    std::vector<double> ttsec, tdt, tTeff, tLs, tLnu, tLnuc, tMdot;
+    std::vector<double> ttsec, tdt, tTeff, tLs, tLnu, tLnuc, tMdot, text;
     if (rc == 0 && cap > 0) {
         size_t tn = (size_t)cap * n;
         tc.resize(n); tmodel.resize(tn); ttsec.resize(tn); tdt.resize(tn); tTeff.resize(tn); tLs.resize(tn); tLnu.resize(tn);
         tLnuc.resize(tn); tMdot.resize(tn);
         rc = dstar_batch_download_trace(b, tc.data(), tmodel.data(), ttsec.data(), tdt.data(), tTeff.data(), tLs.data(),
                                         tLnu.data(), tLnuc.data(), tMdot.data());
+        text.resize(4 * tn);
+        if (rc == 0) rc = dstar_batch_download_trace_extrema(b, text.data());
     }
     std::vector<int32_t> pc, pmodel;
     std::vector<double> ptsec, pMdot, plnT;
@@ -1342,12 +1345,17 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
         for (int k2 = 0; k2 < s->nz; ++k2) s->z["T"][k2] = std::exp(s->z["lnT"][k2]);
         s->Teff = Teff[i]; s->Lsurf = Lsurf[i]; s->dt = dt[i]; s->tsec = tsec[i]; s->model = model[i];
         s->h_model.clear(); s->h_tsec.clear(); s->h_Mdot.clear(); s->h_Teff.clear(); s->h_Lsurf.clear(); s->h_Lnu.clear(); s->h_Lnuc.clear();
+        s->h_dt.clear(); s->h_lnTmax.clear(); s->h_PTmax.clear(); s->h_lnTmin.clear(); s->h_PTmin.clear(); s->h_total = 0;
         if (cap > 0) {
+            s->h_total = tc[i];
             int rows = std::min(tc[i], cap);
+            const size_t cs = (size_t)cap * n;
             for (int r = 0; r < rows; ++r) {
                 size_t q = (size_t)r * n + i;
                 s->h_model.push_back(tmodel[q]); s->h_tsec.push_back(ttsec[q]); s->h_Mdot.push_back(tMdot[q]);
                 s->h_Teff.push_back(tTeff[q]); s->h_Lsurf.push_back(tLs[q]); s->h_Lnu.push_back(tLnu[q]); s->h_Lnuc.push_back(tLnuc[q]);
+                s->h_dt.push_back(tdt[q]); s->h_lnTmax.push_back(text[q]); s->h_PTmax.push_back(text[cs + q]);
+                s->h_lnTmin.push_back(text[2 * cs + q]); s->h_PTmin.push_back(text[3 * cs + q]);
             }
         }
         s->p_model.clear(); s->p_tsec.clear(); s->p_Mdot.clear(); s->p_lnT.clear(); s->p_total = 0;
@@ -1481,6 +1489,7 @@ int dstar_NScool_get_history(int id, int capacity, int32_t* model, double* time_
 int dstar_NScool_write_history(int id, const char* path) {
     Star* s = get(id);
     if (!s || !s->evolved || !path) return -1;
+    if (s->h_total == 0) { g_err = "no history rows were kept (trace_capacity = 0 for this batch: set the control trace_capacity)"; return -1; }
     FILE* fp = std::fopen(path, "w");
     if (!fp) return -1;
     std::fprintf(fp, "dstar-b200/history\n\n");
@@ -1497,7 +1506,66 @@ int dstar_NScool_write_history(int id, const char* path) {
                      safe_log10(s->h_Lnuc[r]));
     }
     std::fclose(fp);
+    if (s->h_total > (int)s->h_model.size()) {   // the file is complete up to the capacity only: tell the caller
+        g_err = "history truncated: " + std::to_string(s->h_total) + " rows produced, " + std::to_string(s->h_model.size()) +
+                " kept (raise the control trace_capacity)";
+        return 1;
+    }
     return 0;
+}
+
+// NScool_terminal.f:17-57 as evaluate_timestep drives it (NScool_evolve.f:206-217): one line per model with
+// mod(model, write_interval_for_terminal) == 0, the column titles before every write_interval_for_terminal_header-th
+// line of an epoch (the counter restarts with each epoch, :109).  path NULL or "-": standard output.
+int dstar_NScool_write_terminal(int id, const char* path) {
+    Star* s = get(id);
+    if (!s || !s->evolved) return -1;
+    if (s->h_total == 0) { g_err = "no history rows were kept (trace_capacity = 0 for this batch: set the control trace_capacity)"; return -1; }
+    const bool to_stdout = !path || std::strcmp(path, "-") == 0;
+    FILE* fp = to_stdout ? stdout : std::fopen(path, "w");
+    if (!fp) return -1;
+    static const char* cols[11] = {"model", "time", "dt", "lg(Lsurf)", "lg(Teff)", "lg(Lnu)", "lg(Lnuc)", "max(lgT)", "lg(P[Tmax])",
+                                   "min(lgT)", "lg(P[Tmin])"};
+    const int every = std::max(1, s->c.write_interval_for_terminal), hdr = std::max(1, s->c.write_interval_for_terminal_header);
+    int epoch = 0, writes = 0;
+    for (size_t r = 0; r < s->h_model.size(); ++r) {
+        // a new epoch: its first row repeats the boundary time with dt = 0, or (first output suppressed) lies past it
+        while (epoch + 1 < s->number_epochs &&
+               ((r > 0 && s->h_dt[r] == 0.0 && s->h_tsec[r] >= s->epoch_boundaries[epoch + 1]) || s->h_tsec[r] > s->epoch_boundaries[epoch + 1])) {
+            ++epoch; writes = 0;
+        }
+        if (s->h_model[r] % every != 0) continue;
+        if (writes % hdr == 0) {
+            std::fprintf(fp, "\n");
+            for (int i = 0; i < 11; ++i) std::fprintf(fp, "%15s", cols[i]);
+            std::fprintf(fp, "\n\n");
+        }
+        std::fprintf(fp, "%15d%15.6E%15.6E%15.6f%15.6f%15.6f%15.6f%15.6f%15.6f%15.6f%15.6f\n", s->h_model[r], s->h_tsec[r], s->h_dt[r],
+                     std::log10(s->h_Lsurf[r]), std::log10(s->h_Teff[r]), std::log10(s->h_Lnu[r]), safe_log10(s->h_Lnuc[r]),
+                     s->h_lnTmax[r] / k::ln10, std::log10(s->h_PTmax[r]), s->h_lnTmin[r] / k::ln10, std::log10(s->h_PTmin[r]));
+        ++writes;
+    }
+    if (!to_stdout) std::fclose(fp);
+    else std::fflush(stdout);
+    if (s->h_total > (int)s->h_model.size()) { g_err = "terminal log truncated (raise the control trace_capacity)"; return 1; }
+    return 0;
+}
+
+int dstar_NScool_get_terminal(int id, int capacity, int32_t* model, double* tsec, double* dt, double* lgTmax,
+                              double* lgP_Tmax, double* lgTmin, double* lgP_Tmin) {
+    Star* s = get(id);
+    if (!s || !s->evolved) return -1;
+    const int rows = (int)s->h_model.size();
+    for (int r = 0; r < rows && r < capacity; ++r) {
+        if (model) model[r] = s->h_model[r];
+        if (tsec) tsec[r] = s->h_tsec[r];
+        if (dt) dt[r] = s->h_dt[r];
+        if (lgTmax) lgTmax[r] = s->h_lnTmax[r] / k::ln10;
+        if (lgP_Tmax) lgP_Tmax[r] = std::log10(s->h_PTmax[r]);
+        if (lgTmin) lgTmin[r] = s->h_lnTmin[r] / k::ln10;
+        if (lgP_Tmin) lgP_Tmin[r] = std::log10(s->h_PTmin[r]);
+    }
+    return rows;
 }
 
 // ---- profiles (NScool_profile.f): the device keeps ln T per zone at the profile models; every other column is

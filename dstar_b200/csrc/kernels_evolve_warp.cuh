@@ -400,6 +400,29 @@ __global__ void __launch_bounds__(32 * S) ds_evolve_warp_kernel(DsEvolveArgs a, 
                         a.trace_Teff[r] = Teff; a.trace_Lsurf[r] = Lsurf; a.trace_Lnu[r] = Lnu;
                         a.trace_Lnuc[r] = Lnuc; a.trace_Mdot[r] = Mdot;
                     }
+                    {   // the terminal line's extrema (NScool_terminal.f:53-56)
+                        double ymax = -1.0e300, ymn = 1.0e300;
+#pragma unroll
+                        for (int i = 0; i < Z; ++i)
+                            if (lane * Z + i < n) { ymax = fmax(ymax, y[i]); ymn = fmin(ymn, y[i]); }
+                        ymax = -warp_min(-ymax); ymn = warp_min(ymn);
+                        double kx = 1.0e9, kn = 1.0e9;
+#pragma unroll
+                        for (int i = Z - 1; i >= 0; --i)
+                            if (lane * Z + i < n) {
+                                if (y[i] == ymax) kx = (double)(lane * Z + i);
+                                if (y[i] == ymn) kn = (double)(lane * Z + i);
+                            }
+                        const int kmax = (int)warp_min(kx), kmin = (int)warp_min(kn);
+                        if (ntrace < a.trace_cap) {
+                            const size_t cs = (size_t)a.trace_cap * a.n_star, r = (size_t)ntrace * a.n_star + star;
+#pragma unroll
+                            for (int i = 0; i < Z; ++i) {
+                                if (lane * Z + i == kmax) { a.trace_ext[r] = ymax; a.trace_ext[cs + r] = Pz[i]; }
+                                if (lane * Z + i == kmin) { a.trace_ext[2 * cs + r] = ymn; a.trace_ext[3 * cs + r] = Pz[i]; }
+                            }
+                        }
+                    }
                     ++ntrace;
                 }
                 if (a.prof_cap > 0 && model % a.prof_interval == 0) {

@@ -162,6 +162,11 @@ int dstar_batch_reset_state(dstar_batch* b);
 /* seam B: every star through all its epochs in ONE launch.  trace_cap > 0 keeps that many
  * history rows per star. */
 int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap);
+/* test support, function level: get_derivatives (NScool/private/NScool_evolve.f:237-283) and the tridiagonal rows of
+ * get_jacobian (:285-359) of epoch `epoch` at the batch's current ln T (as uploaded or as the last evolve left it),
+ * computed by the device functions the evolve kernel is built from.  f (total_zones); jac (3, total_zones) =
+ * d f_k / d lnT_{k-1}, d f_k / d lnT_k, d f_k / d lnT_{k+1}; surf (3, n_star) = Lsurf, dlnLs/dlnT, Teff.  May be NULL. */
+int dstar_batch_eval_rhs(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int epoch, double* f, double* jac, double* surf);
 /* thread mapping of seam B: 0 = automatic (default), 1 = one CTA per star, one thread per zone, cyclic reduction through
  * shared memory (any nz <= 512), 2 = one warp per star, nz/32 zones per lane, partitioned solve with cyclic reduction
  * over warp shuffles (nz <= 320; larger stars fall back to 1).  Same formulas and driver, so the same light curves;
@@ -176,6 +181,10 @@ int dstar_batch_download_results(dstar_batch* b, double* t_monitor, double* Teff
 /* D2H of the trace: count(n_star); the rest (trace_cap,n_star): model, tsec, dt, Teff, Lsurf, Lnu, Lnuc, Mdot */
 int dstar_batch_download_trace(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* dt,
                                double* Teff, double* Lsurf, double* Lnu, double* Lnuc, double* Mdot);
+
+/* D2H of the extrema the terminal line prints (NScool/private/NScool_terminal.f:53-56), per trace row:
+ * ext (4, trace_cap, n_star) = maxval(lnT), P(maxloc(lnT)), minval(lnT), P(minloc(T)) */
+int dstar_batch_download_trace_extrema(dstar_batch* b, double* ext);
 
 /* Profile capture (evaluate_timestep, NScool/private/NScool_evolve.f:227-233 -> do_write_profile,
  * NScool/private/NScool_profile.f:27-106): before dstar_batch_evolve, ask the kernel to keep ln T of every zone at

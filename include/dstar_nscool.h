@@ -77,8 +77,17 @@ int dstar_NScool_get_counters(int id, int32_t counters[7]);
 /* history rows kept from the last evolve (NScool_history.f:84-86); returns the row count */
 int dstar_NScool_get_history(int id, int capacity, int32_t* model, double* time_d, double* lg_Mdot,
                              double* lg_Teff, double* lg_Lsurf, double* lg_Lnu, double* lg_Lnuc);
-/* write LOGS/history.data in the reference's format (readable by tools/reader.py) */
+/* write LOGS/history.data in the reference's format (NScool_history.f:25-89; readable by tools/reader.py).
+ * Returns 0, 1 = written but truncated at the trace capacity (more rows were produced than kept), < 0 = error
+ * (including: no rows kept at all because the batch ran with trace_capacity = 0). */
 int dstar_NScool_write_history(int id, const char* path);
+/* the terminal log of the last evolve (do_write_terminal, NScool/private/NScool_terminal.f:17-57, driven as
+ * evaluate_timestep does, NScool_evolve.f:206-217): model, time [s], dt, lg Lsurf, lg Teff, lg Lnu, lg Lnuc,
+ * max lg T and lg P there, min lg T and lg P there.  path NULL or "-" = standard output.  Return as write_history. */
+int dstar_NScool_write_terminal(int id, const char* path);
+/* the same rows as arrays: (capacity) each; returns the number of rows kept */
+int dstar_NScool_get_terminal(int id, int capacity, int32_t* model, double* tsec, double* dt, double* lgTmax,
+                              double* lgP_Tmax, double* lgTmin, double* lgP_Tmin);
 
 /* Profiles (do_write_profile, NScool/private/NScool_profile.f:27-106; written when mod(model,
  * write_interval_for_profile) == 0, NScool_evolve.f:227-233).  The device keeps ln T of every zone at those

@@ -201,6 +201,9 @@ int dso_micro_tables(const MicroTablesIn* in, double* tab_lnT, double* tab_lnCp,
 int dso_evolve_epoch(const EvolveIn* in, EvolveState* st, EvolveTrace* trace) {
     return evolve_epoch(*in, *st, trace);
 }
+int dso_evolve_rhs_jac(const EvolveIn* in, const double* lnT, double* f, double* lo, double* di, double* up, double* surf) {
+    return evolve_rhs_jac(*in, lnT, f, lo, di, up, surf);
+}
 int dso_crust_composition(int nv, int nisos, const double* lgP_tab, const double* Ycoef,
                           const double* Ziso, const double* Aiso, int nz, const double* lgP,
                           double* ionic, double* Yion, int* ncharged) {

@@ -532,6 +532,24 @@ struct Star {
 };
 }  // namespace
 
+// get_derivatives (:237-283) and get_jacobian (:285-359) at a given ln T, for the function-level tests: f (nz); rows
+// lo/di/up (nz) = d f_k / d lnT_{k-1}, d f_k / d lnT_k, d f_k / d lnT_{k+1} (the band storage of :340-356 transposed
+// to rows); surf = Lsurf, dlnLs/dlnT, Teff.  in.Mdot, in.heat select the epoch.
+int evolve_rhs_jac(const EvolveIn& in, const double* lnT, double* f, double* lo, double* di, double* up, double* surf) {
+    const int n = in.nz;
+    Star s(in);
+    std::vector<double> y(lnT, lnT + n), sup(n), diag(n), sub(n);
+    if (s.accreting_fixed()) y[0] = dsm::log(in.atmosphere_temperature_when_accreting);
+    s.jacobian(y.data(), f, sup.data(), diag.data(), sub.data());
+    for (int k = 0; k < n; ++k) {
+        di[k] = diag[k];
+        up[k] = (k < n - 1) ? sup[k + 1] : 0.0;   // dfdy(1, k+1) = d f_k / d y_{k+1}
+        lo[k] = (k > 0) ? sub[k - 1] : 0.0;       // dfdy(3, k-1) = d f_k / d y_{k-1}
+    }
+    if (surf) { surf[0] = s.Lsurf; surf[1] = s.dlnLsdlnT; surf[2] = s.Teff; }
+    return 0;
+}
+
 int evolve_epoch(const EvolveIn& in, EvolveState& st, EvolveTrace* trace) {
     const int n = in.nz;
     Star s(in);

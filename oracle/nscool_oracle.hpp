@@ -71,6 +71,7 @@ struct EvolveTrace {  // one row per solout call (history columns, NScool_histor
     double* lnT_rows;  // optional (capacity, nz) snapshots, may be null
 };
 int evolve_epoch(const EvolveIn& in, EvolveState& st, EvolveTrace* trace);
+int evolve_rhs_jac(const EvolveIn& in, const double* lnT, double* f, double* lo, double* di, double* up, double* surf);
 
 // RODASP order/self-consistency test problems (tests/test_oracle_integrator.py)
 int rodasp_selftest(int problem, double tend, double rtol, double atol, double h0, double* y,

@@ -255,7 +255,8 @@ def _evolve_epoch(self, ein_kwargs, lnT, dt, trace_cap=0):
         tr.model = _ptr(arrs["model"], ip)
         for nm in ("tsec", "dt", "Teff", "Lsurf", "Lnu", "Lnuc"):
             arrs[nm] = np.zeros(trace_cap); setattr(tr, nm, _ptr(arrs[nm]))
-        tr.lnT_rows = dp()
+        arrs["lnT_rows"] = np.zeros((trace_cap, int(ein_kwargs["nz"])))
+        tr.lnT_rows = _ptr(arrs["lnT_rows"])
     rc = self.lib.dso_evolve_epoch(C.byref(e), C.byref(st), C.byref(tr) if tr is not None else None)
     out = {"rc": rc, "lnT": y, "dt": st.dt, "tsec": st.tsec, "model": st.model, "Teff": st.Teff, "Lsurf": st.Lsurf,
            "idid": st.idid, "counters": np.array(list(st.counters))}
@@ -263,6 +264,37 @@ def _evolve_epoch(self, ein_kwargs, lnT, dt, trace_cap=0):
         n = tr.count
         out["trace"] = {k: v[:n] for k, v in arrs.items()}
     return out
+
+
+def _fill_evolve_in(ein_kwargs):
+    e = EvolveIn()
+    keep = []
+    for k, v in ein_kwargs.items():
+        if isinstance(v, np.ndarray):
+            a = f64(v); keep.append(a); setattr(e, k, _ptr(a))
+        elif k == "heat":
+            e.heat = (C.c_double * 9)(*v)
+        else:
+            setattr(e, k, v)
+    return e, keep
+
+
+class RhsEvaluator:
+    """get_derivatives / get_jacobian of ONE star and epoch at arbitrary ln T (function-level tests, independent
+    integrations).  Keeps the filled EvolveIn alive, so repeated calls cost one C call each."""
+
+    def __init__(self, oracle, ein_kwargs):
+        self.lib = oracle.lib
+        self.e, self._keep = _fill_evolve_in(ein_kwargs)
+        self.n = int(ein_kwargs["nz"])
+
+    def __call__(self, lnT):
+        y = f64(lnT)
+        n = self.n
+        f = np.zeros(n); lo = np.zeros(n); di = np.zeros(n); up = np.zeros(n); surf = np.zeros(3)
+        rc = self.lib.dso_evolve_rhs_jac(C.byref(self.e), _ptr(y), _ptr(f), _ptr(lo), _ptr(di), _ptr(up), _ptr(surf))
+        assert rc == 0
+        return {"f": f, "lo": lo, "di": di, "up": up, "Lsurf": surf[0], "dlnLsdlnT": surf[1], "Teff": surf[2]}
 
 
 Oracle.micro_tables = _micro_tables

@@ -28,6 +28,31 @@ def oracle_micro_tables(o, s, gaps=("ns", "sfb03", "t72"), cond_ctrl=(0, 0, 1, 1
                           shell_Urca=shell_Urca)
 
 
+def evolve_in_kwargs(s, epoch, tabs=None, ctrl=None, heat=None, T_atm=None):
+    """EvolveIn fields of one epoch of star s (same defaults as oracle_evolve_star)."""
+    nz = s.get_int("nz")
+    t = tabs or {k: s.array(k) for k in ("tab_lnT", "tab_lnK", "tab_lnCp", "tab_lnGamma", "tab_lnEnu")}
+    if "tab_lnT" not in t:
+        t["tab_lnT"] = s.array("tab_lnT")
+    eb = s.array("epoch_boundaries"); em = s.array("epoch_Mdots")
+    kw = dict(nz=nz, n_tab=128, tab_lnT=t["tab_lnT"], tab_lnK=t["tab_lnK"], tab_lnCp=t["tab_lnCp"],
+              tab_lnGamma=t["tab_lnGamma"], tab_lnEnu=t["tab_lnEnu"], dm=s.array("dm"), dm_bar=s.array("dm_bar"),
+              area=s.array("area"), rho_bar=s.array("rho_bar"), ePhi=s.array("ePhi"), e2Phi=s.array("e2Phi"),
+              ePhi_bar=s.array("ePhi_bar"), e2Phi_bar=s.array("e2Phi_bar"), P=s.array("P"), atm_nv=256,
+              atm_lgTb=s.array("atm_lgTb"), atm_lgTeff=s.array("atm_lgTeff"), atm_lgflux=s.array("atm_lgflux"),
+              heat=heat or [26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, 3.0], turn_on_extra_heating=0,
+              fix_core_temperature=1, make_inner_boundary_insulating=0,
+              fix_atmosphere_temperature_when_accreting=1,
+              atmosphere_temperature_when_accreting=T_atm or 1.0e8, integration_tolerance=1.0e-4, min_lg_T=7.0,
+              max_lg_T=9.5, maximum_timestep=0.0, maximum_number_of_models=10000, starting_number_for_profile=0,
+              suppress_first_step_output=0, reference_cost_quirks=0)
+    if ctrl:
+        kw.update(ctrl)
+    kw["Mdot"] = float(em[epoch]); kw["epoch_start_time"] = float(eb[epoch])
+    kw["epoch_duration"] = float(eb[epoch + 1] - eb[epoch])
+    return kw
+
+
 def oracle_evolve_star(o, s, lnT0, tabs=None, ctrl=None, heat=None, T_atm=None, trace_cap=0, quirks=0):
     """NScool_evolve_model's epoch loop (NScool_lib.f:68-90) on the oracle, from the star's own tables
     (or `tabs`).  ctrl: dict overriding EvolveIn scalar fields."""

@@ -158,10 +158,11 @@ def test_too_many_zones_is_refused(nscool):
     s.free()
 
 
-def test_full_size_sweep_properties(nscool):
+def test_full_size_sweep_properties(nscool, oracle):
     """configs[1] at BASELINE size (256 stars x 253 zones): everything converges, the coefficient pass is idempotent,
-    cell tables depend on the core Tc only through ... nothing (same crust), face tables only on pasta Qimp, and a
-    star pulled out of the batch reproduces its in-batch result bit for bit."""
+    cell tables depend on the core Tc only through ... nothing (same crust), face tables only on pasta Qimp, a
+    star pulled out of the batch reproduces its in-batch result bit for bit, and six stars spread over the grid equal
+    the oracle at full resolution (every table entry to 1e-10, T_eff at the nine epochs to 1e-6, same solver counters)."""
     from dstar_b200 import workloads
     ds = nscool
     stars = workloads.custom_Tc_Qimp(256, resolution=0.05)
@@ -170,7 +171,17 @@ def test_full_size_sweep_properties(nscool):
     ds.create_models(stars)                                    # idempotence of the coefficient pass
     for n in TABS:
         assert np.array_equal(bits(stars[37].array(n)), bits(first[n])), n
+    picks = (0, 15, 85, 119, 170, 255)
+    y0 = {i: stars[i].array("lnT").copy() for i in picks}
     ds.evolve_models(stars)
+    for i in picks:
+        s = stars[i]
+        ref = oracle_micro_tables(oracle, s, gaps=("ns", "sfb03", "t72"), Tc_cell=s.array("Tc_cell"), Tc_face=s.array("Tc_face"))
+        check_tables(s, ref)
+        ev = oracle_evolve_star(oracle, s, y0[i], heat=[26.86, 30.13, 0.3, 30.42, 31.20, 1.5, 27.0, 28.0, 1.7],
+                                ctrl=dict(turn_on_extra_heating=1, fix_atmosphere_temperature_when_accreting=0))
+        assert rel(s.monitors()[1], ev["Teff_monitor"]) < 1e-6, i
+        np.testing.assert_array_equal(s.counters(), ev["counters"])
     Teff = np.array([s.monitors()[1] for s in stars])
     assert Teff.shape == (256, 9) and np.all(np.isfinite(Teff)) and np.all(Teff > 1e5) and np.all(Teff < 1e7)
     nz = stars[0].get_int("nz")
