@@ -559,6 +559,7 @@ struct CrustTable {  // dStar_crust_def.f:10-24
     int nv = 0;
     double T = 0;
     std::vector<double> lgP, Ycoef /* (4*nv, nisos) */, lgRho /* (4*nv) */, lgEps;
+    std::vector<double> ionic /* (11, nv) */, Yion /* (ncharged, nv) */, mass_excess /* (ncharged) */;   // the table points' composition (tests)
 };
 std::map<std::string, std::shared_ptr<CrustTable>> g_crust_cache;
 
@@ -755,6 +756,7 @@ int build_crust_table(const Controls& c, std::shared_ptr<CrustTable>& out) {
     for (int i = 0; i < N; ++i) { tab->lgRho[4 * i] = x[i]; tab->lgEps[4 * i] = lgEps[i]; }
     interp_pm(tab->lgP.data(), N, tab->lgRho.data());
     interp_pm(tab->lgP.data(), N, tab->lgEps.data());
+    tab->ionic = ionic; tab->Yion = Yion; tab->mass_excess = ME;
     g_crust_cache[key] = tab;
     out = tab;
     return 0;
@@ -1419,6 +1421,16 @@ int dstar_NScool_get_zone_array(int id, const char* name, double* out, int capac
         const Network& net = s->crust->net;
         for (size_t i = 0; i < net.Z.size(); ++i) if (net.Z[i] > 0) tmp.push_back(nm == "Zion" ? net.Z[i] : net.A[i]);
         src = &tmp;
+    } else if (nm.rfind("crust_", 0) == 0 && s->crust) {   // the star's crust table (dStar_crust_def.f:10-24)
+        const CrustTable& ct = *s->crust;
+        if (nm == "crust_lgP") src = &ct.lgP;
+        else if (nm == "crust_lgRho") src = &ct.lgRho;      // (4, nv) monotone-cubic coefficients
+        else if (nm == "crust_lgEps") src = &ct.lgEps;
+        else if (nm == "crust_ionic") src = &ct.ionic;
+        else if (nm == "crust_Yion") src = &ct.Yion;
+        else if (nm == "crust_mass_excess") src = &ct.mass_excess;
+        else if (nm == "crust_Tref") { tmp.push_back(ct.T); src = &tmp; }
+        else return -2;
     } else if (nm == "Qimp_bar") {
         auto& ib = s->z["ionic_bar"];
         for (int k2 = 0; k2 < s->nz; ++k2) tmp.push_back(ib[11 * k2 + 10]);
