@@ -177,6 +177,12 @@ class Batch:
             (tf.nbytes if tf is not None else 0)
         check(self.L.dstar_batch_upload_structure(self.h, *[p(x) for x in a], p(tc), p(tf)), "upload_structure")
 
+    def set_table_sharing(self, which, owner):
+        """which = 1 cell tables, 2 face tables; owner[i] = first star of star i's group, or None to end the sharing
+        (dstar_batch_set_table_sharing)."""
+        o = None if owner is None else i32(owner)
+        check(self.L.dstar_batch_set_table_sharing(self.h, int(which), p(o, ip)), "dstar_batch_set_table_sharing")
+
     def micro_tables(self, ctrl=None, which=3):
         ctrl = ctrl or MicroCtrl.defaults()
         check(self.L.dstar_batch_micro_tables(self.h, C.byref(ctrl), int(which)), "dstar_batch_micro_tables")
@@ -425,6 +431,13 @@ class NScool:
 def create_models(stars):
     ids = i32([s.id for s in stars])
     _nerr(lib().dstar_NScool_create_models(len(ids), p(ids, ip)), "NScool_create_models")
+
+
+def table_sets():
+    """(distinct cell-table sets, distinct face-table sets) the last create_models evaluated."""
+    a, b = C.c_int32(), C.c_int32()
+    lib().dstar_NScool_table_sets(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def evolve_models(stars):

@@ -102,6 +102,15 @@ struct dstar_batch {
     // entry (Z = 0) is the CTA-per-star fallback for stars with more than 320 zones
     struct EvolveClass { int Z = 0, count = 0, max_nz = 0; DevBuf<int> list; };
     EvolveClass ev_class[DS_N_EVOLVE_CLASS + 1];
+    // table sharing (dstar_batch_set_table_sharing), [0] = cell tables, [1] = face tables: owner star of each star's
+    // tables, first table slot of each star in the compact arrays, zones of the owner stars (the work list of the pass)
+    struct Share {
+        bool on = false;
+        std::vector<int> owner, tab0;
+        size_t slots = 0;
+        int n_work = 0;
+        DevBuf<int> d_owner, d_tab0, d_work;
+    } share[2];
     int evolve_mapping = 0;   // dstar_batch_set_evolve_mapping: 0 = automatic, 1 = CTA per star, 2 = warp per star
 };
 
@@ -644,10 +653,10 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     CK(cudaSetDevice(c->device));
     CK(ensure_stack_limit());
     cudaStream_t s = c->stream;
-    const size_t tsz = (size_t)4 * DS_NTAB * b->total;
-    if (!b->tab_lnCp.p) {
-        CK(b->tab_lnCp.alloc(tsz)); CK(b->tab_lnGamma.alloc(tsz)); CK(b->tab_lnEnu.alloc(tsz)); CK(b->tab_lnK.alloc(tsz));
-    }
+    const size_t csz = (size_t)4 * DS_NTAB * (b->share[0].on ? b->share[0].slots : (size_t)b->total);
+    const size_t fsz = (size_t)4 * DS_NTAB * (b->share[1].on ? b->share[1].slots : (size_t)b->total);
+    if ((which & 1) && b->tab_lnCp.n != csz) { CK(b->tab_lnCp.alloc(csz)); CK(b->tab_lnGamma.alloc(csz)); CK(b->tab_lnEnu.alloc(csz)); }
+    if ((which & 2) && b->tab_lnK.n != fsz) CK(b->tab_lnK.alloc(fsz));
     DsMicroArgs a{};
     a.total_zones = b->total; a.ncharged = b->ncharged; a.zone_star = b->zone_star.p; a.zone_offset = b->zone_offset.p;
     a.rho = b->rho.p; a.rho_bar = b->rho_bar.p; a.P = b->P.p; a.P_bar = b->P_bar.p; a.dm = b->dm.p;
@@ -676,10 +685,13 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = b->redo.p; a.redo_count = b->redo_count.p;
+            const dstar_batch::Share& sh = b->share[0];
+            a.work_list = sh.on ? sh.d_work.p : nullptr; a.n_work = sh.n_work; a.tab_zone0 = sh.on ? sh.d_tab0.p : nullptr;
             ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
             CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
             a.force_redo = g_force_redo;   // test hook (dstar_debug_force_redo)
-            CK(launch_micro<false>(micro_minb(), sms, b->total, s, a, c->helm, c->sf));
+            CK(launch_micro<false>(micro_minb(), sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf));
+            if (sh.on) ds_share_rho_bar1_kernel<<<(b->n_star + 127) / 128, 128, 0, s>>>(b->n_star, sh.d_owner.p, b->rho_bar1.p);
             ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
         }
         CK(cudaGetLastError());
@@ -691,9 +703,11 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         {   // one persistent CTA per SM, G zone-groups of 128 lanes in lockstep (see kernels_micro.cuh)
             const int sms = c->prop.multiProcessorCount;
             a.redo = nullptr; a.redo_count = nullptr;
+            const dstar_batch::Share& sh = b->share[1];
+            a.work_list = sh.on ? sh.d_work.p : nullptr; a.n_work = sh.n_work; a.tab_zone0 = sh.on ? sh.d_tab0.p : nullptr;
             CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
             ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
-            CK(launch_micro<true>(micro_minb(), sms, b->total, s, a, c->helm, c->sf));
+            CK(launch_micro<true>(micro_minb(), sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev3, s));
@@ -710,6 +724,40 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     return DSTAR_OK;
 }
 
+int dstar_batch_set_table_sharing(dstar_batch* b, int which, const int32_t* owner) {
+    if (!b || (which != 1 && which != 2)) return fail(DSTAR_ERR_ARG, "batch_set_table_sharing: which = 1 (cell tables) or 2 (face tables)");
+    dstar_batch::Share& sh = b->share[which - 1];
+    CK(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    b->have_tables = false;
+    if (!owner) { sh.on = false; return DSTAR_OK; }
+    const int n = b->n_star;
+    sh.owner.assign(owner, owner + n);
+    sh.tab0.assign(n, -1);
+    std::vector<int> work;
+    size_t slots = 0;
+    for (int i = 0; i < n; ++i) {
+        const int o = owner[i];
+        if (o < 0 || o >= n || owner[o] != o) return fail(DSTAR_ERR_ARG, "table sharing: owner[i] must name a star that owns its tables");
+        const int nz = b->h_zone_offset[i + 1] - b->h_zone_offset[i];
+        if (b->h_zone_offset[o + 1] - b->h_zone_offset[o] != nz) return fail(DSTAR_ERR_ARG, "table sharing: stars with different zone counts");
+        if (o == i) {
+            sh.tab0[i] = (int)slots;
+            slots += nz;
+            for (int k = 0; k < nz; ++k) work.push_back(b->h_zone_offset[i] + k);
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        if (owner[i] > i) return fail(DSTAR_ERR_ARG, "table sharing: the owner must be the first star of its group");
+        sh.tab0[i] = sh.tab0[owner[i]];
+    }
+    sh.slots = slots; sh.n_work = (int)work.size();
+    CK(sh.d_owner.upload(sh.owner.data(), n, s)); CK(sh.d_tab0.upload(sh.tab0.data(), n, s)); CK(sh.d_work.upload(work.data(), work.size(), s));
+    CK(cudaStreamSynchronize(s));
+    sh.on = true;
+    return DSTAR_OK;
+}
+
 int dstar_batch_download_tables(dstar_batch* b, double* tab_lnT, double* tab_lnCp, double* tab_lnGamma,
                                 double* tab_lnEnu, double* tab_lnK, double* rho_bar1, int32_t* status) {
     if (!b) return fail(DSTAR_ERR_ARG, "batch_download_tables");
@@ -718,11 +766,24 @@ int dstar_batch_download_tables(dstar_batch* b, double* tab_lnT, double* tab_lnC
     cudaStream_t s = b->ctx->stream;
     const size_t tsz = (size_t)4 * DS_NTAB * b->total;
     if (tab_lnT) std::memcpy(tab_lnT, b->ctx->h_tab_lnT, sizeof(double) * DS_NTAB);
-    if (tab_lnCp) CK(b->tab_lnCp.download(tab_lnCp, tsz, s));
-    if (tab_lnGamma) CK(b->tab_lnGamma.download(tab_lnGamma, tsz, s));
-    if (tab_lnEnu) CK(b->tab_lnEnu.download(tab_lnEnu, tsz, s));
-    if (tab_lnK) CK(b->tab_lnK.download(tab_lnK, tsz, s));
-    if (rho_bar1) CK(b->rho_bar1.download(rho_bar1, b->n_star, s));
+    {   // with shared tables the device holds one copy per owner; the caller gets every star's (4*128, nz) block
+        struct Item { double* host; const DevBuf<double>* dev; int which; };
+        const Item items[4] = {{tab_lnCp, &b->tab_lnCp, 0}, {tab_lnGamma, &b->tab_lnGamma, 0}, {tab_lnEnu, &b->tab_lnEnu, 0}, {tab_lnK, &b->tab_lnK, 1}};
+        std::vector<double> tmp;
+        for (const Item& it : items) {
+            if (!it.host) continue;
+            const dstar_batch::Share& sh = b->share[it.which];
+            if (!sh.on) { CK(it.dev->download(it.host, tsz, s)); continue; }
+            tmp.resize((size_t)4 * DS_NTAB * sh.slots);
+            CK(it.dev->download(tmp.data(), tmp.size(), s));
+            CK(cudaStreamSynchronize(s));
+            for (int i = 0; i < b->n_star; ++i) {
+                const size_t nz = b->h_zone_offset[i + 1] - b->h_zone_offset[i];
+                std::memcpy(it.host + (size_t)4 * DS_NTAB * b->h_zone_offset[i], tmp.data() + (size_t)4 * DS_NTAB * sh.tab0[i],
+                            sizeof(double) * 4 * DS_NTAB * nz);
+            }
+        }
+    }
     if (status) CK(b->status.download(status, b->n_star, s));
     CK(cudaStreamSynchronize(s));
     return DSTAR_OK;
@@ -735,6 +796,7 @@ int dstar_batch_upload_tables(dstar_batch* b, const double* tab_lnT, const doubl
     CK(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
     const size_t tsz = (size_t)4 * DS_NTAB * b->total;
+    b->share[0].on = false; b->share[1].on = false;   // the caller brings every star's own tables
     CK(b->tab_lnCp.upload(tab_lnCp, tsz, s)); CK(b->tab_lnGamma.upload(tab_lnGamma, tsz, s));
     CK(b->tab_lnEnu.upload(tab_lnEnu, tsz, s)); CK(b->tab_lnK.upload(tab_lnK, tsz, s));
     CK(cudaStreamSynchronize(s));
@@ -802,6 +864,8 @@ static DsEvolveArgs fill_evolve_args(dstar_batch* b, const dstar_evolve_ctrl* ct
     a.n_star = b->n_star; a.n_epoch = b->n_epoch; a.n_tab = DS_NTAB; a.zone_offset = b->zone_offset.p;
     a.tab_lnT = c->tab_lnT.p; a.tab_lnK = b->tab_lnK.p; a.tab_lnCp = b->tab_lnCp.p; a.tab_lnGamma = b->tab_lnGamma.p;
     a.tab_lnEnu = b->tab_lnEnu.p;
+    a.cell_tab_zone0 = b->share[0].on ? b->share[0].d_tab0.p : nullptr;
+    a.face_tab_zone0 = b->share[1].on ? b->share[1].d_tab0.p : nullptr;
     a.dm = b->dm.p; a.dm_bar = b->dm_bar.p; a.area = b->area.p; a.rho_bar = b->rho_bar.p; a.ePhi = b->ePhi.p;
     a.e2Phi = b->e2Phi.p; a.ePhi_bar = b->ePhi_bar.p; a.e2Phi_bar = b->e2Phi_bar.p; a.P = b->P.p;
     a.atm_index = b->atm_index.p; a.atm_nv = b->atm_nv; a.atm_lgTb = b->atm_lgTb.p; a.atm_lgTeff = b->atm_lgTeff.p;

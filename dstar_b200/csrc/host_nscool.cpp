@@ -87,6 +87,7 @@ struct Controls {  // NScool/public/NScool_controls.inc, defaults NScool/default
     double Qimp = 0.0;
     int trace_capacity = -1;  // dstar_b200 extension: history rows kept on the device (-1: automatic)
     int profile_capacity = -1;  // dstar_b200 extension: profiles kept on the device per star (-1: automatic, 0: none)
+    bool share_identical_tables = false;  // dstar_b200 extension: stars of a batch with identical coefficient-pass inputs share one table set
     std::string base_profile_filename = "profile", profile_manifest_filename = "profiles";
     Controls() { basic_epoch_boundaries[1] = 365.0; }
 };
@@ -218,6 +219,7 @@ int set_control(Controls& c, const std::string& name_in, const std::string& valu
     if (name == "fix_qimp") return parse_logical(vals[0], c.fix_Qimp) ? 0 : -1;
     if (name == "qimp") return parse_real(vals[0], c.Qimp) ? 0 : -1;
     INT(trace_capacity) INT(profile_capacity)
+    if (name == "share_identical_tables") return parse_logical(vals[0], c.share_identical_tables) ? 0 : -1;
     // stored-but-unused controls of the reference (load_model_file, model_file, use_core_nu_*)
     if (name == "load_model_file" || name == "model_file" || name.rfind("use_core_nu_", 0) == 0) return 0;
     return -2;
@@ -994,6 +996,7 @@ int check_batch_controls(const std::vector<Star*>& ss, bool micro, bool evolve) 
 }
 
 int g_evolve_mapping = 0;   // dstar_NScool_set_evolve_mapping
+int g_share_stats[2] = {0, 0};   // distinct cell / face table sets of the last create_models
 
 // cached device batch shared by create_models -> evolve_models on the same id list
 struct BatchCache {
@@ -1119,6 +1122,28 @@ int dstar_NScool_set_hooks(int id, dstar_set_Qimp_fn qimp, dstar_sf_fn sf) {
     return 0;
 }
 
+namespace {
+// owner[i] = first star of the batch whose listed per-zone arrays (and scalar tags) are byte-identical to star i's
+void group_identical(const std::vector<Star*>& ss, const std::vector<const char*>& names, const std::vector<std::vector<double>>& extra,
+                     const std::vector<int32_t>* seed, std::vector<int32_t>& owner) {
+    const int n = (int)ss.size();
+    std::map<std::string, int> first;
+    owner.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+        std::string key;
+        auto add = [&](const void* p, size_t bytes) { key.append(reinterpret_cast<const char*>(p), bytes); };
+        const int nz = ss[i]->nz;
+        add(&nz, sizeof nz);
+        if (seed) add(&(*seed)[i], sizeof(int32_t));
+        for (const char* nm : names) { const auto& v = ss[i]->z[nm]; add(v.data(), v.size() * sizeof(double)); }
+        if (!extra.empty()) add(extra[i].data(), extra[i].size() * sizeof(double));
+        auto it = first.find(key);
+        if (it == first.end()) { first.emplace(std::move(key), i); owner[i] = i; }
+        else owner[i] = it->second;
+    }
+}
+}  // namespace
+
 int dstar_NScool_create_models(int n, const int32_t* ids) {
     if (!g_ctx) { g_err = "NScool_init not called"; return -1; }
     std::vector<Star*> ss;
@@ -1215,6 +1240,27 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
                                       ionicb.data(), Yion.data(), Yionb.data(), Zion.data(), Aion.data(),
                                       any_hook ? Tc_cell.data() : nullptr, nullptr);
     dstar_micro_ctrl mc = micro_ctrl_of(ss[0]->c);
+    // table sharing (control share_identical_tables): a star's cell tables are a function of these inputs only
+    // (create_model.f:344-403: rho, composition, T_c; P, P_bar, dm enter through the rho_bar(1) fix-up and shell Urca)
+    bool share = n > 1;
+    for (Star* s : ss) share = share && s->c.share_identical_tables;
+    std::vector<int32_t> cell_owner, face_owner;
+    g_share_stats[0] = g_share_stats[1] = n;
+    if (share && rc == 0) {
+        // the impurity parameter Q (11th moment) is carried by the cell composition too (create_model.f:283-286 copies
+        // ionic_bar) but no cell quantity reads it -- EOS and crust neutrino emissivities take Z, A, Ye, Yn and the
+        // charge moments -- so it stays out of the key (test_shared_tables_are_bit_identical holds this to the bit)
+        std::vector<std::vector<double>> extra(n);
+        for (int i = 0; i < n; ++i) {
+            extra[i] = ss[i]->z["ionic"];
+            for (int k2 = 0; k2 < ss[i]->nz; ++k2) extra[i][11 * k2 + 10] = 0.0;
+            if (any_hook) extra[i].insert(extra[i].end(), &Tc_cell[(size_t)3 * zoff[i]], &Tc_cell[(size_t)3 * zoff[i]] + 3 * ss[i]->nz);
+        }
+        group_identical(ss, {"rho", "P", "P_bar", "dm", "Yion"}, extra, nullptr, cell_owner);
+        rc = dstar_batch_set_table_sharing(b, 1, cell_owner.data());
+        g_share_stats[0] = 0;
+        for (int i = 0; i < n; ++i) g_share_stats[0] += cell_owner[i] == i;
+    }
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 1);
     if (rc == 0) { g_ms[0] = dstar_batch_last_kernel_ms(b, 0); rc = dstar_batch_get_rho_bar1(b, rb1.data()); }
     if (rc == 0 && any_hook) { eval_Tc(true, rb1, Tc_face); rc = dstar_batch_set_Tc_face(b, Tc_face.data()); }
@@ -1224,6 +1270,19 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
             if (!Tc_face.empty())
                 ss[i]->z["Tc_face"].assign(&Tc_face[(size_t)3 * zoff[i]], &Tc_face[(size_t)3 * zoff[i]] + 3 * ss[i]->nz);
         }
+    if (share && rc == 0) {
+        // face tables (create_model.f:406-441): rho_bar (element 1 follows from the cell inputs: the cell owner stands
+        // for it), the face composition with the impurity parameter, the face T_c
+        std::vector<std::vector<double>> extra;
+        if (any_hook) for (int i = 0; i < n; ++i) extra.emplace_back(&Tc_face[(size_t)3 * zoff[i]], &Tc_face[(size_t)3 * zoff[i]] + 3 * ss[i]->nz);
+        std::vector<double> keep(n);
+        for (int i = 0; i < n; ++i) { keep[i] = ss[i]->z["rho_bar"][0]; ss[i]->z["rho_bar"][0] = 0.0; }
+        group_identical(ss, {"rho_bar", "ionic_bar", "Yion_bar"}, extra, &cell_owner, face_owner);
+        for (int i = 0; i < n; ++i) ss[i]->z["rho_bar"][0] = keep[i];
+        rc = dstar_batch_set_table_sharing(b, 2, face_owner.data());
+        g_share_stats[1] = 0;
+        for (int i = 0; i < n; ++i) g_share_stats[1] += face_owner[i] == i;
+    }
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 2);
     if (rc == 0) g_ms[1] = dstar_batch_last_kernel_ms(b, 1);
     std::vector<double> tlnT(DSTAR_NTAB), tCp((size_t)4 * DSTAR_NTAB * total), tGa(tCp.size()), tEn(tCp.size()), tK(tCp.size());
@@ -1377,6 +1436,12 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
 }
 
 int dstar_NScool_evolve_model(int id) { int32_t i = id; return dstar_NScool_evolve_models(1, &i); }
+
+int dstar_NScool_table_sets(int32_t* cell_sets, int32_t* face_sets) {
+    if (cell_sets) *cell_sets = g_share_stats[0];
+    if (face_sets) *face_sets = g_share_stats[1];
+    return 0;
+}
 
 int dstar_NScool_set_evolve_mapping(int mapping) {
     if (mapping < 0 || mapping > 2) { g_err = "evolve mapping: 0 automatic, 1 CTA per star, 2 warp per star"; return -1; }

@@ -123,6 +123,7 @@ DS_D void solve(const Lu<Z>& f, double (&d)[Z]) {   // d: right-hand side in, so
 
 struct WCtx {
     int n, lane, z0;   // zones of the star, lane, first flattened zone
+    int zc0, zf0;      // first slot of the star's cell / face tables (= z0 unless tables are shared)
     bool fixed_atm, insulating;
     int n_tab;
     double x0, inv_dx;
@@ -161,7 +162,7 @@ DS_D void rhs(const WCtx& cx, double* sm, const double (&y)[Z], double (&f)[Z], 
             const double lnT_bar = log(T_bar);
             // get_coefficients :461-524
             const int kK = dsv::spline_locate(cx.tab, cx.n_tab, cx.x0, cx.inv_dx, lnT_bar);
-            const double4 cK = reinterpret_cast<const double4*>(cx.tab_lnK + (size_t)4 * cx.n_tab * (cx.z0 + k))[kK];
+            const double4 cK = reinterpret_cast<const double4*>(cx.tab_lnK + (size_t)4 * cx.n_tab * (cx.zf0 + k))[kK];
             double lnK;
             dsv::spline_poly(cK, lnT_bar - cx.tab[kK], lnK, dlnK[i]);
             Kc[i] = exp(lnK);
@@ -222,8 +223,8 @@ DS_D void rhs(const WCtx& cx, double* sm, const double (&y)[Z], double (&f)[Z], 
         double lo = 0.0, di = 0.0, up = 0.0;
         if (k < n) {
             const int kY = dsv::spline_locate(cx.tab, cx.n_tab, cx.x0, cx.inv_dx, y[i]);
-            const double4 cCp = reinterpret_cast<const double4*>(cx.tab_lnCp + (size_t)4 * cx.n_tab * (cx.z0 + k))[kY];
-            const double4 cEn = reinterpret_cast<const double4*>(cx.tab_lnEnu + (size_t)4 * cx.n_tab * (cx.z0 + k))[kY];
+            const double4 cCp = reinterpret_cast<const double4*>(cx.tab_lnCp + (size_t)4 * cx.n_tab * (cx.zc0 + k))[kY];
+            const double4 cEn = reinterpret_cast<const double4*>(cx.tab_lnEnu + (size_t)4 * cx.n_tab * (cx.zc0 + k))[kY];
             double lnCp, dlnCp, lnenu, dlnenu;
             dsv::spline_poly(cCp, y[i] - cx.tab[kY], lnCp, dlnCp);
             dsv::spline_poly(cEn, y[i] - cx.tab[kY], lnenu, dlnenu);
@@ -291,6 +292,8 @@ __global__ void __launch_bounds__(32 * S) ds_evolve_warp_kernel(DsEvolveArgs a, 
     cx.lane = lane;
     cx.z0 = a.zone_offset[star];
     cx.n = a.zone_offset[star + 1] - cx.z0;
+    cx.zc0 = a.cell_tab_zone0 ? a.cell_tab_zone0[star] : cx.z0;
+    cx.zf0 = a.face_tab_zone0 ? a.face_tab_zone0[star] : cx.z0;
     const int n = cx.n, z0 = cx.z0;
     cx.n_tab = a.n_tab; cx.tab = tab;
     cx.x0 = tab[0];

@@ -79,6 +79,12 @@ struct DsMicroArgs {
     int* redo;        // (total_zones) or null: compact list of the zones whose branch-free divisions left the safe range
     int* redo_count;  // (1) length of that list (zeroed before the branch-free pass)
     int force_redo;  // test hook: flag every zone, so the plain pass recomputes everything
+    // table sharing (dstar_batch_set_table_sharing): only the zones of the stars that OWN a table set are evaluated
+    // (work_list, n_work; null = every zone), and a star's tables start at slot tab_zone0[star] of the compact table
+    // arrays (null = its own zone offset)
+    const int* work_list;
+    int n_work;
+    const int* tab_zone0;
 };
 
 // MESA interp_pm (Steffen 1990) on one zone's 128 knots; i = knot index of this lane, v holds f(1,:) on entry.
@@ -208,10 +214,10 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
     const double T = a.tab_T[kn], lgT = a.tab_lgT[kn];
     // second pass (FAST = false with a redo list): the work items are the list entries, densely packed
     const bool redo_pass = !FAST && a.redo != nullptr;
-    const int n_items = redo_pass ? *a.redo_count : a.total_zones;
+    const int n_items = redo_pass ? *a.redo_count : (a.work_list ? a.n_work : a.total_zones);
     for (int g0 = blockIdx.x * G; g0 < n_items; g0 += gridDim.x * G) {
         const bool on = g0 + grp < n_items;
-        const int gq = redo_pass ? (on ? a.redo[g0 + grp] : 0) : g0 + grp;
+        const int gq = redo_pass ? (on ? a.redo[g0 + grp] : 0) : (a.work_list ? (on ? a.work_list[g0 + grp] : 0) : g0 + grp);
         if (it == 0) { s_err[grp] = 0; s_lam[grp] = nan(""); s_lam_ierr[grp] = 0; s_bad[grp] = 0; }
         __syncthreads();   // start of round: all groups aligned
         // groups past the end re-evaluate the last zone (results discarded) so that every thread of the
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             if (FAST && bad) s_bad[grp] = 1;
         }
         __syncthreads();
-        const size_t ob = (size_t)4 * DS_NTAB * g;
+        const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
         if (!FACE) {
             ds_group_interp_pm(on, kn, s_h, s_v[grp][2], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
             ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
@@ -463,6 +469,12 @@ __global__ void ds_crust_composition_kernel(DsCompArgs a) {
     double* o = a.ionic + (size_t)11 * z;
     o[0] = A; o[1] = sZ * A; o[2] = sZ53 * A; o[3] = sZ2 * A; o[4] = sZ73 * A; o[5] = sZ52 * A;
     o[6] = sZZ1 * A; o[7] = sX; o[8] = Ye; o[9] = Yn; o[10] = o[3] - o[1] * o[1];
+}
+
+// table sharing: a star whose cell tables are another star's also takes that star's rho_bar(1) fix-up (create_model.f:367-369)
+__global__ void ds_share_rho_bar1_kernel(int n_star, const int* __restrict__ owner, double* rho_bar1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_star && owner[i] != i) rho_bar1[i] = rho_bar1[owner[i]];
 }
 
 // ------------------------------------------------------------ FP64 peak probe (roofline denominator)

@@ -132,6 +132,16 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
 /* seam A on resident data.  which: 1 = cell loop (lnCp, lnGamma, lnEnu, rho_bar(1) fix-up,
  * create_model.f:344-403), 2 = face loop (lnK, :406-441), 3 = both. */
 int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int which);
+/* Table sharing for sweeps (hard part 8): stars whose coefficient-pass inputs are identical -- same
+ * crust, composition and gaps for the cell tables; additionally the same impurity parameter and face critical
+ * temperatures for the face tables -- need one table set between them.  owner(n_star): owner[i] = index of the first
+ * star of i's group (owner[i] == i for a star that owns its tables; owner[i] <= i); the following coefficient pass
+ * evaluates only the owners' zones, the device keeps one table set per owner, and the evolve kernel reads a star's
+ * coefficients from its owner's set.  which = 1: cell tables (lnCp, lnGamma, lnEnu and the rho_bar(1) fix-up), 2: face
+ * tables (lnK).  owner == NULL ends the sharing.  Call before the dstar_batch_micro_tables pass it concerns; results
+ * are bit-identical to the unshared pass because the inputs are.  (The reference has no counterpart: each NScool_info
+ * slot tabulates for itself, NScool_create_model.f:340-441.) */
+int dstar_batch_set_table_sharing(dstar_batch* b, int which, const int32_t* owner);
 /* D2H: tab_lnT(128); tab_* as (4*128, total_zones) (bit layout of NScool_def.f:130-134 per star);
  * rho_bar1(n_star); status(n_star).  Any pointer may be NULL. */
 int dstar_batch_download_tables(dstar_batch* b, double* tab_lnT, double* tab_lnCp, double* tab_lnGamma,

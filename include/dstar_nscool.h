@@ -51,6 +51,12 @@ int dstar_NScool_evolve_model(int id);
  * one evolve launch for all of them */
 int dstar_NScool_create_models(int n, const int32_t* ids);
 int dstar_NScool_evolve_models(int n, const int32_t* ids);
+/* With the control share_identical_tables = .true. on every star of a batch (a dstar_b200 extension; default .false.,
+ * i.e. every star tabulates for itself as NScool_create_model.f:340-441 does), create_models evaluates one cell-table
+ * set per distinct (structure, composition, T_c) and one face-table set per distinct (cell set, face composition with
+ * its impurity parameter, face T_c); every star still reports its own tables, bit-identical to the unshared ones.
+ * table_sets: how many distinct cell / face sets the last create_models evaluated. */
+int dstar_NScool_table_sets(int32_t* cell_sets, int32_t* face_sets);
 /* thread mapping of the evolve kernel for the following evolve calls (dstar_batch_set_evolve_mapping, dstar_b200.h):
  * 0 automatic, 1 CTA per star, 2 warp per star.  Not a reference control: the results do not depend on it. */
 int dstar_NScool_set_evolve_mapping(int mapping);

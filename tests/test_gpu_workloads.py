@@ -203,6 +203,47 @@ def test_full_size_sweep_properties(nscool, oracle):
         s.free()
 
 
+def test_shared_tables_are_bit_identical(nscool):
+    """share_identical_tables: configs[1] as a 4 x 4 (core Tc, pasta Qimp) grid needs ONE cell-table set (the crust is
+    the same) and four face-table sets (one per Qimp); every star still reports its own tables, bit for bit those of
+    the unshared pass, and evolves to the same bits.  A batch of walkers with different Qimp shares cells only."""
+    from dstar_b200 import workloads
+    ds = nscool
+    plain = workloads.custom_Tc_Qimp(16, resolution=0.3)
+    ds.create_models(plain)
+    assert ds.table_sets() == (16, 16)
+    ds.evolve_models(plain)
+    shared = workloads.custom_Tc_Qimp(16, resolution=0.3)
+    for s in shared:
+        s.set_control("share_identical_tables", True)
+    ds.create_models(shared)
+    assert ds.table_sets() == (1, 4)
+    ds.evolve_models(shared)
+    for a, b in zip(plain, shared):
+        for n in TABS:
+            assert np.array_equal(bits(a.array(n)), bits(b.array(n))), n
+        assert a.array("rho_bar")[0] == b.array("rho_bar")[0]
+        for x, y in zip(a.monitors(), b.monitors()):
+            assert np.array_equal(bits(x), bits(y))
+        np.testing.assert_array_equal(a.counters(), b.counters())
+        assert np.array_equal(bits(a.array("lnT")), bits(b.array("lnT")))
+    for s in plain + shared:
+        s.free()
+    walkers = workloads.fit_lightcurve(6, resolution=0.4)
+    for s in walkers:
+        s.set_control("share_identical_tables", True)
+    ds.create_models(walkers)
+    assert ds.table_sets() == (1, 6)
+    # mixed zone counts never share
+    ragged = [_star(ds, r, share_identical_tables=True) for r in (0.4, 0.4, 0.25)]
+    ds.create_models(ragged)
+    assert ds.table_sets() == (2, 2)
+    ds.evolve_models(ragged)
+    assert np.array_equal(bits(ragged[0].monitors()[1]), bits(ragged[1].monitors()[1]))
+    for s in walkers + ragged:
+        s.free()
+
+
 def test_abuntime_composition_many_species(nscool, oracle):
     """configs[4] flavour (INT-16-2b-demo): crust composition from an abuntime-format table -- ~60 nuclides above the
     abundance threshold per zone (the ion-mixture loop, ion.f:72-83, dominates) blended into HZ90 at depth."""
