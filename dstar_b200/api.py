@@ -229,6 +229,9 @@ class Batch:
         """0 automatic, 1 CTA per star, 2 warp per star (dstar_batch_set_evolve_mapping)."""
         check(self.L.dstar_batch_set_evolve_mapping(self.h, int(mapping)), "dstar_batch_set_evolve_mapping")
 
+    def set_evolve_occupancy(self, ctas_per_sm):
+        check(self.L.dstar_batch_set_evolve_occupancy(self.h, int(ctas_per_sm)), "dstar_batch_set_evolve_occupancy")
+
     def eval_rhs(self, epoch, ctrl=None):
         """get_derivatives and the rows of get_jacobian at the batch's current ln T (dstar_batch_eval_rhs)."""
         ctrl = ctrl or EvolveCtrl.defaults()

@@ -111,7 +111,8 @@ struct dstar_batch {
         int n_work = 0;
         DevBuf<int> d_owner, d_tab0, d_work;
     } share[2];
-    int evolve_mapping = 0;   // dstar_batch_set_evolve_mapping: 0 = automatic, 1 = CTA per star, 2 = warp per star
+    int evolve_mapping = 0;   // dstar_batch_set_evolve_mapping
+    int evolve_minb = 0;      // > 0: CTAs per SM the evolve kernel is compiled for (experiments: DSTAR_EVOLVE_MINB): 0 = automatic, 1 = CTA per star, 2 = warp per star
 };
 
 namespace {
@@ -194,6 +195,25 @@ DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
         if (c->rad_full_on_lgrho > 0.0) k.rad_full_on_lgrho = c->rad_full_on_lgrho;
     }
     return k;
+}
+// CTA-per-star evolve kernel: block size from the largest star, CTAs per SM from the batch size (kernels_evolve.cuh)
+cudaError_t launch_evolve_cta(const DsEvolveArgs& a, const int* list, int count, int max_nz, int sms, int minb_override, cudaStream_t s) {
+    const int threads = ((max_nz + 31) / 32) * 32;
+    int minb = minb_override > 0 ? minb_override : (count <= sms ? 1 : count <= 2 * sms ? 2 : count <= 3 * sms ? 3 : 4);
+    if (threads <= 256) {
+        switch (minb) {
+            case 1: ds_evolve_kernel<256, 1><<<count, threads, 0, s>>>(a, list); break;
+            case 2: ds_evolve_kernel<256, 2><<<count, threads, 0, s>>>(a, list); break;
+            case 3: ds_evolve_kernel<256, 3><<<count, threads, 0, s>>>(a, list); break;
+            default: ds_evolve_kernel<256, 4><<<count, threads, 0, s>>>(a, list); break;
+        }
+    } else if (threads <= 384) {
+        if (minb <= 1) ds_evolve_kernel<384, 1><<<count, threads, 0, s>>>(a, list);
+        else ds_evolve_kernel<384, 2><<<count, threads, 0, s>>>(a, list);
+    } else {
+        ds_evolve_kernel<512, 1><<<count, threads, 0, s>>>(a, list);
+    }
+    return cudaGetLastError();
 }
 // warp-per-star evolve kernel for one zones-per-lane class: one star per 32-thread CTA, as many CTAs per SM as their
 // shared memory allows (6 at Z = 8), so a small batch still spreads over all SMs
@@ -554,6 +574,7 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
             if (!lists[q].empty()) CK(b->ev_class[q].list.upload(lists[q].data(), lists[q].size(), st));
         }
     }
+    { static const int v = [] { const char* e = std::getenv("DSTAR_EVOLVE_MINB"); return e ? std::atoi(e) : 0; }(); b->evolve_minb = v; }
     CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
     CK(cudaEventCreate(&b->ev2)); CK(cudaEventCreate(&b->ev3));
     CK(cudaEventCreateWithFlags(&b->ev_face_in, cudaEventDisableTiming));
@@ -858,6 +879,12 @@ int dstar_batch_reset_state(dstar_batch* b) {
     return DSTAR_OK;
 }
 
+int dstar_batch_set_evolve_occupancy(dstar_batch* b, int ctas_per_sm) {
+    if (!b || ctas_per_sm < 0 || ctas_per_sm > 4) return fail(DSTAR_ERR_ARG, "evolve occupancy: 0 (automatic) .. 4 CTAs per SM");
+    b->evolve_minb = ctas_per_sm;
+    return DSTAR_OK;
+}
+
 static DsEvolveArgs fill_evolve_args(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_cap) {
     dstar_ctx* c = b->ctx;
     DsEvolveArgs a{};
@@ -924,10 +951,7 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
     // 17.6 ms), so "automatic" is the CTA form; the warp form stays selectable.
     const bool warp_form = b->evolve_mapping == 2;
     if (!warp_form) {
-        const int threads = ((b->max_nz + 31) / 32) * 32;
-        if (threads <= 256) ds_evolve_kernel<256><<<b->n_star, threads, 0, s>>>(a, nullptr);
-        else ds_evolve_kernel<512><<<b->n_star, threads, 0, s>>>(a, nullptr);
-        CK(cudaGetLastError());
+        CK(launch_evolve_cta(a, nullptr, b->n_star, b->max_nz, c->prop.multiProcessorCount, b->evolve_minb, s));
         ++launches;
     }
     for (int q = 0; warp_form && q <= DS_N_EVOLVE_CLASS; ++q) {
@@ -940,11 +964,8 @@ int dstar_batch_evolve(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int trace_
             case 8: CK(launch_evolve_warp<8>(a, ec.list.p, ec.count, s)); break;
             case 9: CK(launch_evolve_warp<9>(a, ec.list.p, ec.count, s)); break;
             case 10: CK(launch_evolve_warp<10>(a, ec.list.p, ec.count, s)); break;
-            default: {   // more than 320 zones: CTA-per-star form
-                const int threads = ((ec.max_nz + 31) / 32) * 32;
-                if (threads <= 256) ds_evolve_kernel<256><<<ec.count, threads, 0, s>>>(a, ec.list.p);
-                else ds_evolve_kernel<512><<<ec.count, threads, 0, s>>>(a, ec.list.p);
-            }
+            default:   // more than 320 zones: CTA-per-star form
+                CK(launch_evolve_cta(a, ec.list.p, ec.count, ec.max_nz, c->prop.multiProcessorCount, b->evolve_minb, s));
         }
         CK(cudaGetLastError());
         ++launches;

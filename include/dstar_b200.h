@@ -182,6 +182,10 @@ int dstar_batch_eval_rhs(dstar_batch* b, const dstar_evolve_ctrl* ctrl, int epoc
  * over warp shuffles (nz <= 320; larger stars fall back to 1).  Same formulas and driver, so the same light curves;
  * the CTA form is the faster one on B200 at every batch size measured (profiles/r02_notes.md) and is what 0 selects. */
 int dstar_batch_set_evolve_mapping(dstar_batch* b, int mapping);
+/* tuning knob of mapping 1: how many one-star CTAs the evolve kernel is compiled to keep on an SM (1..4; register
+ * budget 255 / 128 / 80 / 64 per thread).  0 = automatic: 1 up to one star per SM, 2 up to two, ... -- fewer resident
+ * stars run each star faster, more resident stars finish a large batch sooner.  Results do not depend on it. */
+int dstar_batch_set_evolve_occupancy(dstar_batch* b, int ctas_per_sm);
 /* D2H: monitors (n_epoch,n_star) as NScool_def.f:136-144; idid (n_epoch,n_star); counters (7,n_star) =
  * nfcn, njac, nstep, naccpt, nrejct, ndec, nsol (isolve iwork(14:20)); lnT(total_zones); Teff, Lsurf,
  * dt, tsec (n_star); model(n_star).  Any pointer may be NULL. */

@@ -42,9 +42,10 @@ def test_bench_line_has_contract_keys():
     assert d["all_stars_converged"] is True
 
 
-@pytest.mark.gpu
 def test_bench_reference_arm():
-    d = _run("--impl", "reference")
+    """The reference arm is CPU-only: committed sample inputs (bench_data/), the oracle port, no product library."""
+    d = _run("--impl", "reference", "--cpu-sample-stars", "2")
+    assert d["product_library_loaded"] is False
     assert d["impl"] == "reference" and d["value"] > 0 and d["metric"] == "zone_microphysics_evals_per_sec"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
