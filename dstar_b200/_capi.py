@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdstar_b200.so")
+# DSTAR_B200_LIB: another build of the same library (kernel experiments: tools/micro_scan.py)
+LIB_PATH = os.environ.get("DSTAR_B200_LIB") or os.path.join(_HERE, "libdstar_b200.so")
 DATA_DIR = os.path.join(_HERE, "data")
 
 dp = C.POINTER(C.c_double)

@@ -15,7 +15,9 @@
 #include "kernels_evolve.cuh"
 #include "kernels_evolve_warp.cuh"
 #include "kernels_micro.cuh"
+#include "kernels_point.cuh"
 #include "kernels_test.cuh"
+#include "micro_launch.hpp"
 
 constexpr int DS_N_EVOLVE_CLASS = 6;
 constexpr int DS_EVOLVE_Z[DS_N_EVOLVE_CLASS] = {2, 4, 6, 8, 9, 10};   // zones per lane: nz <= 64, 128, 192, 256, 288, 320
@@ -69,6 +71,7 @@ struct dstar_ctx {
     DevBuf<double> sf_kF[3], sf_f[3];
     DevBuf<double> tab_lnT, tab_T, tab_lgT;
     double h_tab_lnT[DS_NTAB];
+    DsHostConsts hc{};   // host-evaluated constants (each translation unit with kernels sets its own __constant__ copy)
 };
 
 struct dstar_batch {
@@ -91,12 +94,12 @@ struct dstar_batch {
     DevBuf<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, atm_lgTb, atm_lgTeff, atm_lgflux, heat, T_atm,
         lnT, lnT0, epoch_boundaries, epoch_Mdots, enuc, dt, tsec, t_mon, Teff_mon, Qb_mon, Teff, Lsurf;
     DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot, tr_ext;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_half = nullptr;
     // ordering between the two streams: face inputs / evolve inputs uploaded (copy stream), last compute issued (main)
     cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr, ev_cell_in = nullptr;
     char* h_stage = nullptr;   // pinned staging block for the small result arrays (download_results)
     size_t stage_bytes = 0;
-    double ms[3] = {0, 0, 0};
+    double ms[4] = {0, 0, 0, 0};   // cells, faces, evolve, EOS half of the cells (split pass)
     int launches = 0;
     // evolve launch plan: stars grouped by zones-per-lane class of the warp kernel (kernels_evolve_warp.cuh); the last
     // entry (Z = 0) is the CTA-per-star fallback for stars with more than 320 zones
@@ -138,42 +141,24 @@ void fill_host_consts(DsHostConsts& h) {
     h.yfac = std::sqrt(4.0 * finestructure / pi);
     h.Tp_pre = hbar * std::sqrt(4.0 * pi * finestructure * hbar * clight / Melectron) / boltzmann;
 }
-template <bool FACE, int G>
-cudaError_t launch_micro_g(int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
-    static_assert(16 + DS_PRE + DS_HZ + DS_CP <= DS_NTAB, "the prologue fetches the zone-level inputs with one lane each");
-    const int grid = std::min(sms, (total + G - 1) / G);
-    const size_t dyn = (size_t)G * DS_YMAX * sizeof(double);   // per-group abundances (kernels_micro.cuh: s_Y)
-    // static + dynamic shared memory exceed 48 KB: opt in, once per DEVICE (the attribute is per device and one process
-    // may hold contexts on several)
-    static bool once[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (!once[dev & 63]) {
-        if ((e = cudaFuncSetAttribute(ds_micro_kernel<true, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(ds_micro_kernel<false, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(ds_micro_kernel<false, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
-        once[dev & 63] = true;
-    }
-    if (FACE) {  // one plain pass (a.redo must be null)
-        ds_micro_kernel<true, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
-    } else {     // branch-free pass, then the plain pass over the zones it flagged (normally none)
-        ds_micro_kernel<false, G, true><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
-        ds_micro_kernel<false, G, false><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
-    }
-    return cudaGetLastError();
-}
-template <bool FACE>
-cudaError_t launch_micro(int G, int sms, int total, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
-    switch (G) {
-        case 6: return launch_micro_g<FACE, 6>(sms, total, s, a, h, sf);
-        default: return launch_micro_g<FACE, 7>(sms, total, s, a, h, sf);
-    }
-}
-int micro_minb() {  // zone groups (of 128 lanes) per persistent CTA: 7 (default, 72 regs) or 6 (80 regs).
-    // B200, 144 stars: cell pass G=3 8.8 ms, 4 6.8, 5 5.7, 6 5.4, 7 5.2, 8 5.5 (profiles/r01_notes.md)
-    static int v = [] { const char* e = std::getenv("DSTAR_MICRO_MINB"); return e ? std::atoi(e) : 7; }();
-    return v;
+// Coefficient-pass launch plan (kernels_micro.cuh, micro_*.cu).  Zone groups (of 128 lanes) per persistent CTA:
+//   faces and the fused cell kernel 7 (896 threads, 72 registers; B200, 144 stars, fused cell pass: G=3 8.8 ms, 4 6.8,
+//   5 5.7, 6 5.4, 7 5.2, 8 5.5 -- profiles/r01_notes.md), the EOS half 7, the neutrino half 8 (64 registers, no spill
+//   frame).  DSTAR_MICRO_SPLIT=0 selects the fused cell kernel, DSTAR_MICRO_MINB / _G_EOS / _G_NU the group counts
+//   (experiments; a count the library was not compiled for falls back to the default).
+struct MicroPlan { int split, g_cell, g_eos, g_nu, g_face; };
+const MicroPlan& micro_plan() {
+    static const MicroPlan p = [] {
+        auto geti = [](const char* k, int d) { const char* e = std::getenv(k); return e ? std::atoi(e) : d; };
+        MicroPlan q;
+        q.split = geti("DSTAR_MICRO_SPLIT", 1);
+        q.g_cell = q.g_face = geti("DSTAR_MICRO_MINB", 7);
+        q.g_face = geti("DSTAR_MICRO_G_FACE", q.g_face);
+        q.g_eos = geti("DSTAR_MICRO_G_EOS", 7);
+        q.g_nu = geti("DSTAR_MICRO_G_NU", 8);
+        return q;
+    }();
+    return p;
 }
 DsEosCtrl eos_ctrl_from(const dstar_micro_ctrl* c) {
     DsEosCtrl e{175.0, 140.0, DS_R4(1.0e-9)};  // dStar_eos_def.f:58-62
@@ -276,7 +261,7 @@ int dstar_ctx_create(int device, dstar_ctx** out) {
     CK(cudaGetDeviceProperties(&c->prop, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    DsHostConsts hc;
+    DsHostConsts& hc = c->hc;
     fill_host_consts(hc);
     CK(cudaMemcpyToSymbol(ds_hc, &hc, sizeof hc));
     // table knots (create_model.f:340-341), exp and log10 taken on the host
@@ -556,7 +541,7 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(b->zone_offset.upload(b->h_zone_offset.data(), n_star + 1, st));
     CK(b->zone_star.upload(zs.data(), b->total, st));
     CK(b->status.alloc(n_star)); CK(cudaMemsetAsync(b->status.p, 0, n_star * sizeof(int), st));
-    CK(b->redo.alloc(b->total)); CK(b->redo_count.alloc(1));
+    CK(b->redo.alloc(2 * (size_t)b->total)); CK(b->redo_count.alloc(2));   // [0] EOS half / fused pass, [1] neutrino half
     CK(b->rho_bar1.alloc(n_star));
     {   // evolve launch plan (see dstar_batch::ev_class)
         std::vector<int> lists[DS_N_EVOLVE_CLASS + 1];
@@ -575,7 +560,7 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
         }
     }
     { static const int v = [] { const char* e = std::getenv("DSTAR_EVOLVE_MINB"); return e ? std::atoi(e) : 0; }(); b->evolve_minb = v; }
-    CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
+    CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1)); CK(cudaEventCreate(&b->ev_half));
     CK(cudaEventCreate(&b->ev2)); CK(cudaEventCreate(&b->ev3));
     CK(cudaEventCreateWithFlags(&b->ev_face_in, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_evolve_in, cudaEventDisableTiming));
@@ -596,6 +581,7 @@ void dstar_batch_destroy(dstar_batch* b) {
     if (b->ev_cell_in) cudaEventDestroy(b->ev_cell_in);
     if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev_half) cudaEventDestroy(b->ev_half);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev2) cudaEventDestroy(b->ev2);
     if (b->ev3) cudaEventDestroy(b->ev3);
@@ -709,9 +695,24 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             const dstar_batch::Share& sh = b->share[0];
             a.work_list = sh.on ? sh.d_work.p : nullptr; a.n_work = sh.n_work; a.tab_zone0 = sh.on ? sh.d_tab0.p : nullptr;
             ds_zone_aux_kernel<false><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
-            CK(cudaMemsetAsync(b->redo_count.p, 0, sizeof(int), s));
+            CK(cudaMemsetAsync(b->redo_count.p, 0, 2 * sizeof(int), s));
             a.force_redo = g_force_redo;   // test hook (dstar_debug_force_redo)
-            CK(launch_micro<false>(micro_minb(), sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf));
+            const int n_items = sh.on ? sh.n_work : b->total;
+            const MicroPlan& mp = micro_plan();
+            // branch-free pass, then the plain pass over the zones it flagged (normally none); the two halves of the
+            // split pass keep separate lists
+            if (mp.split) {
+                CK(ds_launch_micro_eos(mp.g_eos, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(ds_launch_micro_eos(mp.g_eos, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(cudaEventRecord(b->ev_half, s));
+                a.redo = b->redo.p + b->total; a.redo_count = b->redo_count.p + 1;
+                CK(ds_launch_micro_nu(mp.g_nu, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(ds_launch_micro_nu(mp.g_nu, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                ++b->launches;
+            } else {
+                CK(ds_launch_micro_cell(mp.g_cell, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(ds_launch_micro_cell(mp.g_cell, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+            }
             if (sh.on) ds_share_rho_bar1_kernel<<<(b->n_star + 127) / 128, 128, 0, s>>>(b->n_star, sh.d_owner.p, b->rho_bar1.p);
             ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
         }
@@ -728,7 +729,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             a.work_list = sh.on ? sh.d_work.p : nullptr; a.n_work = sh.n_work; a.tab_zone0 = sh.on ? sh.d_tab0.p : nullptr;
             CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
             ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
-            CK(launch_micro<true>(micro_minb(), sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf));
+            CK(ds_launch_micro_face(micro_plan().g_face, false, sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf, c->hc));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev3, s));
@@ -739,6 +740,8 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
     if (which & 1) {
         CK(cudaEventSynchronize(b->ev1));
         float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[0] = ms;
+        b->ms[3] = 0.0;
+        if (micro_plan().split) { CK(cudaEventElapsedTime(&ms, b->ev0, b->ev_half)); b->ms[3] = ms; }
     }
     CK(cudaEventRecord(b->ev_busy, s));
     b->have_tables = true;
@@ -805,6 +808,7 @@ int dstar_batch_download_tables(dstar_batch* b, double* tab_lnT, double* tab_lnC
             }
         }
     }
+    if (rho_bar1) CK(b->rho_bar1.download(rho_bar1, b->n_star, s));
     if (status) CK(b->status.download(status, b->n_star, s));
     CK(cudaStreamSynchronize(s));
     return DSTAR_OK;
@@ -1099,10 +1103,17 @@ int dstar_batch_download_trace_extrema(dstar_batch* b, double* ext) {
 }
 
 double dstar_batch_last_kernel_ms(dstar_batch* b, int which) {
-    if (!b || which < 0 || which > 2) return -1.0;
+    if (!b || which < 0 || which > 3) return -1.0;
     return b->ms[which];
 }
 int dstar_batch_last_launch_count(dstar_batch* b) { return b ? b->launches : 0; }
+int dstar_batch_last_redo_counts(dstar_batch* b, int32_t* counts) {
+    if (!b || !counts) return fail(DSTAR_ERR_ARG, "batch_last_redo_counts");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(b->redo_count.download(counts, 2, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    return DSTAR_OK;
+}
 
 int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, int ncharged, const double* rho,
                        const double* rho_bar, const double* P, const double* P_bar, const double* dm,

@@ -841,7 +841,10 @@ struct DsEosRes {
 // FAST selects the branch-free divisions (DsDen, dconst.cuh); `bad` is raised when an operand left their
 // safe range, and the caller then repeats the evaluation with FAST = false (all lanes of the CTA together,
 // because of the DS_PHASE barriers inside).
-template <bool FAST>
+// COMP selects the components to evaluate (the others contribute zero): a kernel that holds only some of them writes
+// partial sums that a later kernel completes (kernels_micro.cuh, split cell pass).
+enum { DS_EOS_ELECTRON = 1, DS_EOS_EXCHANGE = 2, DS_EOS_ION = 4, DS_EOS_NEUTRON = 8, DS_EOS_RADIATION = 16, DS_EOS_ALL = 31 };
+template <bool FAST, int COMP = DS_EOS_ALL>
 DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double rho, double T,
                             double logT, const DsComp& c, const DsZonePre& zp, const DsHelmZone& hz, int ncharged,
                             const double* __restrict__ Zion, const double* __restrict__ Aion,
@@ -858,7 +861,7 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     DsThermo e{0, 0, 0, 0, 0, 0, 0};
     double eta_e = 0.0;
     int ierr_h = 0;
-    if (!(fabs(c.Yn - 1.0) <= (double)1.1920929e-07f)) {
+    if ((COMP & DS_EOS_ELECTRON) && !(fabs(c.Yn - 1.0) <= (double)1.1920929e-07f)) {
         DsHelmOut he;
         ierr_h = ds_helm_electron(helm, T, logT, hz, he);   // hz: ds_helm_zone(helm, rho, A / (1 - Yn), Z)
         if (ierr_h == 0) {
@@ -868,18 +871,22 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
         }
     }
     DS_PHASE();
-    DsThermo ex;
-    dse::ee_exchange<FAST>(Gamma_e, rs, ex, bad);
-    DS_PHASE();
+    DsThermo ex{0, 0, 0, 0, 0, 0, 0};
+    if (COMP & DS_EOS_EXCHANGE) {
+        dse::ee_exchange<FAST>(Gamma_e, rs, ex, bad);
+        DS_PHASE();
+    }
     const double nek = ne * boltzmann;
     const double nekT = nek * T;
     const double uexfac = nekT / den(rho), pexfac = nekT, sexfac = nek / den(rho);
 
     // ions (ion.f:20-92)
-    DsThermo ion;
-    int phase;
-    dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad, act, nact);
-    DS_PHASE();
+    DsThermo ion{0, 0, 0, 0, 0, 0, 0};
+    int phase = 0;
+    if (COMP & DS_EOS_ION) {
+        dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad, act, nact);
+        DS_PHASE();
+    }
     const double n_i = ne / den(c.Z);
     const double nik = n_i * boltzmann;
     const double nikT = nik * T;
@@ -887,13 +894,15 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
 
     // dripped neutrons (neutron.f:15-69)
     const double nn = rho * c.Yn / den_c(amu) / den(1.0 - chi);
-    DsThermo nt;
-    dse::MB77<FAST>(nn, T, Tns, zp, nt, bad);
-    DS_PHASE();
+    DsThermo nt{0, 0, 0, 0, 0, 0, 0};
+    if (COMP & DS_EOS_NEUTRON) {
+        dse::MB77<FAST>(nn, T, Tns, zp, nt, bad);
+        DS_PHASE();
+    }
     const double unfac = avogadro * c.Yn, pnfac = 1.0, snfac = unfac;
 
-    DsThermo rad;
-    dse::get_radiation_eos<FAST>(rho, T, rad, bad);
+    DsThermo rad{0, 0, 0, 0, 0, 0, 0};
+    if (COMP & DS_EOS_RADIATION) dse::get_radiation_eos<FAST>(rho, T, rad, bad);
 
     const double p = e.p + ex.p * pexfac + ion.p * pifac + nt.p * pnfac + rad.p;
     const double u = e.u + ex.u * uexfac + ion.u * uifac + nt.u * unfac + rad.u;

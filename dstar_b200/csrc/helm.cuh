@@ -60,28 +60,39 @@ struct W4 {
 struct Corners {
     const double *c00, *c10, *c01, *c11;
 };
-// biquintic sum in the reference's term order (helm_core.f:244-262); k indexes the record field
-DS_D Sd h5(const Corners& q, const W6& t, const W6& d) {
 #define FQ(k, A) S(__ldg(q.A + (k)))
-    Sd r = FQ(0, c00) * d.w0 * t.w0 + FQ(0, c10) * d.w0m * t.w0;
-    r = r + FQ(0, c01) * d.w0 * t.w0m + FQ(0, c11) * d.w0m * t.w0m;
-    r = r + FQ(1, c00) * d.w0 * t.w1 + FQ(1, c10) * d.w0m * t.w1;
-    r = r + FQ(1, c01) * d.w0 * t.w1m + FQ(1, c11) * d.w0m * t.w1m;
-    r = r + FQ(2, c00) * d.w0 * t.w2 + FQ(2, c10) * d.w0m * t.w2;
-    r = r + FQ(2, c01) * d.w0 * t.w2m + FQ(2, c11) * d.w0m * t.w2m;
-    r = r + FQ(3, c00) * d.w1 * t.w0 + FQ(3, c10) * d.w1m * t.w0;
-    r = r + FQ(3, c01) * d.w1 * t.w0m + FQ(3, c11) * d.w1m * t.w0m;
-    r = r + FQ(4, c00) * d.w2 * t.w0 + FQ(4, c10) * d.w2m * t.w0;
-    r = r + FQ(4, c01) * d.w2 * t.w0m + FQ(4, c11) * d.w2m * t.w0m;
-    r = r + FQ(5, c00) * d.w1 * t.w1 + FQ(5, c10) * d.w1m * t.w1;
-    r = r + FQ(5, c01) * d.w1 * t.w1m + FQ(5, c11) * d.w1m * t.w1m;
-    r = r + FQ(6, c00) * d.w2 * t.w1 + FQ(6, c10) * d.w2m * t.w1;
-    r = r + FQ(6, c01) * d.w2 * t.w1m + FQ(6, c11) * d.w2m * t.w1m;
-    r = r + FQ(7, c00) * d.w1 * t.w2 + FQ(7, c10) * d.w1m * t.w2;
-    r = r + FQ(7, c01) * d.w1 * t.w2m + FQ(7, c11) * d.w1m * t.w2m;
-    r = r + FQ(8, c00) * d.w2 * t.w2 + FQ(8, c10) * d.w2m * t.w2;
-    r = r + FQ(8, c01) * d.w2 * t.w2m + FQ(8, c11) * d.w2m * t.w2m;
-    return r;
+// Biquintic sums in the reference's term order (helm_core.f:244-262): for the record fields k = 0..8
+// (f, ft, ftt, fd, fdd, fdt, fddt, fdtt, fddtt) the density weight w0/w1/w2 and the temperature weight w0/w1/w2 that
+// multiply it, the four corners of each field in the order (i,j), (i+1,j), (i,j+1), (i+1,j+1):
+//   sum = f00 d.w t.w + f10 d.wm t.w + f01 d.w t.wm + f11 d.wm t.wm + (next field) ...   accumulated left to right.
+// h5n forms NT such sums over the SAME density weights d and NT temperature-weight sets, term by term: the products
+// f * d.w are formed once and used NT times.  (Written as five independent sums, the compiler merged them the other
+// way round: all 72 products f * sd.w, f * dsd.w of the first sums were kept for the later ones -- a 580-byte spill
+// frame per thread.)
+template <int I> DS_D Sd wP(const W6& w) { return I == 0 ? w.w0 : I == 1 ? w.w1 : w.w2; }
+template <int I> DS_D Sd wM(const W6& w) { return I == 0 ? w.w0m : I == 1 ? w.w1m : w.w2m; }
+template <int NT, int K, int DI, int TI, bool FIRST>
+DS_D void h5n_field(const Corners& q, const W6& d, const W6* const (&t)[NT], Sd (&r)[NT]) {
+    const Sd p00 = FQ(K, c00) * wP<DI>(d), p10 = FQ(K, c10) * wM<DI>(d);
+    const Sd p01 = FQ(K, c01) * wP<DI>(d), p11 = FQ(K, c11) * wM<DI>(d);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const Sd tp = wP<TI>(*t[n]), tm = wM<TI>(*t[n]);
+        const Sd a = FIRST ? p00 * tp + p10 * tp : r[n] + p00 * tp + p10 * tp;
+        r[n] = a + p01 * tm + p11 * tm;
+    }
+}
+template <int NT>
+DS_D void h5n(const Corners& q, const W6& d, const W6* const (&t)[NT], Sd (&r)[NT]) {
+    h5n_field<NT, 0, 0, 0, true>(q, d, t, r);
+    h5n_field<NT, 1, 0, 1, false>(q, d, t, r);
+    h5n_field<NT, 2, 0, 2, false>(q, d, t, r);
+    h5n_field<NT, 3, 1, 0, false>(q, d, t, r);
+    h5n_field<NT, 4, 2, 0, false>(q, d, t, r);
+    h5n_field<NT, 5, 1, 1, false>(q, d, t, r);
+    h5n_field<NT, 6, 2, 1, false>(q, d, t, r);
+    h5n_field<NT, 7, 1, 2, false>(q, d, t, r);
+    h5n_field<NT, 8, 2, 2, false>(q, d, t, r);
 }
 // bicubic sum (helm_core.f:282-290); base = first field of the 4-field group
 DS_D Sd h3(const Corners& q, int base, const W4& t, const W4& d) {
@@ -170,15 +181,28 @@ DS_D int ds_helm_electron(const DsHelmDev& h, double T, double logT, const DsHel
     const W6& dsd = hz.dsd;
     const W4& cd = hz.cd;
 
+    // Two passes over the cell's 36 table values: the sums that share the density-derivative weights (dF/dd,
+    // d2F/dd dT), then the ones that share the plain density weights (dF/dT, d2F/dT2, F).  The node pointer is laundered
+    // between the passes so that the table values are loaded again (L1 hits) instead of being kept in registers.
     const W6 st{psi0(xt), psi1(xt) * dt, psi2(xt) * dt2, psi0(mxt), -psi1(mxt) * dt, psi2(mxt) * dt2};
     const W6 dst{dpsi0(xt) * dti, dpsi1(xt), dpsi2(xt) * dt, -dpsi0(mxt) * dti, dpsi1(mxt), -dpsi2(mxt) * dt};
-    const W6 ddst{ddpsi0(xt) * dt2i, ddpsi1(xt) * dti, ddpsi2(xt), ddpsi0(mxt) * dt2i, -ddpsi1(mxt) * dti, ddpsi2(mxt)};
-
-    const Sd free_ = h5(q, st, sd);
-    const Sd df_d = h5(q, st, dsd);
-    const Sd df_t = h5(q, dst, sd);
-    const Sd df_tt = h5(q, ddst, sd);
-    const Sd df_dt = h5(q, dst, dsd);
+    Sd free_, df_d, df_t, df_tt, df_dt;
+    {
+        const W6* const ts[2] = {&st, &dst};
+        Sd r[2];
+        h5n<2>(q, dsd, ts, r);
+        df_d = r[0]; df_dt = r[1];
+    }
+    {
+        const double* b2 = base;
+        asm volatile("" : "+l"(b2));
+        const Corners q2{b2, b2 + DS_HELM_REC, b2 + (size_t)DS_HELM_REC * h.imax, b2 + (size_t)DS_HELM_REC * h.imax + DS_HELM_REC};
+        const W6 ddst{ddpsi0(xt) * dt2i, ddpsi1(xt) * dti, ddpsi2(xt), ddpsi0(mxt) * dt2i, -ddpsi1(mxt) * dti, ddpsi2(mxt)};
+        const W6* const ts[3] = {&dst, &ddst, &st};
+        Sd r[3];
+        h5n<3>(q2, sd, ts, r);
+        df_t = r[0]; df_tt = r[1]; free_ = r[2];
+    }
 
     const W4 ct{xpsi0(xt), xpsi1(xt) * dt, xpsi0(mxt), -xpsi1(mxt) * dt};
     Sd dpepdd_in = h3(q, 9, ct, cd);

@@ -17,6 +17,9 @@
 #include "neutrino.cuh"
 
 constexpr int DS_NTAB = 128;
+#ifndef DS_EOS_COMP_X
+#define DS_EOS_COMP_X DS_EOS_ALL   // experiments: components the coefficient kernels evaluate
+#endif
 
 // device-resident gap tables (superfluid_def.f:14-21): f = (4,nv) monotone-cubic coefficients
 struct DsSfDev {
@@ -180,24 +183,37 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     }
 }
 
-template <bool FACE, int G, bool FAST>
+// PART selects what a launch evaluates.  The cell pass of the reference computes the EOS (-> lnCp, lnGamma) and the
+// neutrino emissivity (-> lnEnu) per (zone, knot) in one loop body (create_model.f:344-403); the emissivity takes
+// nothing from the EOS, so the two halves are independent kernels here (DS_PART_EOS + DS_PART_NU), each with the
+// register allocation and group count its own live state wants.  DS_PART_CELL is the fused form (kept selectable:
+// DSTAR_MICRO_SPLIT=0), DS_PART_FACE the face pass (EOS -> Gamma, Theta, mu_e -> conductivity -> lnK).
+enum { DS_PART_CELL = 0, DS_PART_EOS = 1, DS_PART_NU = 2, DS_PART_FACE = 3 };
+
+template <int PART, int G, bool FAST>
 __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
-    __shared__ double s_h[DS_NTAB], s_v[G][3][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
+    constexpr bool FACE = PART == DS_PART_FACE;
+    constexpr bool HAS_EOS = PART != DS_PART_NU;                          // evaluates eval_crust_eos
+    constexpr bool HAS_NU = PART == DS_PART_CELL || PART == DS_PART_NU;   // evaluates the crust neutrino emissivity
+    constexpr bool SPECIES = PART == DS_PART_CELL || PART == DS_PART_EOS; // enters the species loop of ion_mixture
+    constexpr int NV = PART == DS_PART_CELL ? 3 : PART == DS_PART_EOS ? 2 : 1;
+    constexpr int V_ENU = PART == DS_PART_CELL ? 2 : 0;   // row of s_v holding lnEnu
+    __shared__ double s_h[DS_NTAB], s_v[G][NV][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
-    extern __shared__ double s_Ydyn[];   // G * DS_YMAX abundances (dynamic: the static 48 KB are used up)
+    extern __shared__ double s_Ydyn[];   // G * DS_YMAX abundances (dynamic: the static 48 KB are used up); none for DS_PART_NU
     double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_Ydyn);
-    __shared__ unsigned char s_act[G][DS_YMAX];   // indices of the zone's species above the abundance threshold
+    __shared__ unsigned char s_act[SPECIES ? G : 1][DS_YMAX];   // indices of the zone's species above the abundance threshold
     __shared__ int s_nact[G];
     __shared__ DsZonePre s_pre[G];
-    __shared__ DsHelmZone s_hz[G];
+    __shared__ DsHelmZone s_hz[HAS_EOS ? G : 1];
     __shared__ dsk::DsCondPre s_cp[FACE ? G : 1];
-    __shared__ double s_ZA[2][DS_YMAX];       // charge and mass numbers of the network
-    __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];   // per-species constants of the first species (the rest: global)
+    __shared__ double s_ZA[2][HAS_EOS ? DS_YMAX : 1];       // charge and mass numbers of the network
+    __shared__ DsIonZ s_ionz[HAS_EOS ? DS_IONZ_SMEM : 1];   // per-species constants of the first species (the rest: global)
     const int grp = threadIdx.x / DS_NTAB, it = threadIdx.x % DS_NTAB;
     if (threadIdx.x < DS_NTAB - 1) s_h[it] = a.tab_lnT[it + 1] - a.tab_lnT[it];
-    const bool net_in_smem = a.ncharged <= DS_YMAX, ionz_in_smem = a.ncharged <= DS_IONZ_SMEM;
+    const bool net_in_smem = HAS_EOS && a.ncharged <= DS_YMAX, ionz_in_smem = HAS_EOS && a.ncharged <= DS_IONZ_SMEM;
     if (net_in_smem)
         for (int i = threadIdx.x; i < a.ncharged; i += blockDim.x) { s_ZA[0][i] = a.Zion[i]; s_ZA[1][i] = a.Aion[i]; }
     if (ionz_in_smem)
@@ -233,27 +249,23 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         if (it < 11) reinterpret_cast<double*>(&s_zone[grp])[it] = ((FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g)[it];
         else if (it < 16) reinterpret_cast<double*>(&s_zone[grp])[it] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         else if (it < 16 + DS_PRE) reinterpret_cast<double*>(&s_pre[grp])[it - 16] = a.aux[(size_t)DS_AUX * g + (it - 11)];
-        else if (it < 16 + DS_PRE + DS_HZ)
-            reinterpret_cast<double*>(&s_hz[grp])[it - 16 - DS_PRE] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+        else if (HAS_EOS && it < 16 + DS_PRE + DS_HZ)
+            reinterpret_cast<double*>(&s_hz[HAS_EOS ? grp : 0])[it - 16 - DS_PRE] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         else if (FACE && it < 16 + DS_PRE + DS_HZ + DS_CP)
-            reinterpret_cast<double*>(&s_cp[grp])[it - 16 - DS_PRE - DS_HZ] = a.aux[(size_t)DS_AUX * g + (it - 11)];
+            reinterpret_cast<double*>(&s_cp[FACE ? grp : 0])[it - 16 - DS_PRE - DS_HZ] = a.aux[(size_t)DS_AUX * g + (it - 11)];
         const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
-        if (a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
+        if (HAS_EOS && a.ncharged <= DS_YMAX && it < a.ncharged) s_Y[grp][it] = Yg[it];
         __syncthreads();
-        if (!FACE) {   // (the face pass never enters the species loop: its ion thermodynamics are dead code)
+        if (SPECIES) {   // (the face pass never enters the species loop: its ion thermodynamics are dead code)
             if (a.ncharged <= DS_YMAX && it == 0) {   // active-species list of the zone (ascending, as the reference loops)
                 int na = 0;
-                for (int i = 0; i < a.ncharged; ++i) if (s_Y[grp][i] > a.eos.Ythresh) s_act[grp][na++] = (unsigned char)i;
+                for (int i = 0; i < a.ncharged; ++i) if (s_Y[grp][i] > a.eos.Ythresh) s_act[SPECIES ? grp : 0][na++] = (unsigned char)i;
                 s_nact[grp] = na;
             }
             __syncthreads();
         }
         const DsComp& c = s_zone[grp].c;
         const DsZonePre& zp = s_pre[grp];
-        // cells pull the 16 density weights into registers once (read through shared memory inside the biquintic
-        // sums the cell pass is 25 % slower); the face pass, which uses only two of the sums, reads them in place
-        const DsHelmZone hz_regs = FACE ? DsHelmZone{} : s_hz[grp];
-        const DsHelmZone& hz = FACE ? s_hz[grp] : hz_regs;
         const double& rho = s_zone[grp].rho;
         const double& chi = s_zone[grp].chi;
         const double* Tc = s_zone[grp].Tc;
@@ -267,225 +279,49 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
             }
             __syncthreads();
         }
-        {
+        bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
+        if (HAS_EOS) {
+            // the 16 density weights of the HELM interpolation are read in place (shared memory, broadcast): a register
+            // copy per lane added 150 bytes to the spill frame (EOS half 4.39 -> 4.12 ms without it)
+            const DsHelmZone& hz = s_hz[HAS_EOS ? grp : 0];
             DsEosRes r;
             const double* Yz = (a.ncharged <= DS_YMAX) ? s_Y[grp] : Yg;
-            bool bad = false;  // branch-free divisions left their safe operand range somewhere (dconst.cuh)
-            ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, zp, hz, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
-                                    (!FACE && a.ncharged <= DS_YMAX) ? s_act[grp] : nullptr, FACE ? 0 : s_nact[grp]);
+            ds_eval_crust_eos<FAST, DS_EOS_COMP_X>(helm, a.eos, rho, T, lgT, c, zp, hz, a.ncharged, Zn, An, ionz, Yz, Tc[1], chi, r, bad, nullptr,
+                                    (SPECIES && a.ncharged <= DS_YMAX) ? s_act[SPECIES ? grp : 0] : nullptr, SPECIES ? s_nact[grp] : 0);
             if (on && r.ierr != 0) s_err[grp] = r.ierr;
             if (!FACE) {
                 s_v[grp][0][kn] = dsm::log(r.Cp);
-                s_v[grp][1][kn] = dsm::log(r.Gamma);
+                s_v[grp][NV > 1 ? 1 : 0][kn] = dsm::log(r.Gamma);
                 if (on && iz == 0 && kn == 0)  // create_model.f:367-369
                     a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
-                DsNeutrino eps;
-                dsn::ds_crust_neutrino<FAST>(rho, T, c, zp, chi, Tc[1], a.nu_channels, eps, bad);
-                double lnenu = dsm::log(eps.total / rho);
-                if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
-                    if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
-                        lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
-                                                     dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
-                }
-                s_v[grp][2][kn] = lnenu;
             } else {
                 DsCond K;
                 dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, s_cp[FACE ? grp : 0], Tc[1], s_lam[grp],
                                      s_lam_ierr[grp], K);
                 s_v[grp][0][kn] = dsm::log(K.total);
             }
-            if (FAST && bad) s_bad[grp] = 1;
         }
+        if (HAS_NU) {
+            DsNeutrino eps;
+            dsn::ds_crust_neutrino<FAST>(rho, T, c, zp, chi, Tc[1], a.nu_channels, eps, bad);
+            double lnenu = dsm::log(eps.total / rho);
+            if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
+                if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
+                    lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
+                                                 dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
+            }
+            s_v[grp][V_ENU][kn] = lnenu;
+        }
+        if (FAST && bad) s_bad[grp] = 1;
         __syncthreads();
         const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
-        if (!FACE) {
-            ds_group_interp_pm(on, kn, s_h, s_v[grp][2], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
+        if (HAS_NU) ds_group_interp_pm(on, kn, s_h, s_v[grp][V_ENU], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
+        if (HAS_EOS && !FACE) {
             ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
-            ds_group_interp_pm(on, kn, s_h, s_v[grp][1], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
-        } else {
-            ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][NV > 1 ? 1 : 0], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
         }
+        if (FACE) ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
         if (FAST && on && it == 0 && (s_bad[grp] | a.force_redo)) a.redo[atomicAdd(a.redo_count, 1)] = g;
     }
-}
-
-// ---------------------------------------------------------------- batched point evaluators
-struct DsEvalEosArgs {
-    int n, ncharged;
-    const double *rho, *T, *ionic, *Zion, *Aion, *Yion, *Tcs, *chi_in;
-    const DsIonZ* ionz;
-    DsEosCtrl eos;
-    double* res;  // (15, n)
-    double* comps;  // (7, 4, n) or null
-    int* phase;
-    double* chi_out;
-    int* ierr;
-};
-__global__ void ds_eval_eos_kernel(DsEvalEosArgs a, DsHelmDev helm) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.n <= 0) return;
-    const bool live = k < a.n;  // tail threads redo the last point and discard it (DS_PHASE needs all threads)
-    if (!live) k = a.n - 1;
-    DsComp c = ds_load_comp(a.ionic + (size_t)11 * k);
-    double rho = a.rho[k], T = a.T[k];
-    double chi = a.chi_in ? a.chi_in[k] : -1.0;
-    if (chi == -1.0) chi = dse::nuclear_volume_fraction(rho, c, DS_DEFAULT_NUCLEAR_RADIUS);
-    DsEosRes r;
-    bool bad = false;
-    const DsZonePre zp = ds_zone_pre(rho, c, chi);
-    const DsHelmZone hz = ds_helm_zone(helm, rho, c.A / (1.0 - c.Yn), c.Z);
-    double* cp = (a.comps && live) ? a.comps + (size_t)28 * k : nullptr;
-    ds_eval_crust_eos<true>(helm, a.eos, rho, T, dsm::log10(T), c, zp, hz, a.ncharged, a.Zion, a.Aion, a.ionz,
-                            a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, bad, cp);
-    if (__syncthreads_or(bad)) {
-        bool unused = false;
-        ds_eval_crust_eos<false>(helm, a.eos, rho, T, dsm::log10(T), c, zp, hz, a.ncharged, a.Zion, a.Aion, a.ionz,
-                                 a.Yion + (size_t)a.ncharged * k, a.Tcs[3 * (size_t)k + 1], chi, r, unused, cp);
-    }
-    if (!live) return;
-    double* o = a.res + (size_t)15 * k;
-    o[0] = r.lnP; o[1] = r.lnE; o[2] = r.lnS; o[3] = r.grad_ad; o[4] = r.chiRho; o[5] = r.chiT; o[6] = r.Cp;
-    o[7] = r.Cv; o[8] = r.Chi; o[9] = r.Gamma; o[10] = r.Theta; o[11] = r.mu_e; o[12] = r.mu_n;
-    o[13] = r.Gamma1; o[14] = r.Gamma3;
-    a.phase[k] = r.phase;
-    a.chi_out[k] = chi;
-    a.ierr[k] = r.ierr;
-}
-
-struct DsEvalNuArgs {
-    int n;
-    const double *rho, *T, *ionic, *chi, *Tcn;
-    int channels[5];
-    double* eps;  // (6, n)
-};
-__global__ void ds_eval_nu_kernel(DsEvalNuArgs a) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.n <= 0) return;
-    const bool live = k < a.n;
-    if (!live) k = a.n - 1;
-    DsNeutrino e;
-    bool unused = false;
-    const DsComp cc = ds_load_comp(a.ionic + (size_t)11 * k);
-    dsn::ds_crust_neutrino<false>(a.rho[k], a.T[k], cc, ds_zone_pre(a.rho[k], cc, a.chi[k]), a.chi[k], a.Tcn[k],
-                                  a.channels, e, unused);
-    if (!live) return;
-    double* o = a.eps + (size_t)6 * k;
-    o[0] = e.total; o[1] = e.pair; o[2] = e.photo; o[3] = e.plasma; o[4] = e.brems; o[5] = e.pbf;
-}
-
-struct DsEvalCondArgs {
-    int n;
-    const double *rho, *T, *chi, *Gamma, *eta, *mu_e, *ionic, *Tns;
-    DsCondCtrl cond;
-    double* K;  // (10, n)
-};
-__global__ void ds_eval_cond_kernel(DsEvalCondArgs a) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.n <= 0) return;
-    const bool live = k < a.n;
-    if (!live) k = a.n - 1;
-    DsCond c;
-    const DsComp cc = ds_load_comp(a.ionic + (size_t)11 * k);
-    dsk::ds_conductivity(a.cond, a.rho[k], a.T[k], a.chi[k], a.Gamma[k], a.eta[k], a.mu_e[k], cc,
-                         dsk::ds_cond_pre(a.cond, a.rho[k], cc), a.Tns[k], nan(""), 0, c);
-    if (!live) return;
-    double* o = a.K + (size_t)10 * k;
-    o[0] = c.total; o[1] = c.ee; o[2] = c.ei; o[3] = c.eQ; o[4] = c.sf; o[5] = c.nQ; o[6] = c.np; o[7] = c.kap;
-    o[8] = c.electron_total; o[9] = c.neutron_total;
-}
-
-__global__ void ds_sf_kernel(int n, const double* kFp, const double* kFn, double* Tc, DsSfDev sf) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double t[3];
-    ds_sf_get_results(sf, kFp[k], kFn[k], t);
-    Tc[3 * (size_t)k] = t[0]; Tc[3 * (size_t)k + 1] = t[1]; Tc[3 * (size_t)k + 2] = t[2];
-}
-
-// ------------------------------------------------------------ crust composition lookup
-// Device-resident composition table Y_i(lgP) (dStar_crust_def.f:10-24): per isotope a (4,nv)
-// monotone-cubic coefficient block.  One thread per zone: interpolate every isotope, clip
-// negatives, renormalise, moments with neutrons excluded (nucchem_lib.f:47-133).
-struct DsCompArgs {
-    int nz, nv, nisos, ncharged;
-    const double* lgP_tab;  // (nv)
-    const double* Ycoef;    // (4*nv, nisos)
-    const double *Ziso, *Aiso;  // (nisos)
-    // host-evaluated per-isotope powers: Z^(5/3), Z^(7/3), Z^2.5, Z*(Z+1)^1.5
-    const double *Z53, *Z73, *Z52, *ZZ1;
-    const double* lgP;  // (nz)
-    double* ionic;      // (11, nz)
-    double* Yion;       // (ncharged, nz)
-};
-__global__ void ds_crust_composition_kernel(DsCompArgs a) {
-    int z = blockIdx.x * blockDim.x + threadIdx.x;
-    if (z >= a.nz) return;
-    double lgP_c = fmax(a.lgP[z], a.lgP_tab[0]);
-    lgP_c = fmin(lgP_c, a.lgP_tab[a.nv - 1]);
-    const int k = ds_locate(a.lgP_tab, a.nv, lgP_c);
-    const double dx = lgP_c - a.lgP_tab[k];
-    double* Yout = a.Yion + (size_t)a.ncharged * z;
-    // pass 1: Xsum = sum(Y*A) in isotope order (dot_product, nucchem_lib.f:94)
-    double Xsum = 0.0;
-    int ic = 0;
-    for (int i = 0; i < a.nisos; ++i) {
-        const double* c = a.Ycoef + (size_t)4 * a.nv * i + 4 * k;
-        double Y = c[0] + dx * (c[1] + dx * (c[2] + dx * c[3]));
-        if (Y < 0.0) Y = 0.0;
-        Xsum += Y * a.Aiso[i];
-    }
-    // pass 2: renormalise, Ye, Yn in isotope order
-    double Ye = 0.0, Yn = 0.0;
-    ic = 0;
-    for (int i = 0; i < a.nisos; ++i) {
-        const double* c = a.Ycoef + (size_t)4 * a.nv * i + 4 * k;
-        double Y = c[0] + dx * (c[1] + dx * (c[2] + dx * c[3]));
-        if (Y < 0.0) Y = 0.0;
-        Y = Y / Xsum;
-        Ye += Y * a.Ziso[i];
-        if (a.Ziso[i] == 0.0 && a.Aiso[i] == 1.0) Yn += Y;
-        if (a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0) Yout[ic++] = Y;
-    }
-    if (Yn > 0.0 && Yn != 1.0)
-        for (int j = 0; j < a.ncharged; ++j) Yout[j] = Yout[j] / (1.0 - Yn);
-    double sA = 0, sZ = 0, sZ53 = 0, sZ2 = 0, sZ73 = 0, sZ52 = 0, sZZ1 = 0, sX = 0;
-    ic = 0;
-    for (int i = 0; i < a.nisos; ++i)
-        if (a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0) sA += fmin(1.0, fmax(Yout[ic++], 1.0e-50));
-    const double A = 1.0 / sA;
-    ic = 0;
-    for (int i = 0; i < a.nisos; ++i) {
-        if (!(a.Ziso[i] > 0.0 && a.Aiso[i] > 0.0)) continue;
-        const double Y = Yout[ic++], Z = a.Ziso[i];
-        sZ += Y * Z;
-        sZ53 += Y * a.Z53[i];
-        sZ2 += Y * (Z * Z);
-        sZ73 += Y * a.Z73[i];
-        sZ52 += Y * a.Z52[i];
-        sZZ1 += Y * a.ZZ1[i];
-        sX += Z * Z * Y / a.Aiso[i];
-    }
-    double* o = a.ionic + (size_t)11 * z;
-    o[0] = A; o[1] = sZ * A; o[2] = sZ53 * A; o[3] = sZ2 * A; o[4] = sZ73 * A; o[5] = sZ52 * A;
-    o[6] = sZZ1 * A; o[7] = sX; o[8] = Ye; o[9] = Yn; o[10] = o[3] - o[1] * o[1];
-}
-
-// table sharing: a star whose cell tables are another star's also takes that star's rho_bar(1) fix-up (create_model.f:367-369)
-__global__ void ds_share_rho_bar1_kernel(int n_star, const int* __restrict__ owner, double* rho_bar1) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_star && owner[i] != i) rho_bar1[i] = rho_bar1[owner[i]];
-}
-
-// ------------------------------------------------------------ FP64 peak probe (roofline denominator)
-// Eight independent DFMA chains per thread; flops = 2 * 8 * iters * threads.
-__global__ void ds_fp64_peak_kernel(double* out, int iters, double seed) {
-    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
-           a7 = seed + 7;
-    const double m = 0.999999, b = 1.0e-9;
-    for (int i = 0; i < iters; ++i) {
-        a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
-        a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }

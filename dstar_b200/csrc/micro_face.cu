@@ -1,0 +1,11 @@
+// Coefficient pass, faces: EOS (Gamma, Theta, mu_e) + thermal conductivity per (face, knot) -> lnK table
+// (NScool_create_model.f:406-441).
+#define DS_MICRO_PART DS_PART_FACE
+#define DS_MICRO_FN ds_launch_micro_face
+#ifdef DS_MICRO_SCAN
+#define DS_MICRO_GS(X) X(5) X(6) X(7)
+#else
+#define DS_MICRO_GS(X) X(7)
+#endif
+#define DS_MICRO_FAST 0
+#include "micro_part.cuh"

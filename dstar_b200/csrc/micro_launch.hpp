@@ -1,0 +1,22 @@
+// Launchers of the coefficient-pass kernels (kernels_micro.cuh).  Each part of the pass is its own translation unit
+// of libdstar_b200.so (micro_eos.cu, micro_nu.cu, micro_face.cu, micro_cell.cu): the parts compile side by side, and
+// each unit owns its copy of the __constant__ data (ds_hc is set by the launcher, once per device).
+#pragma once
+#include <cuda_runtime.h>
+
+struct DsMicroArgs;
+struct DsHelmDev;
+struct DsSfDev;
+struct DsHostConsts;
+
+// One launch of ds_micro_kernel<PART, G, fast> on stream s: `sms` persistent CTAs at most, n_items work items (an upper
+// bound for a redo pass, whose true count is read on the device).  G = zone groups (of 128 lanes) per CTA; a value the
+// unit was not compiled for selects its default.  Returns the launch error.
+cudaError_t ds_launch_micro_cell(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
+                                 const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);   // EOS + neutrino fused
+cudaError_t ds_launch_micro_eos(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
+                                const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);    // lnCp, lnGamma, rho_bar(1)
+cudaError_t ds_launch_micro_nu(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
+                               const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);     // lnEnu
+cudaError_t ds_launch_micro_face(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
+                                 const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);   // lnK

@@ -1,0 +1,11 @@
+// Coefficient pass, cell half 2: crust neutrino emissivity per (zone, knot) -> lnEnu table, with the shell-Urca term
+// (NScool_create_model.f:371-384, :398-403).
+#define DS_MICRO_PART DS_PART_NU
+#define DS_MICRO_FN ds_launch_micro_nu
+#ifdef DS_MICRO_SCAN
+#define DS_MICRO_GS(X) X(4) X(5) X(6) X(7) X(8)
+#else
+#define DS_MICRO_GS(X) X(8)
+#endif
+#define DS_MICRO_FAST 1
+#include "micro_part.cuh"

@@ -1,0 +1,61 @@
+// Body of one coefficient-pass translation unit: the including .cu defines
+//   DS_MICRO_PART   DS_PART_*            which part of the pass this unit holds
+//   DS_MICRO_FN     ds_launch_micro_*    its launcher (micro_launch.hpp)
+//   DS_MICRO_GS(X)  X(4) X(5) ...        the group counts to compile, the LAST one being the default
+//   DS_MICRO_FAST   0/1                  also compile the branch-free (FAST = true) form
+#include <algorithm>
+
+#include "kernels_micro.cuh"
+#include "micro_launch.hpp"
+
+namespace {
+template <int G, bool FAST>
+cudaError_t launch_g(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+    static_assert(16 + DS_PRE + DS_HZ + DS_CP <= DS_NTAB, "the prologue fetches the zone-level inputs with one lane each");
+    constexpr int PART = DS_MICRO_PART;
+    const int grid = std::max(1, std::min(sms, (n_items + G - 1) / G));
+    // per-group abundances (kernels_micro.cuh: s_Y); the neutrino part has no species data
+    const size_t dyn = PART == DS_PART_NU ? 0 : (size_t)G * DS_YMAX * sizeof(double);
+    // static + dynamic shared memory exceed 48 KB: opt in, once per DEVICE (the attribute is per device and one process
+    // may hold contexts on several)
+    static bool once[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!once[dev & 63]) {
+        if (dyn && (e = cudaFuncSetAttribute(ds_micro_kernel<PART, G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        once[dev & 63] = true;
+    }
+    ds_micro_kernel<PART, G, FAST><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);
+    return cudaGetLastError();
+}
+template <int G>
+cudaError_t launch_f(bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
+#if DS_MICRO_FAST
+    if (fast) return launch_g<G, true>(sms, n_items, s, a, h, sf);
+#endif
+    (void)fast;
+    return launch_g<G, false>(sms, n_items, s, a, h, sf);
+}
+}  // namespace
+
+cudaError_t DS_MICRO_FN(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
+                        const DsSfDev& sf, const DsHostConsts& hc) {
+    static bool hc_set[64] = {};   // this unit's own copy of the host-evaluated constants, per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!hc_set[dev & 63]) {
+        if ((e = cudaMemcpyToSymbol(ds_hc, &hc, sizeof hc)) != cudaSuccess) return e;
+        hc_set[dev & 63] = true;
+    }
+    int last = 0;
+#define DS_X(g) if (G == g) return launch_f<g>(fast, sms, n_items, s, a, h, sf); last = g;
+    DS_MICRO_GS(DS_X)
+#undef DS_X
+    (void)last;
+#define DS_X(g) if (last == g) return launch_f<g>(fast, sms, n_items, s, a, h, sf);
+    DS_MICRO_GS(DS_X)
+#undef DS_X
+    return cudaErrorInvalidValue;
+}

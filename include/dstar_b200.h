@@ -208,10 +208,13 @@ int dstar_batch_download_trace_extrema(dstar_batch* b, double* ext);
  * eps_nu, K) follows from ln T through the coefficient tables on the host. */
 int dstar_batch_set_profile_capture(dstar_batch* b, int interval, int capacity);
 int dstar_batch_download_profiles(dstar_batch* b, int32_t* count, int32_t* model, double* tsec, double* Mdot, double* lnT);
-/* device time [ms] of the last launch of kernel `which` (0 = cell loop, 1 = face loop, 2 = evolve),
- * measured with CUDA events on the library's stream; launches = kernels launched by the last call */
+/* device time [ms] of the last launch of kernel `which` (0 = cell loop, 1 = face loop, 2 = evolve, 3 = the EOS half
+ * of the cell loop: the loop runs as an EOS kernel followed by a neutrino-emissivity kernel), measured with CUDA events on the library's stream; launches = kernels launched by the last call */
 double dstar_batch_last_kernel_ms(dstar_batch* b, int which);
 int dstar_batch_last_launch_count(dstar_batch* b);
+/* zones the last cell pass re-evaluated with plain IEEE divisions because an operand of the branch-free form left its
+ * safe range: counts[0] = EOS half (or the fused kernel), counts[1] = neutrino half.  Normally zero. */
+int dstar_batch_last_redo_counts(dstar_batch* b, int32_t* counts);
 
 /* ---- one-shot host-buffer forms (what the Fortran shim calls for a single star) ---- */
 int dstar_micro_tables(dstar_ctx* ctx, int n_star, const int32_t* zone_offset, int ncharged, const double* rho,
