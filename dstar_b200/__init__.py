@@ -6,7 +6,7 @@ importing works anywhere, but every computation needs libdstar_b200.so and a CUD
 """
 from ._capi import DATA_DIR, LIB_PATH, DStarError, EvolveCtrl, MicroCtrl  # noqa: F401
 from .api import (Batch, Context, NScool, NScool_init, NScool_shutdown, create_models, evolve_models,  # noqa: F401
-                  abuntime_table, host_interp_pm, last_kernel_ms, table_sets)
+                  abuntime_table, host_interp_pm, last_kernel_ms, run_batch, table_sets)
 
 __all__ = ["Batch", "Context", "NScool", "NScool_init", "NScool_shutdown", "create_models", "evolve_models",
-           "host_interp_pm", "abuntime_table", "MicroCtrl", "EvolveCtrl", "DStarError", "DATA_DIR", "LIB_PATH", "last_kernel_ms", "table_sets"]
+           "host_interp_pm", "abuntime_table", "MicroCtrl", "EvolveCtrl", "DStarError", "DATA_DIR", "LIB_PATH", "last_kernel_ms", "table_sets", "run_batch"]

@@ -453,5 +453,25 @@ def evolve_models(stars):
     return _nerr(lib().dstar_NScool_evolve_models(len(ids), p(ids, ip)), "NScool_evolve_models")
 
 
+def run_batch(stars, n_gpu=1, devices=None):
+    """dstar_NScool_run_batch: create + evolve `stars` on n_gpu devices of this node, one host thread per device,
+    contiguous blocks of stars per device.  Returns (t_monitor, Teff_monitor, Qb_monitor) as (number_epochs, n)
+    arrays and the per-star status (0 or the most negative isolve code)."""
+    ids = i32([s.id for s in stars])
+    n = len(ids)
+    st = np.zeros(n, dtype=np.int32)
+    dv = i32(devices) if devices is not None else None
+    L = lib()
+    # first call: no monitor buffers (number_epochs is known only after create_model has read the epochs)
+    _nerr(L.dstar_NScool_run_batch(int(n_gpu), p(dv, ip), n, p(ids, ip), None, None, None, p(st, ip)), "NScool_run_batch")
+    mons = [s.monitors() for s in stars]
+    ne = max(len(m[0]) for m in mons) if mons else 0
+    out = [np.zeros((ne, n)) for _ in range(3)]
+    for i, m in enumerate(mons):
+        for q in range(3):
+            out[q][:len(m[q]), i] = m[q]
+    return out[0], out[1], out[2], st
+
+
 def last_kernel_ms(which):
     return lib().dstar_NScool_last_kernel_ms(int(which))

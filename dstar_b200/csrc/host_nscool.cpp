@@ -17,8 +17,10 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dstar_nscool.h"
@@ -36,9 +38,34 @@ const double density_g = mass_g / (length_g * length_g * length_g);
 const double pressure_g = density_g * potential_g;
 
 std::string g_data_dir;
-dstar_ctx* g_ctx = nullptr;
-double g_ms[3] = {0, 0, 0};
-std::string g_loaded_gaps[3];
+
+// ------------------------------------------------------------------ per-device state
+// One slot per GPU this process uses: the kernel-ABI context, the gap tables loaded into it (with their host copies for
+// the hook path), the cached batch of the last create_models, the last kernel timings.  dstar_NScool_init opens the
+// first slot; dstar_NScool_run_batch opens one per further device and runs one host thread per slot, each thread bound
+// to its slot through t_slot.  Everything else (star handles, crust and atmosphere table caches) is shared by the
+// threads: handles are disjoint between them, the caches are guarded by g_cache_mu.
+struct GapTable { std::vector<double> kF, f; double kmin = 0, kmax = 0; bool loaded = false; };
+struct BatchCache {   // device batch shared by create_models -> evolve_models on the same id list
+    std::vector<int> ids;
+    dstar_batch* b = nullptr;
+    void clear() { if (b) dstar_batch_destroy(b); b = nullptr; ids.clear(); }
+};
+struct DevSlot {
+    int device = -1;
+    dstar_ctx* ctx = nullptr;
+    double ms[3] = {0, 0, 0};
+    std::string loaded_gaps[3];
+    GapTable gaps[3];
+    double sf_scale[3] = {1, 1, 1};
+    BatchCache batch;
+    int table_sets[2] = {0, 0};
+};
+std::vector<std::unique_ptr<DevSlot>> g_slots;   // [0] = the device of dstar_NScool_init
+thread_local DevSlot* t_slot = nullptr;          // set by the worker threads of dstar_NScool_run_batch
+DevSlot g_no_slot;
+DevSlot& cur() { return t_slot ? *t_slot : (g_slots.empty() ? g_no_slot : *g_slots[0]); }
+std::recursive_mutex g_cache_mu;                 // crust-table and atmosphere-table caches
 
 // ------------------------------------------------------------------ controls
 struct Controls {  // NScool/public/NScool_controls.inc, defaults NScool/defaults/controls.defaults
@@ -546,14 +573,11 @@ int process_abuntime(const std::string& path, double lgP_increment, double abund
 }
 
 // ------------------------------------------------------------------ tables shared between stars
-struct GapTable { std::vector<double> kF, f; double kmin = 0, kmax = 0; bool loaded = false; };
-GapTable g_gaps[3];
-double g_sf_scale[3] = {1, 1, 1};
 
 double host_sf_Tc(int id, double kF) {  // superfluid_lib.f:75-101
-    const GapTable& t = g_gaps[id];
+    const GapTable& t = cur().gaps[id];
     if (!t.loaded || kF < t.kmin || kF > t.kmax) return 0.0;
-    return std::max(interp_value(t.kF.data(), (int)t.kF.size(), t.f.data(), kF), 0.0) * g_sf_scale[id];
+    return std::max(interp_value(t.kF.data(), (int)t.kF.size(), t.f.data(), kF), 0.0) * cur().sf_scale[id];
 }
 
 struct CrustTable {  // dStar_crust_def.f:10-24
@@ -608,7 +632,7 @@ struct Star {
 };
 constexpr int max_handles = 1 << 16;  // the reference allows 10 (NScool_def.f:159); batches need many more
 std::vector<std::unique_ptr<Star>> g_stars;
-std::string g_err;
+thread_local std::string g_err;   // per thread: the workers of run_batch report through their own copy
 
 Star* get(int id) {
     if (id < 1 || id > (int)g_stars.size() || !g_stars[id - 1] || !g_stars[id - 1]->in_use) return nullptr;
@@ -619,7 +643,7 @@ int ensure_gaps(const Controls& c) {
     const std::string want[3] = {c.which_proton_1S0_gap, c.which_neutron_1S0_gap, c.which_neutron_3P2_gap};
     const char* code[3] = {"p1", "n1", "n3"};
     for (int t = 0; t < 3; ++t) {
-        if (g_loaded_gaps[t] != want[t]) {
+        if (cur().loaded_gaps[t] != want[t]) {
             std::string path = g_data_dir + "/Tc_data/" + want[t] + "_" + code[t] + ".data";
             GapTable gt;
             std::vector<double> Tc;
@@ -628,18 +652,19 @@ int ensure_gaps(const Controls& c) {
             for (size_t i = 0; i < gt.kF.size(); ++i) gt.f[4 * i] = Tc[i];
             interp_pm(gt.kF.data(), (int)gt.kF.size(), gt.f.data());
             gt.loaded = true;
-            int rc = dstar_ctx_set_gaps(g_ctx, t, (int)gt.kF.size(), gt.kmin, gt.kmax, gt.kF.data(), gt.f.data());
+            int rc = dstar_ctx_set_gaps(cur().ctx, t, (int)gt.kF.size(), gt.kmin, gt.kmax, gt.kF.data(), gt.f.data());
             if (rc != 0) { g_err = dstar_last_error(); return rc; }
-            g_gaps[t] = gt;
-            g_loaded_gaps[t] = want[t];
+            cur().gaps[t] = gt;
+            cur().loaded_gaps[t] = want[t];
         }
-        g_sf_scale[t] = c.scale_sf_critical_temperatures[t];
+        cur().sf_scale[t] = c.scale_sf_critical_temperatures[t];
     }
-    return dstar_ctx_set_sf_scale(g_ctx, g_sf_scale);
+    return dstar_ctx_set_sf_scale(cur().ctx, cur().sf_scale);
 }
 
 // do_generate_crust_table + find_densities (dStar_crust_mod.f:74-171, :282-368); EOS on the device
 int build_crust_table(const Controls& c, std::shared_ptr<CrustTable>& out) {
+    std::lock_guard<std::recursive_mutex> lock(g_cache_mu);   // one thread builds a table, the others find it cached
     char key[256];
     std::snprintf(key, sizeof key, "%s|%.17g|%s|%s|%.17g|%.17g", c.crust_composition.c_str(),
                   c.crust_reference_temperature, c.which_neutron_1S0_gap.c_str(), c.which_proton_1S0_gap.c_str(),
@@ -700,7 +725,7 @@ int build_crust_table(const Controls& c, std::shared_ptr<CrustTable>& out) {
             double kn = std::pow(k::threepisquare * nn, k::onethird) / k::cm_to_fm;
             Tcs[3 * i] = host_sf_Tc(0, 0.0); Tcs[3 * i + 1] = host_sf_Tc(1, kn); Tcs[3 * i + 2] = host_sf_Tc(2, kn);
         }
-        int rc = dstar_eval_crust_eos(g_ctx, N, rho.data(), T.data(), ionic.data(), nch, Zion.data(), Aion.data(),
+        int rc = dstar_eval_crust_eos(cur().ctx, N, rho.data(), T.data(), ionic.data(), nch, Zion.data(), Aion.data(),
                                       Yion.data(), Tcs.data(), chi.data(), eos_ctrl, res.data(), phase.data(),
                                       chio.data(), ie.data());
         if (rc <= -100) return rc;
@@ -894,6 +919,7 @@ int setup_zones(Star& s) {
 // the distinct (grav, Plight, Psurf) triples not yet in the cache go to the device in ONE call (thread = table x
 // knot, kernels_atm.cuh), then interp_pm in lgTb on the host.
 int build_bc09_tables(const std::vector<Star*>& ss) {
+    std::lock_guard<std::recursive_mutex> lock(g_cache_mu);
     std::vector<AtmKey> want;
     for (Star* s : ss) {
         if (s->c.atm_model != "bc09") continue;
@@ -908,7 +934,7 @@ int build_bc09_tables(const std::vector<Star*>& ss) {
         std::vector<int32_t> ierr(nt);
         for (int t = 0; t < nt; ++t) { g[t] = want[t].g; pl[t] = want[t].pl; pb[t] = want[t].pb; }
         for (int i = 0; i < nv; ++i) lgTeff[i] = 5.5 + (double)i * (7.0 - 5.5) / (double)(nv - 1);   // dStar_atm_def.f:7-8
-        const int rc = dstar_atm_bc09_Teff(g_ctx, nt, g.data(), pl.data(), pb.data(), nv, lgTeff.data(), lgTb.data(),
+        const int rc = dstar_atm_bc09_Teff(cur().ctx, nt, g.data(), pl.data(), pb.data(), nv, lgTeff.data(), lgTb.data(),
                                            lgflux.data(), ierr.data(), nullptr);
         if (rc != 0) { g_err = std::string("bc09 atmosphere: ") + dstar_last_error(); return rc; }
         for (int t = 0; t < nt; ++t) {
@@ -996,14 +1022,7 @@ int check_batch_controls(const std::vector<Star*>& ss, bool micro, bool evolve) 
 }
 
 int g_evolve_mapping = 0;   // dstar_NScool_set_evolve_mapping
-int g_share_stats[2] = {0, 0};   // distinct cell / face table sets of the last create_models
 
-// cached device batch shared by create_models -> evolve_models on the same id list
-struct BatchCache {
-    std::vector<int> ids;
-    dstar_batch* b = nullptr;
-    void clear() { if (b) dstar_batch_destroy(b); b = nullptr; ids.clear(); }
-} g_batch;
 
 void concat(const std::vector<Star*>& ss, const char* name, std::vector<double>& out) {
     out.clear();
@@ -1059,24 +1078,38 @@ int dstar_ctx_load_gap_file(dstar_ctx* ctx, int type, const char* path) {
     return dstar_ctx_set_gaps(ctx, type, (int)kF.size(), kmin, kmax, kF.data(), f.data());
 }
 
-int dstar_NScool_init(const char* data_dir, int device) {
-    if (g_ctx) return 0;
-    g_data_dir = data_dir ? data_dir : "";
-    int rc = dstar_ctx_create(device, &g_ctx);
-    if (rc != 0) return rc;
-    rc = dstar_ctx_load_helm_file(g_ctx, (g_data_dir + "/helm_table.bin").c_str());
-    if (rc != 0) { g_err = "unable to read helm table in " + g_data_dir; dstar_ctx_destroy(g_ctx); g_ctx = nullptr; return -1; }
+namespace {
+// open the slot of `device` (context + HELM table); slot 0 is the device of dstar_NScool_init
+int open_slot(int device, DevSlot** out) {
+    for (auto& sl : g_slots) if (sl->device == device) { *out = sl.get(); return 0; }
+    std::unique_ptr<DevSlot> sl(new DevSlot);
+    sl->device = device;
+    int rc = dstar_ctx_create(device, &sl->ctx);
+    if (rc != 0) { g_err = dstar_last_error(); return rc; }
+    rc = dstar_ctx_load_helm_file(sl->ctx, (g_data_dir + "/helm_table.bin").c_str());
+    if (rc != 0) { g_err = "unable to read helm table in " + g_data_dir; dstar_ctx_destroy(sl->ctx); return -1; }
+    g_slots.push_back(std::move(sl));
+    *out = g_slots.back().get();
     return 0;
+}
+}  // namespace
+
+int dstar_NScool_init(const char* data_dir, int device) {
+    if (!g_slots.empty()) return 0;
+    g_data_dir = data_dir ? data_dir : "";
+    DevSlot* sl = nullptr;
+    return open_slot(device, &sl);
 }
 
 void dstar_NScool_shutdown(void) {
-    g_batch.clear();
     g_stars.clear();
     g_crust_cache.clear();
     g_atm_cache.clear();
-    for (auto& s : g_loaded_gaps) s.clear();
-    if (g_ctx) dstar_ctx_destroy(g_ctx);
-    g_ctx = nullptr;
+    for (auto& sl : g_slots) {
+        sl->batch.clear();
+        if (sl->ctx) dstar_ctx_destroy(sl->ctx);
+    }
+    g_slots.clear();
 }
 
 int dstar_alloc_NScool(void) {
@@ -1145,10 +1178,10 @@ void group_identical(const std::vector<Star*>& ss, const std::vector<const char*
 }  // namespace
 
 int dstar_NScool_create_models(int n, const int32_t* ids) {
-    if (!g_ctx) { g_err = "NScool_init not called"; return -1; }
+    if (!cur().ctx) { g_err = "NScool_init not called"; return -1; }
     std::vector<Star*> ss;
     for (int i = 0; i < n; ++i) { Star* s = get(ids[i]); if (!s || !s->setup) { g_err = "bad NScool id"; return -1; } ss.push_back(s); }
-    g_batch.clear();
+    cur().batch.clear();
     if (n > 1 && check_batch_controls(ss, true, false) != 0) return -1;
     // store_controls: epochs (NScool_ctrls_io.f:244-256), startup microphysics, zones
     for (Star* s : ss) {
@@ -1185,7 +1218,7 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
             std::vector<double> io((size_t)11 * lgP.size()), yi((size_t)nch * lgP.size());
             int32_t nc2 = 0;
             CrustTable* ct = g.first;
-            int rc = dstar_crust_composition_info(g_ctx, ct->nv, (int)ct->net.Z.size(), ct->lgP.data(), ct->Ycoef.data(),
+            int rc = dstar_crust_composition_info(cur().ctx, ct->nv, (int)ct->net.Z.size(), ct->lgP.data(), ct->Ycoef.data(),
                                                   ct->net.Z.data(), ct->net.A.data(), (int)lgP.size(), lgP.data(), io.data(),
                                                   yi.data(), &nc2);
             if (rc != 0) { g_err = dstar_last_error(); return rc; }
@@ -1234,7 +1267,7 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
     std::vector<double> Tc_cell, Tc_face, rb1(n, 0.0);
     if (any_hook) eval_Tc(false, rb1, Tc_cell);
     dstar_batch* b = nullptr;
-    int rc = dstar_batch_create(g_ctx, n, zoff.data(), nch, &b);
+    int rc = dstar_batch_create(cur().ctx, n, zoff.data(), nch, &b);
     if (rc != 0) { g_err = dstar_last_error(); return rc; }
     rc = dstar_batch_upload_structure(b, rho.data(), rho_bar.data(), P.data(), P_bar.data(), dm.data(), ionic.data(),
                                       ionicb.data(), Yion.data(), Yionb.data(), Zion.data(), Aion.data(),
@@ -1245,7 +1278,7 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
     bool share = n > 1;
     for (Star* s : ss) share = share && s->c.share_identical_tables;
     std::vector<int32_t> cell_owner, face_owner;
-    g_share_stats[0] = g_share_stats[1] = n;
+    cur().table_sets[0] = cur().table_sets[1] = n;
     if (share && rc == 0) {
         // the impurity parameter Q (11th moment) is carried by the cell composition too (create_model.f:283-286 copies
         // ionic_bar) but no cell quantity reads it -- EOS and crust neutrino emissivities take Z, A, Ye, Yn and the
@@ -1258,11 +1291,11 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
         }
         group_identical(ss, {"rho", "P", "P_bar", "dm", "Yion"}, extra, nullptr, cell_owner);
         rc = dstar_batch_set_table_sharing(b, 1, cell_owner.data());
-        g_share_stats[0] = 0;
-        for (int i = 0; i < n; ++i) g_share_stats[0] += cell_owner[i] == i;
+        cur().table_sets[0] = 0;
+        for (int i = 0; i < n; ++i) cur().table_sets[0] += cell_owner[i] == i;
     }
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 1);
-    if (rc == 0) { g_ms[0] = dstar_batch_last_kernel_ms(b, 0); rc = dstar_batch_get_rho_bar1(b, rb1.data()); }
+    if (rc == 0) { cur().ms[0] = dstar_batch_last_kernel_ms(b, 0); rc = dstar_batch_get_rho_bar1(b, rb1.data()); }
     if (rc == 0 && any_hook) { eval_Tc(true, rb1, Tc_face); rc = dstar_batch_set_Tc_face(b, Tc_face.data()); }
     if (any_hook)
         for (int i = 0; i < n; ++i) {  // keep the hook-evaluated critical temperatures with the star
@@ -1280,11 +1313,11 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
         group_identical(ss, {"rho_bar", "ionic_bar", "Yion_bar"}, extra, &cell_owner, face_owner);
         for (int i = 0; i < n; ++i) ss[i]->z["rho_bar"][0] = keep[i];
         rc = dstar_batch_set_table_sharing(b, 2, face_owner.data());
-        g_share_stats[1] = 0;
-        for (int i = 0; i < n; ++i) g_share_stats[1] += face_owner[i] == i;
+        cur().table_sets[1] = 0;
+        for (int i = 0; i < n; ++i) cur().table_sets[1] += face_owner[i] == i;
     }
     if (rc == 0) rc = dstar_batch_micro_tables(b, &mc, 2);
-    if (rc == 0) g_ms[1] = dstar_batch_last_kernel_ms(b, 1);
+    if (rc == 0) cur().ms[1] = dstar_batch_last_kernel_ms(b, 1);
     std::vector<double> tlnT(DSTAR_NTAB), tCp((size_t)4 * DSTAR_NTAB * total), tGa(tCp.size()), tEn(tCp.size()), tK(tCp.size());
     std::vector<int32_t> status(n);
     if (rc == 0) rc = dstar_batch_download_tables(b, tlnT.data(), tCp.data(), tGa.data(), tEn.data(), tK.data(), rb1.data(), status.data());
@@ -1299,15 +1332,15 @@ int dstar_NScool_create_models(int n, const int32_t* ids) {
         s->created = true; s->tsec = 0; s->dt = 0; s->model = 0;
         if (status[i] != 0) { g_err = "error in helmeos2 while tabulating coefficients"; dstar_batch_destroy(b); return -1; }
     }
-    g_batch.b = b;
-    g_batch.ids.assign(ids, ids + n);
+    cur().batch.b = b;
+    cur().batch.ids.assign(ids, ids + n);
     return 0;
 }
 
 int dstar_NScool_create_model(int id) { int32_t i = id; return dstar_NScool_create_models(1, &i); }
 
 int dstar_NScool_evolve_models(int n, const int32_t* ids) {
-    if (!g_ctx) { g_err = "NScool_init not called"; return -1; }
+    if (!cur().ctx) { g_err = "NScool_init not called"; return -1; }
     std::vector<Star*> ss;
     for (int i = 0; i < n; ++i) { Star* s = get(ids[i]); if (!s || !s->created) { g_err = "model not created"; return -1; } ss.push_back(s); }
     const int ne = ss[0]->number_epochs;
@@ -1318,22 +1351,22 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     const int total = zoff[n];
     dstar_batch* b = nullptr;
     int rc = 0;
-    bool reuse = g_batch.b && g_batch.ids == std::vector<int>(ids, ids + n);
-    if (reuse) b = g_batch.b;
+    bool reuse = cur().batch.b && cur().batch.ids == std::vector<int>(ids, ids + n);
+    if (reuse) b = cur().batch.b;
     else {
-        g_batch.clear();
+        cur().batch.clear();
         const Network& net = ss[0]->crust->net;
         std::vector<double> rho, rho_bar, P, P_bar, dm, ionic, ionicb, Yion, Yionb, Zion, Aion, tCp, tGa, tEn, tK;
         concat(ss, "rho", rho); concat(ss, "rho_bar", rho_bar); concat(ss, "P", P); concat(ss, "P_bar", P_bar); concat(ss, "dm", dm);
         concat(ss, "ionic", ionic); concat(ss, "ionic_bar", ionicb); concat(ss, "Yion", Yion); concat(ss, "Yion_bar", Yionb);
         for (size_t i = 0; i < net.Z.size(); ++i) if (net.Z[i] > 0) { Zion.push_back(net.Z[i]); Aion.push_back(net.A[i]); }
         concat(ss, "tab_lnCp", tCp); concat(ss, "tab_lnGamma", tGa); concat(ss, "tab_lnEnu", tEn); concat(ss, "tab_lnK", tK);
-        rc = dstar_batch_create(g_ctx, n, zoff.data(), ss[0]->ncharged, &b);
+        rc = dstar_batch_create(cur().ctx, n, zoff.data(), ss[0]->ncharged, &b);
         if (rc == 0) rc = dstar_batch_upload_structure(b, rho.data(), rho_bar.data(), P.data(), P_bar.data(), dm.data(), ionic.data(),
                                                        ionicb.data(), Yion.data(), Yionb.data(), Zion.data(), Aion.data(), nullptr, nullptr);
         if (rc == 0) rc = dstar_batch_upload_tables(b, nullptr, tCp.data(), tGa.data(), tEn.data(), tK.data());
         if (rc != 0) { g_err = dstar_last_error(); if (b) dstar_batch_destroy(b); return rc; }
-        g_batch.b = b; g_batch.ids.assign(ids, ids + n);
+        cur().batch.b = b; cur().batch.ids.assign(ids, ids + n);
     }
     std::vector<double> dm_bar, area, ePhi, e2Phi, ePhi_bar, e2Phi_bar, lnT0;
     concat(ss, "dm_bar", dm_bar); concat(ss, "area", area); concat(ss, "ePhi", ePhi); concat(ss, "e2Phi", e2Phi);
@@ -1368,7 +1401,7 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
     if (rc == 0) rc = dstar_batch_set_profile_capture(b, pcap > 0 ? pint : 0, pcap);
     if (rc == 0) rc = dstar_batch_set_evolve_mapping(b, g_evolve_mapping);
     if (rc == 0) rc = dstar_batch_evolve(b, &ec, cap);
-    if (rc == 0) g_ms[2] = dstar_batch_last_kernel_ms(b, 2);
+    if (rc == 0) cur().ms[2] = dstar_batch_last_kernel_ms(b, 2);
     std::vector<double> tm((size_t)ne * n), Tm(tm.size()), Qm(tm.size()), lnT(total), Teff(n), Lsurf(n), dt(n), tsec(n);
     std::vector<int32_t> idid((size_t)ne * n), cnt((size_t)7 * n), model(n);
     if (rc == 0) rc = dstar_batch_download_results(b, tm.data(), Tm.data(), Qm.data(), idid.data(), cnt.data(), lnT.data(),
@@ -1437,9 +1470,82 @@ int dstar_NScool_evolve_models(int n, const int32_t* ids) {
 
 int dstar_NScool_evolve_model(int id) { int32_t i = id; return dstar_NScool_evolve_models(1, &i); }
 
+// The sweep driver over the GPUs of one node: what N processes calling NScool_create_model / NScool_evolve_model do in
+// the reference (NScool/public/NScool_lib.f:40-90, one star per call).  Stars are dealt to the devices in contiguous
+// blocks (sizes differ by at most one, as dstar_b200/dist.py shard_range), one host thread per device runs
+// create_models + evolve_models on its block; nothing is exchanged between the devices -- stars do not interact
+// (NScool_def.f:160) -- and the results stay in the star handles.  Monitors are also returned concatenated.
+int dstar_NScool_run_batch(int n_gpu, const int32_t* devices, int n, const int32_t* ids, double* t_monitor,
+                           double* Teff_monitor, double* Qb_monitor, int32_t* star_status) {
+    if (g_slots.empty()) { g_err = "NScool_init not called"; return -1; }
+    if (n_gpu < 1 || n < 1 || !ids) { g_err = "run_batch: n_gpu >= 1, n >= 1 and an id list are required"; return -1; }
+    if (t_slot) { g_err = "run_batch: not re-entrant"; return -1; }
+    // devices == NULL: the device of NScool_init, then the other devices of the node in index order
+    std::vector<int> devs;
+    if (devices) devs.assign(devices, devices + n_gpu);
+    else {
+        devs.push_back(g_slots[0]->device);
+        for (int d = 0; (int)devs.size() < n_gpu; ++d) if (d != g_slots[0]->device) devs.push_back(d);
+    }
+    std::vector<DevSlot*> slots(n_gpu, nullptr);
+    for (int g = 0; g < n_gpu; ++g) {
+        for (int h = 0; h < g; ++h) if (devs[h] == devs[g]) { g_err = "run_batch: a device is listed twice"; return -1; }
+        int rc = open_slot(devs[g], &slots[g]);
+        if (rc != 0) return rc;
+    }
+    std::vector<int> rcs(n_gpu, 0);
+    std::vector<std::string> errs(n_gpu);
+    std::vector<std::thread> th;
+    const int base = n / n_gpu, rem = n % n_gpu;
+    std::vector<int> lo(n_gpu + 1, 0);
+    for (int g = 0; g < n_gpu; ++g) lo[g + 1] = lo[g] + base + (g < rem ? 1 : 0);
+    for (int g = 0; g < n_gpu; ++g) {
+        th.emplace_back([&, g] {
+            t_slot = slots[g];
+            const int cnt = lo[g + 1] - lo[g];
+            int rc = 0;
+            if (cnt > 0) {
+                rc = dstar_NScool_create_models(cnt, ids + lo[g]);
+                if (rc == 0) rc = dstar_NScool_evolve_models(cnt, ids + lo[g]);
+                if (rc < 0) errs[g] = g_err;
+            }
+            rcs[g] = rc;
+            t_slot = nullptr;
+        });
+    }
+    for (auto& t : th) t.join();
+    int worst = 0;
+    for (int g = 0; g < n_gpu; ++g) {
+        if (rcs[g] < 0 && worst >= 0) { worst = rcs[g]; g_err = "device " + std::to_string(slots[g]->device) + ": " + errs[g]; }
+        else if (rcs[g] > worst && worst >= 0) worst = rcs[g];
+    }
+    // what the last batch call reports for the whole job: distinct table sets summed, kernel times the slowest device's
+    int sets[2] = {0, 0};
+    double ms[3] = {0, 0, 0};
+    for (int g = 0; g < n_gpu; ++g) {
+        if (lo[g + 1] == lo[g]) continue;
+        for (int q = 0; q < 2; ++q) sets[q] += slots[g]->table_sets[q];
+        for (int q = 0; q < 3; ++q) ms[q] = std::max(ms[q], slots[g]->ms[q]);
+    }
+    for (int q = 0; q < 2; ++q) g_slots[0]->table_sets[q] = sets[q];
+    for (int q = 0; q < 3; ++q) g_slots[0]->ms[q] = ms[q];
+    if (worst < 0) return worst;
+    for (int i = 0; i < n; ++i) {
+        Star* s = get(ids[i]);
+        if (!s) continue;
+        for (int e = 0; e < s->number_epochs; ++e) {   // (number_epochs, n): epoch-major, as the batch kernels keep them
+            if (t_monitor) t_monitor[(size_t)e * n + i] = s->t_monitor[e];
+            if (Teff_monitor) Teff_monitor[(size_t)e * n + i] = s->Teff_monitor[e];
+            if (Qb_monitor) Qb_monitor[(size_t)e * n + i] = s->Qb_monitor[e];
+        }
+        if (star_status) { int w = 0; for (int v : s->idid) w = std::min(w, v); star_status[i] = w; }
+    }
+    return worst;
+}
+
 int dstar_NScool_table_sets(int32_t* cell_sets, int32_t* face_sets) {
-    if (cell_sets) *cell_sets = g_share_stats[0];
-    if (face_sets) *face_sets = g_share_stats[1];
+    if (cell_sets) *cell_sets = cur().table_sets[0];
+    if (face_sets) *face_sets = cur().table_sets[1];
     return 0;
 }
 
@@ -1521,7 +1627,7 @@ int dstar_NScool_set_zone_array(int id, const char* name, const double* in, int 
     auto it = s->z.find(nm);
     if (it == s->z.end() || (int)it->second.size() != count) return -2;
     std::copy(in, in + count, it->second.begin());
-    if (g_batch.b && std::find(g_batch.ids.begin(), g_batch.ids.end(), id) != g_batch.ids.end()) g_batch.clear();
+    if (cur().batch.b && std::find(cur().batch.ids.begin(), cur().batch.ids.end(), id) != cur().batch.ids.end()) cur().batch.clear();
     return 0;
 }
 
@@ -1762,7 +1868,7 @@ int dstar_NScool_write_profiles(int id, const char* directory) {
     return 0;
 }
 
-double dstar_NScool_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? g_ms[which] : -1.0; }
+double dstar_NScool_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? cur().ms[which] : -1.0; }
 
 const char* dstar_NScool_last_error(void) { return g_err.c_str(); }
 

@@ -130,6 +130,55 @@ DS_D void ds_group_interp_pm(bool on, int i, const double* __restrict__ hh, doub
     __syncthreads();
 }
 
+// Two tables of the same zone at once (lnCp and lnGamma of the EOS half): the same operations per table as
+// ds_group_interp_pm, with the three CTA barriers shared.
+DS_D void ds_group_interp_pm2(bool on, int i, const double* __restrict__ hh, double* va, double* vb, double* sma, double* smb,
+                              double* sla, double* slb, double* __restrict__ outa, double* __restrict__ outb) {
+    const int n = DS_NTAB;
+    if (on && i < n - 1) { sma[i] = (va[i + 1] - va[i]) / hh[i]; smb[i] = (vb[i + 1] - vb[i]) / hh[i]; }
+    __syncthreads();
+    double s2[2] = {0.0, 0.0};
+    if (on) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double* sm = q ? smb : sma;
+            double s = 0.0;
+            if (i > 0 && i < n - 1) {
+                double p = (sm[i - 1] * hh[i] + sm[i] * hh[i - 1]) / (hh[i - 1] + hh[i]);
+                double sg = copysign(1.0, sm[i - 1]) + copysign(1.0, sm[i]);
+                s = sg * fmin(fmin(fabs(sm[i - 1]), fabs(sm[i])), 0.5 * fabs(p));
+            } else if (i == 0) {
+                double p1 = sm[0] * (1.0 + hh[0] / (hh[0] + hh[1])) - sm[1] * hh[0] / (hh[0] + hh[1]);
+                if (p1 * sm[0] <= 0.0) s = 0.0;
+                else if (fabs(p1) > 2.0 * fabs(sm[0])) s = 2.0 * sm[0];
+                else s = p1;
+            } else {
+                double pn = sm[n - 2] * (1.0 + hh[n - 2] / (hh[n - 2] + hh[n - 3])) -
+                            sm[n - 3] * hh[n - 2] / (hh[n - 2] + hh[n - 3]);
+                if (pn * sm[n - 2] <= 0.0) s = 0.0;
+                else if (fabs(pn) > 2.0 * fabs(sm[n - 2])) s = 2.0 * sm[n - 2];
+                else s = pn;
+            }
+            (q ? slb : sla)[i] = s;
+            s2[q] = s;
+        }
+    }
+    __syncthreads();
+    if (on) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double *sm = q ? smb : sma, *sl = q ? slb : sla, *v = q ? vb : va;
+            double c2 = 0.0, c3 = 0.0;
+            if (i < n - 1) {
+                c2 = (3.0 * sm[i] - 2.0 * sl[i] - sl[i + 1]) / hh[i];
+                c3 = (sl[i] + sl[i + 1] - 2.0 * sm[i]) / (hh[i] * hh[i]);
+            }
+            reinterpret_cast<double4*>(q ? outb : outa)[i] = make_double4(v[i], s2[q], c2, c3);
+        }
+    }
+    __syncthreads();
+}
+
 // Persistent form: ONE CTA per SM, G groups of 128 lanes; group k of CTA b handles zones
 // (b*G + k) + round * gridDim.x * G.  The kernel body is ~430 KB of straight-line SASS executed once per
 // evaluation, far larger than the instruction caches: with independent 128-thread CTAs the SM held six CTAs
@@ -189,21 +238,33 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
 // register allocation and group count its own live state wants.  DS_PART_CELL is the fused form (kept selectable:
 // DSTAR_MICRO_SPLIT=0), DS_PART_FACE the face pass (EOS -> Gamma, Theta, mu_e -> conductivity -> lnK).
 enum { DS_PART_CELL = 0, DS_PART_EOS = 1, DS_PART_NU = 2, DS_PART_FACE = 3 };
+__host__ __device__ constexpr int ds_micro_nb(int part) { return part == DS_PART_EOS ? 2 : 1; }   // tables interpolated together (EOS half: lnCp, lnGamma)
+// dynamic shared memory of ds_micro_kernel<PART, G, *>
+__host__ __device__ constexpr size_t ds_micro_dyn_bytes(int part, int G) {
+    return sizeof(double) * ((size_t)2 * G * ds_micro_nb(part) * 128 + (part == DS_PART_NU ? 0 : (size_t)G * 96));
+}
 
+#ifndef DS_MICRO_CTAS
+#define DS_MICRO_CTAS 1   // experiments: persistent CTAs per SM
+#endif
 template <int PART, int G, bool FAST>
-__global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
+__global__ void __launch_bounds__(DS_NTAB* G, DS_MICRO_CTAS) ds_micro_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     constexpr bool FACE = PART == DS_PART_FACE;
     constexpr bool HAS_EOS = PART != DS_PART_NU;                          // evaluates eval_crust_eos
     constexpr bool HAS_NU = PART == DS_PART_CELL || PART == DS_PART_NU;   // evaluates the crust neutrino emissivity
     constexpr bool SPECIES = PART == DS_PART_CELL || PART == DS_PART_EOS; // enters the species loop of ion_mixture
     constexpr int NV = PART == DS_PART_CELL ? 3 : PART == DS_PART_EOS ? 2 : 1;
     constexpr int V_ENU = PART == DS_PART_CELL ? 2 : 0;   // row of s_v holding lnEnu
-    __shared__ double s_h[DS_NTAB], s_v[G][NV][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
+    constexpr int NB = ds_micro_nb(PART);
+    __shared__ double s_h[DS_NTAB], s_v[G][NV][DS_NTAB];
     __shared__ double s_lam[G];
     __shared__ int s_lam_ierr[G], s_err[G], s_bad[G];
     __shared__ DsZoneIn s_zone[G];
-    extern __shared__ double s_Ydyn[];   // G * DS_YMAX abundances (dynamic: the static 48 KB are used up); none for DS_PART_NU
-    double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_Ydyn);
+    // dynamic part (the static 48 KB are used up): interpolation scratch, then G * DS_YMAX abundances (none for DS_PART_NU)
+    extern __shared__ double s_dyn[];
+    double (*s_m)[NB][DS_NTAB] = reinterpret_cast<double (*)[NB][DS_NTAB]>(s_dyn);
+    double (*s_s)[NB][DS_NTAB] = reinterpret_cast<double (*)[NB][DS_NTAB]>(s_dyn + G * NB * DS_NTAB);
+    double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_dyn + 2 * G * NB * DS_NTAB);
     __shared__ unsigned char s_act[SPECIES ? G : 1][DS_YMAX];   // indices of the zone's species above the abundance threshold
     __shared__ int s_nact[G];
     __shared__ DsZonePre s_pre[G];
@@ -315,12 +376,15 @@ __global__ void __launch_bounds__(DS_NTAB* G, 1) ds_micro_kernel(DsMicroArgs a, 
         if (FAST && bad) s_bad[grp] = 1;
         __syncthreads();
         const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
-        if (HAS_NU) ds_group_interp_pm(on, kn, s_h, s_v[grp][V_ENU], s_m[grp], s_s[grp], a.tab_lnEnu + ob);
-        if (HAS_EOS && !FACE) {
-            ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnCp + ob);
-            ds_group_interp_pm(on, kn, s_h, s_v[grp][NV > 1 ? 1 : 0], s_m[grp], s_s[grp], a.tab_lnGamma + ob);
+        if (HAS_NU) ds_group_interp_pm(on, kn, s_h, s_v[grp][V_ENU], s_m[grp][0], s_s[grp][0], a.tab_lnEnu + ob);
+        if (PART == DS_PART_EOS) {
+            ds_group_interp_pm2(on, kn, s_h, s_v[grp][0], s_v[grp][NV > 1 ? 1 : 0], s_m[grp][0], s_m[grp][NB - 1], s_s[grp][0],
+                                s_s[grp][NB - 1], a.tab_lnCp + ob, a.tab_lnGamma + ob);
+        } else if (HAS_EOS && !FACE) {
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp][0], s_s[grp][0], a.tab_lnCp + ob);
+            ds_group_interp_pm(on, kn, s_h, s_v[grp][NV > 1 ? 1 : 0], s_m[grp][0], s_s[grp][0], a.tab_lnGamma + ob);
         }
-        if (FACE) ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp], s_s[grp], a.tab_lnK + ob);
+        if (FACE) ds_group_interp_pm(on, kn, s_h, s_v[grp][0], s_m[grp][0], s_s[grp][0], a.tab_lnK + ob);
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
         if (FAST && on && it == 0 && (s_bad[grp] | a.force_redo)) a.redo[atomicAdd(a.redo_count, 1)] = g;
     }

@@ -13,9 +13,9 @@ template <int G, bool FAST>
 cudaError_t launch_g(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsSfDev& sf) {
     static_assert(16 + DS_PRE + DS_HZ + DS_CP <= DS_NTAB, "the prologue fetches the zone-level inputs with one lane each");
     constexpr int PART = DS_MICRO_PART;
-    const int grid = std::max(1, std::min(sms, (n_items + G - 1) / G));
-    // per-group abundances (kernels_micro.cuh: s_Y); the neutrino part has no species data
-    const size_t dyn = PART == DS_PART_NU ? 0 : (size_t)G * DS_YMAX * sizeof(double);
+    const int grid = std::max(1, std::min(sms * DS_MICRO_CTAS, (n_items + G - 1) / G));
+    static_assert(DS_NTAB == 128 && DS_YMAX == 96, "ds_micro_dyn_bytes spells these out");
+    const size_t dyn = ds_micro_dyn_bytes(PART, G);   // interpolation scratch + per-group abundances
     // static + dynamic shared memory exceed 48 KB: opt in, once per DEVICE (the attribute is per device and one process
     // may hold contexts on several)
     static bool once[64] = {};
@@ -23,7 +23,7 @@ cudaError_t launch_g(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (!once[dev & 63]) {
-        if (dyn && (e = cudaFuncSetAttribute(ds_micro_kernel<PART, G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ds_micro_kernel<PART, G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
         once[dev & 63] = true;
     }
     ds_micro_kernel<PART, G, FAST><<<grid, DS_NTAB * G, dyn, s>>>(a, h, sf);

@@ -51,6 +51,19 @@ int dstar_NScool_evolve_model(int id);
  * one evolve launch for all of them */
 int dstar_NScool_create_models(int n, const int32_t* ids);
 int dstar_NScool_evolve_models(int n, const int32_t* ids);
+/* The sweep driver over the GPUs of ONE node: create_models + evolve_models for n stars on n_gpu devices.  The stars
+ * are dealt out in contiguous blocks (block sizes differ by at most one), one host thread per device works on its
+ * block, nothing is exchanged between the devices (stars do not interact, NScool_def.f:160).  It replaces N processes
+ * each looping NScool_create_model / NScool_evolve_model over their stars (NScool/public/NScool_lib.f:40-90).
+ *   devices       (n_gpu) CUDA device indices, or NULL = the device of dstar_NScool_init followed by the node's other
+ *                 devices in index order;  the stars of one block must satisfy create_models' batch rules
+ *   t/Teff/Qb_monitor  optional (number_epochs, n) arrays, epoch-major: the monitors of all stars, concatenated in the
+ *                 order of `ids` (they are also in the star handles: dstar_NScool_get_monitors)
+ *   star_status   optional (n): 0, or the most negative isolve return code of the star's epochs
+ * Hooks (dstar_NScool_set_hooks) are called from the worker threads.  Returns as evolve_models: 0, or the first
+ * device's error (< 0; message in dstar_NScool_last_error). */
+int dstar_NScool_run_batch(int n_gpu, const int32_t* devices, int n, const int32_t* ids, double* t_monitor,
+                           double* Teff_monitor, double* Qb_monitor, int32_t* star_status);
 /* With the control share_identical_tables = .true. on every star of a batch (a dstar_b200 extension; default .false.,
  * i.e. every star tabulates for itself as NScool_create_model.f:340-441 does), create_models evaluates one cell-table
  * set per distinct (structure, composition, T_c) and one face-table set per distinct (cell set, face composition with
