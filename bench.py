@@ -35,6 +35,7 @@ UNIT = "evals/s"
 # algorithmic FP64 work per evaluation: cell = EOS + neutrino, face = EOS + conductivity,
 # one ion species, neutron channels off; weighted operation counts incl. transcendentals
 FLOP_CELL, FLOP_FACE = 6.0e3, 1.6e3
+FLOP_EOS = 3.7e3   # the EOS half of a cell evaluation: SURVEY 8d, 6.0 k - 2.3 k (neutrino emissivities)
 ARRS_STRUCT = ["rho", "rho_bar", "P", "P_bar", "dm", "ionic", "ionic_bar", "Yion", "Yion_bar"]
 ARRS_GEOM = ["dm_bar", "area", "ePhi", "e2Phi", "ePhi_bar", "e2Phi_bar"]
 
@@ -345,14 +346,21 @@ def measure_resident(ds, ctx, W, steps, warmup, share=False, sampler=None, sync=
         b.set_table_sharing(1, cell); b.set_table_sharing(2, face)
         sets = (int(np.sum(cell == np.arange(W["n_star"]))), int(np.sum(face == np.arange(W["n_star"]))))
 
+    launches = [0]
+    eos_ms = [0.0]
+
     def step():
         b.reset_state()
         b.micro_tables(W["mc"], 3)
         t_c, t_f = b.kernel_ms(0), b.kernel_ms(1)
+        eos_ms[0] += b.kernel_ms(3)
+        launches[0] += b.launch_count()
         b.evolve(W["ec"], 0)
+        launches[0] += b.launch_count()
         return t_c, t_f, b.kernel_ms(2)
     for _ in range(warmup):
         step()
+    launches[0] = 0; eos_ms[0] = 0.0
     if sync:
         sync()
     if sampler:
@@ -369,6 +377,7 @@ def measure_resident(ds, ctx, W, steps, warmup, share=False, sampler=None, sync=
     res = b.download_results(full=False)
     out = {"cells_ms": tc / steps, "faces_ms": tf / steps, "evolve_ms": te / steps, "step_ms": (tc + tf + te) / steps,
            "wall_s": wall, "clocks": clocks, "res": res, "converged": bool(np.all(res["idid"] >= 0)), "table_sets": sets,
+           "launches": launches[0], "eos_ms": eos_ms[0] / steps, "redo": [int(x) for x in b.redo_counts()],
            "h2d": b._h2d_structure + b._h2d_evolve}
     return out, b
 
@@ -386,9 +395,13 @@ def workload_roofline(workload, W, m, fp64_peak):
     workload, tools/count_flops.py) next to SURVEY 8d's algorithmic estimate for the one-species / electron-only case."""
     counts = load_json("r02_flop_counts.json", {}).get(workload)
     evals_cell = int(np.sum(W["nz"])) * 128
-    out = {"evals_per_pass": evals_cell, "kernel_ms": {"cells": m["cells_ms"], "faces": m["faces_ms"], "evolve": m["evolve_ms"]}}
+    eos_ms = m.get("eos_ms", 0.0)
+    out = {"evals_per_pass": evals_cell, "kernel_ms": {"cells": m["cells_ms"], "cells_eos": eos_ms, "cells_nu": m["cells_ms"] - eos_ms,
+                                                       "faces": m["faces_ms"], "evolve": m["evolve_ms"]}}
     if counts:
-        for kind, ms in (("cell", m["cells_ms"]), ("face", m["faces_ms"])):
+        for kind, ms in (("eos", eos_ms), ("nu", m["cells_ms"] - eos_ms), ("cell", m["cells_ms"]), ("face", m["faces_ms"])):
+            if kind not in counts or ms <= 0:
+                continue
             fl = counts[kind]["flop_per_eval"]
             tf_ = fl * evals_cell / (ms * 1e-3) / 1e12
             out[kind] = {"executed_flop_per_eval": fl, "achieved_tflops": tf_, "frac": tf_ / fp64_peak if fp64_peak > 0 else None,
@@ -460,43 +473,58 @@ def run_b200(args):
                   "table_bytes": 4 * 4096 * int(np.median(nz)) * (3 * ms_["table_sets"][0] + ms_["table_sets"][1]),
                   "table_bytes_unshared": 4 * 4 * 4096 * total}
         bs_.close()
-    # ---------------- roofline of the dominant kernel (coefficient pass), FP64 pipe
+    # ---------------- roofline of the dominant kernel, FP64 pipe
     fp64_peak = ctx.fp64_peak_tflops()
-    # dominant kernel = the cell pass (ds_micro_kernel<cell>: EOS + neutrino emissivities, ~60 % of the step); its
-    # duration is the library's CUDA-event time on the launching stream, averaged over the timed steps
+    # The cell pass runs as two kernels: ds_micro_kernel<EOS> (eval_crust_eos -> lnCp, lnGamma; the dominant kernel,
+    # ~44 % of the step) and ds_micro_kernel<NU> (crust neutrino emissivity -> lnEnu).  Durations are the library's
+    # CUDA-event times on the launching stream, averaged over the timed steps; the EOS time includes its (normally
+    # empty) plain-division launch.  `roofline` is the EOS kernel; `cell_pass` is both kernels together, the figure
+    # comparable with round 1's fused kernel (6.0 kflop per evaluation over the cell time).
     cell_ms = tc / args.steps
+    eos_ms = m["eos_ms"] if m["eos_ms"] > 0 else cell_ms
+    nu_ms = cell_ms - eos_ms
     micro_ms = (tc + tf) / args.steps
-    achieved_tf = FLOP_CELL * evals_cell / (cell_ms * 1e-3) / 1e12
+    split = m["eos_ms"] > 0
+    flop_dom = FLOP_EOS if split else FLOP_CELL
+    achieved_tf = flop_dom * evals_cell / (eos_ms * 1e-3) / 1e12
+    cell_tf = FLOP_CELL * evals_cell / (cell_ms * 1e-3) / 1e12
     both_tf = (FLOP_CELL + FLOP_FACE) * evals_cell / (micro_ms * 1e-3) / 1e12
     alg_bytes = 64.0 * evals_cell       # ~64 B / eval (32 B of spline coefficients per knot and quantity)
+    alg_bytes_dom = (2.0 / 3.0 if split else 1.0) * alg_bytes   # the EOS kernel writes two of the three cell tables
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # DRAM bytes per cell-pass launch: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full` capture of
-    # the named configuration (profiles/r02_traffic.json names the capture); scaled by the zone count when the run's
-    # batch differs from the captured one (the traffic is spill frames + tables, both proportional to the zones)
+    # DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full`
+    # capture of the named configuration (profiles/r02_traffic.json names the capture); scaled by the zone count when
+    # the run's batch differs from the captured one (the traffic is spill frames + tables, both proportional to the zones)
     tr = load_json("r02_traffic.json", {}).get(args.workload)
     traffic, traffic_note = None, "no ncu capture for this workload"
-    if tr:
-        traffic = tr["cell_dram_bytes_per_launch"] * (total / float(tr["zones"]))
+    if tr and split:
+        traffic = tr["eos_dram_bytes_per_launch"] * (total / float(tr["zones"]))
         traffic_note = "bytes per launch from %s (%d zones), scaled to %d zones; algorithmic bytes per launch %.3g" % (
-            tr["capture"], tr["zones"], total, alg_bytes)
+            tr["capture"], tr["zones"], total, alg_bytes_dom)
     wr = workload_roofline(args.workload, W, m, fp64_peak)
-    roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<cell>", "achieved": achieved_tf, "peak": fp64_peak,
+    roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<EOS> (cell pass, EOS half)" if split else "ds_micro_kernel<cell>",
+                "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
                 "traffic_note": traffic_note,
                 "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
                                "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
-                "flops_per_eval": {"cell": FLOP_CELL, "face": FLOP_FACE, "source": "SURVEY.md 8d algorithmic estimate"},
-                "executed": {k: wr.get(k) for k in ("cell", "face", "flop_source")},
+                "flops_per_eval": {"eos": FLOP_EOS, "nu": FLOP_CELL - FLOP_EOS, "cell": FLOP_CELL, "face": FLOP_FACE,
+                                   "source": "SURVEY.md 8d algorithmic estimate (cell = EOS 3.7 k + neutrino 2.3 k)"},
+                "cell_pass": {"achieved": cell_tf, "frac": cell_tf / fp64_peak if fp64_peak > 0 else None,
+                              "note": "EOS + neutrino kernels together: 6.0 kflop per evaluation over the cell time"},
+                "executed": {k: wr.get(k) for k in ("eos", "nu", "cell", "face", "flop_source")},
                 "cell_plus_face": {"achieved": both_tf, "frac": both_tf / fp64_peak if fp64_peak > 0 else None},
-                "fp64_pipe_busy_ncu": load_json("r02_traffic.json", {}).get("fp64_pipe_busy"),
-                "hbm": {"achieved_gbs": alg_bytes / (cell_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "ncu": load_json("r02_traffic.json", {}).get("ncu_" + args.workload),
+                "hbm": {"achieved_gbs": alg_bytes_dom / (eos_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
-                "kernel_ms": {"cells": tc / args.steps, "faces": tf / args.steps, "evolve": te / args.steps}}
+                "kernel_ms": {"cells": cell_ms, "cells_eos": eos_ms, "cells_nu": nu_ms, "faces": tf / args.steps,
+                              "evolve": te / args.steps},
+                "redo_zones": m["redo"]}
     b.close()
     # ---------------- the other named configs at their BASELINE sizes (rank-local; N = 1 default run only)
     others = None
@@ -544,8 +572,9 @@ def run_b200(args):
             "curves_per_sec": n_star * world / (ms_step * 1e-3),
             "e2e": {"value": evals * world / e2e_s, "unit": UNIT, "curves_per_sec": n_star * world / e2e_s,
                     "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            # launches per step: zone pre-pass + cell pass (branch-free) + cell redo pass, zone pre-pass + face pass, evolve
-            "gpu_launches": 6 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            # kernels launched in the timed region, counted by the library (per step: zone pre-pass, EOS kernel + its
+            # plain-division pass, neutrino kernel + its plain-division pass, zone pre-pass, face kernel, evolve)
+            "gpu_launches": m["launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "all_stars_converged": ok, "wall_s_resident_loop": wall_res, "shared_tables": shared, "other_workloads": others}
     if dist is not None:
         # final gather of the light curves (the only collective of the job)

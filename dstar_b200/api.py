@@ -264,6 +264,10 @@ class Batch:
     def kernel_ms(self, which):
         return self.L.dstar_batch_last_kernel_ms(self.h, int(which))
 
+    def launch_count(self):
+        """kernels launched by the last micro_tables / evolve call"""
+        return int(self.L.dstar_batch_last_launch_count(self.h))
+
     def redo_counts(self):
         out = np.zeros(2, dtype=np.int32)
         check(self.L.dstar_batch_last_redo_counts(self.h, p(out, ip)), "last_redo_counts")

@@ -184,7 +184,10 @@ DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
 // CTA-per-star evolve kernel: block size from the largest star, CTAs per SM from the batch size (kernels_evolve.cuh)
 cudaError_t launch_evolve_cta(const DsEvolveArgs& a, const int* list, int count, int max_nz, int sms, int minb_override, cudaStream_t s) {
     const int threads = ((max_nz + 31) / 32) * 32;
-    int minb = minb_override > 0 ? minb_override : (count <= sms ? 1 : count <= 2 * sms ? 2 : count <= 3 * sms ? 3 : 4);
+    // resident stars per SM (B200, 253-zone stars, ms for 148 / 256 / 512 / 768 / 1024 stars -- profiles/r02_notes.md):
+    //   1: 1.32 / 1.87 / 3.60 / 5.20 / 6.64    2: 1.93 / 2.16 / 3.30 / 4.77 / 6.18    4: 2.50 / 2.87 / 3.43 / 4.91 / 6.18
+    // one star per SM (255 registers, no spills) wins until three waves' worth, then two per SM
+    int minb = minb_override > 0 ? minb_override : (count <= 3 * sms ? 1 : count <= 8 * sms ? 2 : 4);
     if (threads <= 256) {
         switch (minb) {
             case 1: ds_evolve_kernel<256, 1><<<count, threads, 0, s>>>(a, list); break;
@@ -708,17 +711,16 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
                 a.redo = b->redo.p + b->total; a.redo_count = b->redo_count.p + 1;
                 CK(ds_launch_micro_nu(mp.g_nu, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
                 CK(ds_launch_micro_nu(mp.g_nu, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                ++b->launches;
+                b->launches += 2;
             } else {
                 CK(ds_launch_micro_cell(mp.g_cell, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
                 CK(ds_launch_micro_cell(mp.g_cell, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
             }
-            if (sh.on) ds_share_rho_bar1_kernel<<<(b->n_star + 127) / 128, 128, 0, s>>>(b->n_star, sh.d_owner.p, b->rho_bar1.p);
-            ++b->launches;  // two launches: branch-free pass + plain pass over flagged zones
+            if (sh.on) { ds_share_rho_bar1_kernel<<<(b->n_star + 127) / 128, 128, 0, s>>>(b->n_star, sh.d_owner.p, b->rho_bar1.p); ++b->launches; }
+            b->launches += 3;   // zone pre-pass, branch-free pass, plain pass over flagged zones (+ 2 more when split)
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev1, s));   // read back after the face pass has been queued: no idle gap between them
-        ++b->launches;
     }
     if (which & 2) {
         CK(cudaEventRecord(b->ev2, s));
@@ -735,7 +737,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventRecord(b->ev3, s));
         CK(cudaEventSynchronize(b->ev3));
         float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev2, b->ev3)); b->ms[1] = ms;
-        ++b->launches;
+        b->launches += 2;   // zone pre-pass, face pass
     }
     if (which & 1) {
         CK(cudaEventSynchronize(b->ev1));

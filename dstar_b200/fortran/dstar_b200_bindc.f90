@@ -143,5 +143,49 @@ module dstar_b200
          import :: c_int, c_ptr
          type(c_ptr), value :: batch, count, model, tsec, Mdot, lnT
       end function
+
+      ! ---- batch controls added in round 2 (include/dstar_b200.h)
+      ! stars with identical coefficient-pass inputs share one table set: owner(i) = 0-based index of the star whose
+      ! tables star i uses (owner(i) = i: owns its tables); which = 1 cell tables, 2 face tables
+      integer(c_int) function dstar_batch_set_table_sharing(batch, which, owner) &
+            & bind(C, name='dstar_batch_set_table_sharing')
+         import :: c_int, c_ptr, c_int32_t
+         type(c_ptr), value :: batch
+         integer(c_int), value :: which
+         integer(c_int32_t), intent(in) :: owner(*)
+      end function
+      ! bc09 envelope tables on the device (dStar_atm_mod.f:46-106): lgTb(nv, n_tab) for n_tab (g, Plight, Pb) triples
+      integer(c_int) function dstar_atm_bc09_Teff(ctx, n_tab, grav, Plight, Pb, nv, lgTeff, lgTb, lgflux, ierr, info) &
+            & bind(C, name='dstar_atm_bc09_Teff')
+         import :: c_int, c_ptr, c_double, c_int32_t
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: n_tab, nv
+         real(c_double), intent(in) :: grav(*), Plight(*), Pb(*), lgTeff(*)
+         real(c_double), intent(out) :: lgTb(*), lgflux(*)
+         integer(c_int32_t), intent(out) :: ierr(*)
+         type(c_ptr), value :: info          ! optional diagnostics (4,nv,n_tab), c_null_ptr to skip
+      end function
+
+      ! ---- the sweep driver (include/dstar_nscool.h): NScool handles are the integers alloc_NScool returns
+      integer(c_int) function dstar_NScool_create_models(n, ids) bind(C, name='dstar_NScool_create_models')
+         import :: c_int, c_int32_t
+         integer(c_int), value :: n
+         integer(c_int32_t), intent(in) :: ids(*)
+      end function
+      integer(c_int) function dstar_NScool_evolve_models(n, ids) bind(C, name='dstar_NScool_evolve_models')
+         import :: c_int, c_int32_t
+         integer(c_int), value :: n
+         integer(c_int32_t), intent(in) :: ids(*)
+      end function
+      ! n stars over n_gpu devices of the node, one host thread per device (replaces n processes looping
+      ! NScool_create_model / NScool_evolve_model, NScool_lib.f:40-90); monitors (number_epochs, n) or c_null_ptr
+      integer(c_int) function dstar_NScool_run_batch(n_gpu, devices, n, ids, t_monitor, Teff_monitor, Qb_monitor, &
+            & star_status) bind(C, name='dstar_NScool_run_batch')
+         import :: c_int, c_ptr, c_int32_t
+         integer(c_int), value :: n_gpu, n
+         type(c_ptr), value :: devices       ! c_loc of an integer(c_int32_t) device list, or c_null_ptr
+         integer(c_int32_t), intent(in) :: ids(*)
+         type(c_ptr), value :: t_monitor, Teff_monitor, Qb_monitor, star_status
+      end function
    end interface
 end module dstar_b200

@@ -48,7 +48,10 @@ def batch_from_star(ds, ctx, s, lnT, heat=HEAT, T_atm=2.4e8):
 @pytest.mark.parametrize("insulating", [False, True])
 def test_device_rhs_and_jacobian_match_oracle(nscool, oracle, insulating):
     """f(y) and the three Jacobian diagonals of every zone, accreting (fixed atmosphere) and cooling epochs, at the
-    initial isothermal profile and at the evolved (non-isothermal) one: relative deviation <= 1e-12 of the row scale."""
+    initial isothermal profile and at the evolved (non-isothermal) one: relative deviation <= 1e-12 of the row scale.
+    f itself is the small difference of neighbouring fluxes (they cancel exactly in an isothermal crust), and the device
+    forms it with precomputed reciprocals of the zone constants, so its deviation is measured against the
+    scale of the terms it is the difference of -- the row scale of the Jacobian -- not against f."""
     ds = nscool
     s = make_star(ds)
     s.create_model()
@@ -72,7 +75,8 @@ def test_device_rhs_and_jacobian_match_oracle(nscool, oracle, insulating):
                 o = ev(y)
                 scale = np.maximum.reduce([np.abs(o["di"]), np.abs(o["lo"]), np.abs(o["up"])]) + 1e-300
                 fscale = np.max(np.abs(o["f"])) + 1e-300
-                assert np.max(np.abs(g["f"] - o["f"])) / fscale < 1e-12
+                fdev = np.max(np.abs(g["f"] - o["f"]) / (scale + fscale))
+                assert fdev < 1e-12, (epoch, fdev)
                 for nm in ("lo", "di", "up"):
                     dev = np.max(np.abs(g[nm] - o[nm]) / scale)
                     worst = max(worst, dev)

@@ -40,8 +40,12 @@ def main():
         zones = line["config"]["zones_total_per_gpu"]
         evals = zones * 128.0
         ent = {"source": "ncu hardware counters, %s, %d zones x 128 knots per launch (tools/count_flops.py)" % (csv_path.split("/")[-1], zones)}
-        for kind, tag in (("cell", "ds_micro_kernel<0, 7, 1>"), ("face", "ds_micro_kernel<1, 7, 0>")):
-            ls = [l for l in read(csv_path) if tag.replace(" ", "") in l["kernel"].replace(" ", "").replace("(bool)", "").replace("(int)", "")]
+        # ds_micro_kernel<PART, G, FAST>: PART 1 = EOS half, 2 = neutrino half (cells), 3 = faces (kernels_micro.cuh)
+        launches = read(csv_path)
+        for kind, part in (("eos", 1), ("nu", 2), ("face", 3)):
+            pat = "ds_micro_kernel<%d," % part
+            ls = [l for l in launches if pat in l["kernel"].replace(" ", "").replace("(bool)", "").replace("(int)", "")]
+            ls = [l for l in ls if l.get("smsp__thread_inst_executed.sum", 0.0) > 1.0e6]   # skip the (empty) plain-division passes
             if not ls:
                 continue
             l = ls[0]
@@ -51,6 +55,8 @@ def main():
             ent[kind] = {"flop_per_eval": (dadd + dmul + 2.0 * dfma) / evals, "dadd": dadd / evals, "dmul": dmul / evals,
                          "dfma": dfma / evals, "inst_per_eval": l.get("smsp__thread_inst_executed.sum", 0.0) / evals,
                          "launches_seen": len(ls)}
+        if "eos" in ent and "nu" in ent:
+            ent["cell"] = {k: ent["eos"][k] + ent["nu"][k] for k in ("flop_per_eval", "dadd", "dmul", "dfma", "inst_per_eval")}
         out[wl] = ent
     json.dump(out, open(out_path, "w"), indent=1)
     print(json.dumps(out, indent=1))
