@@ -885,7 +885,9 @@ DS_D void ds_eval_crust_eos(const DsHelmDev& helm, const DsEosCtrl& rq, double r
     int phase = 0;
     if (COMP & DS_EOS_ION) {
         dse::ion_mixture<FAST>(rq, rs, Gamma_e, c, ncharged, Zion, Aion, ionz, Yion, Gamma, ionQ, phase, ion, bad, act, nact);
+#ifndef DS_NO_PHASE_ION
         DS_PHASE();
+#endif
     }
     const double n_i = ne / den(c.Z);
     const double nik = n_i * boltzmann;

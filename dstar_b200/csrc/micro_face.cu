@@ -1,5 +1,8 @@
 // Coefficient pass, faces: EOS (Gamma, Theta, mu_e) + thermal conductivity per (face, knot) -> lnK table
 // (NScool_create_model.f:406-441).
+// The face evaluation executes ~3 k instructions per lane (~50 KB of SASS): it stays in the instruction caches without the
+// alignment barriers of the evaluators (faces 1.34 -> 1.26 ms without them; measured per part, profiles/r02_notes.md).
+#define DS_NO_PHASE_SYNC
 #define DS_MICRO_PART DS_PART_FACE
 #define DS_MICRO_FN ds_launch_micro_face
 #ifdef DS_MICRO_SCAN

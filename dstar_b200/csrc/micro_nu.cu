@@ -1,5 +1,7 @@
 // Coefficient pass, cell half 2: crust neutrino emissivity per (zone, knot) -> lnEnu table, with the shell-Urca term
 // (NScool_create_model.f:371-384, :398-403).
+// ~2.7 k instructions per lane: no alignment barriers needed (0.97 -> 0.93 ms without them).
+#define DS_NO_PHASE_SYNC
 #define DS_MICRO_PART DS_PART_NU
 #define DS_MICRO_FN ds_launch_micro_nu
 #ifdef DS_MICRO_SCAN
