@@ -96,7 +96,7 @@ struct dstar_batch {
     DevBuf<double> tr_tsec, tr_dt, tr_Teff, tr_Lsurf, tr_Lnu, tr_Lnuc, tr_Mdot, tr_ext;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_half = nullptr;
     // ordering between the two streams: face inputs / evolve inputs uploaded (copy stream), last compute issued (main)
-    cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr, ev_cell_in = nullptr;
+    cudaEvent_t ev_face_in = nullptr, ev_evolve_in = nullptr, ev_busy = nullptr, ev_cell_in = nullptr, ev_Y_in = nullptr;
     char* h_stage = nullptr;   // pinned staging block for the small result arrays (download_results)
     size_t stage_bytes = 0;
     double ms[4] = {0, 0, 0, 0};   // cells, faces, evolve, EOS half of the cells (split pass)
@@ -569,6 +569,7 @@ int dstar_batch_create(dstar_ctx* c, int n_star, const int32_t* zone_offset, int
     CK(cudaEventCreateWithFlags(&b->ev_evolve_in, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_busy, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_cell_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_Y_in, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(st));
     *out = b;
     return DSTAR_OK;
@@ -582,6 +583,7 @@ void dstar_batch_destroy(dstar_batch* b) {
     if (b->ev_evolve_in) cudaEventDestroy(b->ev_evolve_in);
     if (b->ev_busy) cudaEventDestroy(b->ev_busy);
     if (b->ev_cell_in) cudaEventDestroy(b->ev_cell_in);
+    if (b->ev_Y_in) cudaEventDestroy(b->ev_Y_in);
     if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev_half) cudaEventDestroy(b->ev_half);
@@ -608,7 +610,6 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
     CK(cudaStreamWaitEvent(cs, b->ev_busy, 0));
     CK(b->rho.upload(rho, n, s)); CK(b->P.upload(P, n, s));
     CK(b->P_bar.upload(P_bar, n, s)); CK(b->dm.upload(dm, n, s)); CK(b->ionic.upload(ionic, 11 * n, s));
-    CK(b->Yion.upload(Yion, b->ncharged * n, s));
     CK(b->Zion.upload(Zion, b->ncharged, s));
     CK(b->Aion.upload(Aion, b->ncharged, s));
     CK(upload_ionz(b->ionz, b->h_ionz, b->ncharged, Zion, s));
@@ -618,10 +619,14 @@ int dstar_batch_upload_structure(dstar_batch* b, const double* rho, const double
     b->h_rb1.resize(b->n_star);
     for (int i = 0; i < b->n_star; ++i) b->h_rb1[i] = rho_bar[b->h_zone_offset[i]];
     CK(b->rho_bar1.upload(b->h_rb1.data(), b->n_star, s));
-    // the copy stream starts only when the cell inputs have landed: copies of both streams share the host link, and
-    // interleaved they delayed the start of the cell pass by ~0.4 ms (256 stars); now they run under the cell kernel
+    // the copy stream starts only when the first kernels' inputs have landed: copies of both streams share the host
+    // link, and interleaved they delayed the start of the cell pass by ~0.4 ms (256 stars); now they run under the
+    // kernels.  The abundances (half of the cell inputs) go first on the copy stream: the neutrino kernel, which runs
+    // first, does not read them; the EOS kernel waits for ev_Y_in.
     CK(cudaEventRecord(b->ev_cell_in, s));
     CK(cudaStreamWaitEvent(cs, b->ev_cell_in, 0));
+    CK(b->Yion.upload(Yion, b->ncharged * n, cs));
+    CK(cudaEventRecord(b->ev_Y_in, cs));
     CK(b->rho_bar.upload(rho_bar, n, cs)); CK(b->ionic_bar.upload(ionic_bar, 11 * n, cs));
     CK(b->Yion_bar.upload(Yion_bar, b->ncharged * n, cs));
     if (Tc_face) CK(b->Tc_face.upload(Tc_face, 3 * n, cs));
@@ -704,15 +709,18 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             const MicroPlan& mp = micro_plan();
             // branch-free pass, then the plain pass over the zones it flagged (normally none); the two halves of the
             // split pass keep separate lists
-            if (mp.split) {
-                CK(ds_launch_micro_eos(mp.g_eos, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                CK(ds_launch_micro_eos(mp.g_eos, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                CK(cudaEventRecord(b->ev_half, s));
+            if (mp.split) {   // the neutrino half first: it needs no abundances, which may still be arriving (ev_Y_in)
                 a.redo = b->redo.p + b->total; a.redo_count = b->redo_count.p + 1;
                 CK(ds_launch_micro_nu(mp.g_nu, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
                 CK(ds_launch_micro_nu(mp.g_nu, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(cudaEventRecord(b->ev_half, s));
+                CK(cudaStreamWaitEvent(s, b->ev_Y_in, 0));
+                a.redo = b->redo.p; a.redo_count = b->redo_count.p;
+                CK(ds_launch_micro_eos(mp.g_eos, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                CK(ds_launch_micro_eos(mp.g_eos, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
                 b->launches += 2;
             } else {
+                CK(cudaStreamWaitEvent(s, b->ev_Y_in, 0));
                 CK(ds_launch_micro_cell(mp.g_cell, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
                 CK(ds_launch_micro_cell(mp.g_cell, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
             }
@@ -743,7 +751,7 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
         CK(cudaEventSynchronize(b->ev1));
         float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); b->ms[0] = ms;
         b->ms[3] = 0.0;
-        if (micro_plan().split) { CK(cudaEventElapsedTime(&ms, b->ev0, b->ev_half)); b->ms[3] = ms; }
+        if (micro_plan().split) { CK(cudaEventElapsedTime(&ms, b->ev_half, b->ev1)); b->ms[3] = ms; }   // the EOS half runs second
     }
     CK(cudaEventRecord(b->ev_busy, s));
     b->have_tables = true;

@@ -6,7 +6,7 @@
 #define DS_MICRO_PART DS_PART_FACE
 #define DS_MICRO_FN ds_launch_micro_face
 #ifdef DS_MICRO_SCAN
-#define DS_MICRO_GS(X) X(5) X(6) X(7)
+#define DS_MICRO_GS(X) X(3) X(4) X(5) X(6) X(7)
 #else
 #define DS_MICRO_GS(X) X(7)
 #endif
