@@ -35,7 +35,10 @@ UNIT = "evals/s"
 # algorithmic FP64 work per evaluation: cell = EOS + neutrino, face = EOS + conductivity,
 # one ion species, neutron channels off; weighted operation counts incl. transcendentals
 FLOP_CELL, FLOP_FACE = 6.0e3, 1.6e3
-FLOP_EOS = 3.7e3   # the EOS half of a cell evaluation: SURVEY 8d, 6.0 k - 2.3 k (neutrino emissivities)
+# The cell figure apportioned to the two kernels of the cell pass by their executed-flop shares (hardware counters,
+# profiles/r02_flop_counts.json: EOS 4858, neutrino 1493 per evaluation = 76.5 % / 23.5 %; SURVEY's own split, 3.7 k +
+# 2.3 k, overstates the neutrino part)
+FLOP_EOS = 6.0e3 * 4858.0 / (4858.0 + 1493.0)
 ARRS_STRUCT = ["rho", "rho_bar", "P", "P_bar", "dm", "ionic", "ionic_bar", "Yion", "Yion_bar"]
 ARRS_GEOM = ["dm_bar", "area", "ePhi", "e2Phi", "ePhi_bar", "e2Phi_bar"]
 
@@ -48,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="custom_Tc_Qimp")
     ap.add_argument("--stars", type=int, default=256, help="stars per GPU")
+    ap.add_argument("--total-stars", type=int, default=0,
+                    help="strong scaling: this many stars in the whole job, split evenly over the GPUs (overrides --stars)")
     ap.add_argument("--resolution", type=float, default=0.05)
     ap.add_argument("--cpu-sample-stars", type=int, default=0, help="stars in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -415,6 +420,12 @@ def run_b200(args):
     import dstar_b200 as ds
     ds.NScool_init(device=local)
     ctx = ds.Context(local, gaps=("ns", "sfb03" if args.workload != "accretion" else "gc", "t72"))
+    if args.total_stars > 0:   # strong scaling: a fixed job dealt out in contiguous blocks, as dstar_b200/dist.py shard_range
+        from dstar_b200.dist import shard_range
+        if args.total_stars % world:
+            raise SystemExit("--total-stars must be a multiple of the number of GPUs (the line reports rank 0's share x N)")
+        lo_, hi_ = shard_range(args.total_stars, rank, world)
+        args.stars = hi_ - lo_
     W = prepare_workload(ds, args.workload, args.stars, args.resolution, rank)
     stars, nz, zoff, H = W["stars"], W["nz"], W["zoff"], W["H"]
     n_star, total = W["n_star"], int(zoff[-1])
@@ -514,7 +525,7 @@ def run_b200(args):
                 "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure); the "
                                "reference's formulas may not be contracted into FMAs, so 0.5 is the ceiling of frac",
                 "flops_per_eval": {"eos": FLOP_EOS, "nu": FLOP_CELL - FLOP_EOS, "cell": FLOP_CELL, "face": FLOP_FACE,
-                                   "source": "SURVEY.md 8d algorithmic estimate (cell = EOS 3.7 k + neutrino 2.3 k)"},
+                                   "source": "SURVEY.md 8d algorithmic estimate (cell 6.0 k, face 1.6 k); the cell figure is apportioned to the EOS and neutrino kernels by their executed-flop shares (profiles/r02_flop_counts.json)"},
                 "cell_pass": {"achieved": cell_tf, "frac": cell_tf / fp64_peak if fp64_peak > 0 else None,
                               "note": "EOS + neutrino kernels together: 6.0 kflop per evaluation over the cell time"},
                 "executed": {k: wr.get(k) for k in ("eos", "nu", "cell", "face", "flop_source")},
@@ -566,7 +577,7 @@ def run_b200(args):
         desc += "; %d distinct stars repeated %d times" % (W["n_distinct"], W["reps"])
     line = {"metric": METRIC, "value": evals * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.total_stars > 0 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "stars_per_gpu": n_star, "zones_total_per_gpu": total, "seed": 20261019,
                        "l2_policy": "inputs+tables per step %.0f MB > 126 MB L2" % ((4 * 4096.0 * total + h2d) / 1e6)},
             "curves_per_sec": n_star * world / (ms_step * 1e-3),

@@ -229,25 +229,21 @@ extern "C" {
 const char* dstar_last_error(void) { return g_err.c_str(); }
 void dstar_debug_force_redo(int on) { g_force_redo = on ? 1 : 0; }
 
-// Local-memory window of the device.  The coefficient kernels keep ~0.7 KB of spill frame per thread, and the frames
-// of all resident threads (~90 MB) cycle through L2.  How they map onto L2 depends on the per-thread window the driver
-// lays local memory out with; that follows cudaLimitStackSize and whatever resized the pool earlier in the process.
-// Measured (256 stars, cell pass; profiles/r01_notes.md, r01m): 5.42 ms in a fresh process at the 1 KB default, but
-// 6.25 ms at the same 1 KB when torch had launched a kernel first, and 6.39 ms after NCCL had set 1872 B for its own
-// kernels (every multi-GPU run); with the limit raised to 2 / 4 / 8 / 16 KB: 5.59 / 5.44 / 5.42 / 5.39 ms in all of
-// these situations.  The library therefore raises the limit to 8 KB (never lowers it) and re-checks before every
-// coefficient pass, because NCCL resets it when a communicator is created.  Cost: 8 KB x 303 k resident threads =
-// 2.4 GB of HBM.  DSTAR_STACK_LIMIT=<bytes> overrides, 0 leaves the device alone.
+// Local-memory window of the device.  Round 1's fused cell kernel kept a 0.7-0.8 KB spill frame per thread and its time
+// depended on how the driver laid local memory out (5.4 vs 6.4 ms after NCCL had set cudaLimitStackSize to 1872 B), so
+// the library raised the limit to 8 KB (2.4 GB of HBM).  With the round-2 kernels the dependence is gone (2 GPUs under
+// NCCL: 7.892 ms per step with the device left alone, 7.894 with the 8 KB window; profiles/r02_notes.md), so the library
+// no longer touches the limit unless asked to: DSTAR_STACK_LIMIT=<bytes> raises it (never lowers it).
 static cudaError_t ensure_stack_limit() {
     static const size_t want = [] {
         const char* e = std::getenv("DSTAR_STACK_LIMIT");
-        return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)8192;
+        return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)0;
     }();
     if (want == 0) return cudaSuccess;
     size_t cur = 0;
     cudaError_t e = cudaDeviceGetLimit(&cur, cudaLimitStackSize);
     if (e != cudaSuccess || cur >= want) return e;
-    return cudaDeviceSetLimit(cudaLimitStackSize, want);   // synchronises the device; happens once (or once per NCCL init)
+    return cudaDeviceSetLimit(cudaLimitStackSize, want);   // synchronises the device
 }
 
 int dstar_ctx_create(int device, dstar_ctx** out) {
