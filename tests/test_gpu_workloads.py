@@ -373,3 +373,32 @@ def test_device_stack_limit_is_left_alone(nscool):
     for k in TABS:
         assert np.array_equal(bits(s2.array(k)), bits(ref[k])), k
     assert cu.cuCtxSetLimit(0, ctypes.c_size_t(before)) == 0
+
+
+def test_run_batch_driver_matches_create_and_evolve(nscool):
+    """dstar_NScool_run_batch (the C-level sweep driver, one host thread per GPU): on one device it is create_models +
+    evolve_models; on two devices -- when the box has them -- each device takes a contiguous block of the stars and
+    every monitor, table and solver counter is bit-identical to the one-device run."""
+    ds = nscool
+    Tcs = [0.8e8, 1.0e8, 1.3e8, 1.7e8, 2.2e8]
+    ref = [_star(ds, 0.3, core_temperature=t) for t in Tcs]
+    ds.create_models(ref)
+    ds.evolve_models(ref)
+    import torch
+    n_dev = torch.cuda.device_count()
+    for n_gpu in ([1, 2] if n_dev >= 2 else [1]):
+        run = [_star(ds, 0.3, core_temperature=t) for t in Tcs]
+        tm, Tm, Qm, st = ds.run_batch(run, n_gpu=n_gpu)
+        assert np.all(st == 0)
+        assert Tm.shape == (2, len(Tcs))
+        for i, (a, b) in enumerate(zip(ref, run)):
+            for x, y in zip(a.monitors(), b.monitors()):
+                assert np.array_equal(bits(x), bits(y)), (n_gpu, i)
+            assert np.array_equal(bits(Tm[:, i]), bits(a.monitors()[1]))
+            for name in TABS + ("lnT",):
+                assert np.array_equal(bits(a.array(name)), bits(b.array(name))), (n_gpu, i, name)
+            np.testing.assert_array_equal(a.counters(), b.counters())
+        for s in run:
+            s.free()
+    for s in ref:
+        s.free()
