@@ -84,6 +84,7 @@ struct dstar_batch {
     int max_nz = 0;
     bool have_structure = false, have_tables = false, have_evolve = false, have_Tc_cell = false, have_Tc_face = false,
          have_enuc = false;
+    DevBuf<int> blk_list, blk_count;   // block-scheduled EOS half: four item lists and their lengths
     DevBuf<int> zone_offset, zone_star, status, redo, redo_count, atm_index, idid, counters, model, trace_count, trace_model;
     DevBuf<double> rho, rho_bar, P, P_bar, dm, ionic, ionic_bar, Yion, Yion_bar, Zion, Aion, Tc_cell, Tc_face;
     DevBuf<DsIonZ> ionz;
@@ -146,7 +147,7 @@ void fill_host_consts(DsHostConsts& h) {
 //   5 5.7, 6 5.4, 7 5.2, 8 5.5 -- profiles/r01_notes.md), the EOS half 7, the neutrino half 8 (64 registers, no spill
 //   frame).  DSTAR_MICRO_SPLIT=0 selects the fused cell kernel, DSTAR_MICRO_MINB / _G_EOS / _G_NU the group counts
 //   (experiments; a count the library was not compiled for falls back to the default).
-struct MicroPlan { int split, g_cell, g_eos, g_nu, g_face; };
+struct MicroPlan { int split, g_cell, g_eos, g_nu, g_face, blocks; };
 const MicroPlan& micro_plan() {
     static const MicroPlan p = [] {
         auto geti = [](const char* k, int d) { const char* e = std::getenv(k); return e ? std::atoi(e) : d; };
@@ -156,6 +157,7 @@ const MicroPlan& micro_plan() {
         q.g_face = geti("DSTAR_MICRO_G_FACE", q.g_face);
         q.g_eos = geti("DSTAR_MICRO_G_EOS", 7);
         q.g_nu = geti("DSTAR_MICRO_G_NU", 8);
+        q.blocks = geti("DSTAR_MICRO_BLOCKS", 1);   // EOS half scheduled by 32-knot blocks (0: by zones, ds_micro_kernel<EOS>)
         return q;
     }();
     return p;
@@ -712,9 +714,17 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
                 CK(cudaEventRecord(b->ev_half, s));
                 CK(cudaStreamWaitEvent(s, b->ev_Y_in, 0));
                 a.redo = b->redo.p; a.redo_count = b->redo_count.p;
-                CK(ds_launch_micro_eos(mp.g_eos, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                CK(ds_launch_micro_eos(mp.g_eos, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                b->launches += 2;
+                if (mp.blocks) {
+                    if (!b->blk_list.p) { CK(b->blk_list.alloc((size_t)16 * b->total)); CK(b->blk_count.alloc(4 + 3 * DS_BLK_NKEY)); }
+                    a.blk_list = b->blk_list.p; a.blk_count = b->blk_count.p;
+                    CK(cudaMemsetAsync(b->blk_count.p, 0, (4 + 3 * DS_BLK_NKEY) * sizeof(int), s));
+                    CK(ds_launch_micro_eos_blocks(sms, n_items, s, a, c->helm, c->hc));
+                    b->launches += 6;
+                } else {
+                    CK(ds_launch_micro_eos(mp.g_eos, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                    CK(ds_launch_micro_eos(mp.g_eos, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                    b->launches += 2;
+                }
             } else {
                 CK(cudaStreamWaitEvent(s, b->ev_Y_in, 0));
                 CK(ds_launch_micro_cell(mp.g_cell, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
@@ -1118,6 +1128,12 @@ int dstar_batch_last_redo_counts(dstar_batch* b, int32_t* counts) {
     CK(cudaSetDevice(b->ctx->device));
     CK(b->redo_count.download(counts, 2, b->ctx->stream));
     CK(cudaStreamSynchronize(b->ctx->stream));
+    if (micro_plan().split && micro_plan().blocks && b->blk_count.p) {   // EOS half by blocks: flagged 32-knot blocks
+        int32_t bc[4] = {0, 0, 0, 0};
+        CK(b->blk_count.download(bc, 4, b->ctx->stream));
+        CK(cudaStreamSynchronize(b->ctx->stream));
+        counts[0] = bc[3];
+    }
     return DSTAR_OK;
 }
 

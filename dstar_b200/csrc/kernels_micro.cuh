@@ -88,6 +88,10 @@ struct DsMicroArgs {
     const int* work_list;
     int n_work;
     const int* tab_zone0;
+    // block-scheduled EOS half (ds_eos_block_kernel): work items = (zone, 32-knot block), item = 4 * zone + block, in
+    // four lists of capacity 4 * total_zones each -- all-solid, all-liquid and mixed blocks, then the redo list
+    int* blk_list;
+    int* blk_count;   // (4 + 3 * DS_BLK_NKEY): list lengths, then the sort bins
 };
 
 // MESA interp_pm (Steffen 1990) on one zone's 128 knots; i = knot index of this lane, v holds f(1,:) on entry.
@@ -388,4 +392,177 @@ __global__ void __launch_bounds__(DS_NTAB* G, DS_MICRO_CTAS) ds_micro_kernel(DsM
         if (on && it == 0 && s_err[grp] != 0) a.status[star] = s_err[grp];
         if (FAST && on && it == 0 && (s_bad[grp] | a.force_redo)) a.redo[atomicAdd(a.redo_count, 1)] = g;
     }
+}
+
+// ---------------------------------------------------------------- EOS half, scheduled by 32-knot blocks
+// In ds_micro_kernel a zone is a group of four warps, and its interp_pm needs all four: the warp whose 32 knots
+// straddle the melting line runs the liquid AND the solid ion fits, the other three wait for it at the next barrier,
+// every round (9 % of the EOS kernel's stall samples at that one barrier, profiles/r02_ncu_full_summary.md).  Here the
+// evaluation and the interpolation are separate kernels, so the unit of work is one warp = one (zone, 32-knot block);
+// the blocks are sorted into all-solid, all-liquid and mixed ones (ds_eos_classify_kernel) and a persistent CTA takes
+// 28 blocks of ONE class per round: every warp of a round has the same work.  The class only steers the schedule: a
+// misclassified block is evaluated correctly, its warp just diverges.
+#ifndef DS_BLK_W_X
+#define DS_BLK_W_X 28
+#endif
+constexpr int DS_BLK_W = DS_BLK_W_X;   // warps (blocks) per CTA and round
+
+// Sort key of a block: its phase class (0 all solid, 1 all liquid, 2 mixed -- the phase of every knot as ion_mixture
+// decides it, ion.f:55 with lattice_properties' Gamma_e) and the number of species above the abundance threshold
+// (the trip count of ion_mixture's loop), capped.  Blocks are laid out class by class and, inside a class, by
+// ascending species count, so that the 28 blocks of a round cost the same.
+constexpr int DS_BLK_NKEY = 64;   // species-count keys per class
+struct DsBlkKey { int cls[4], nkey; };
+DS_D DsBlkKey ds_blk_keys(const DsMicroArgs& a, int g) {
+    DsBlkKey k;
+    const double Z53 = a.ionic[(size_t)11 * g + 2];
+    const double rs = a.aux[(size_t)DS_AUX * g + 5 + 1];   // DsZonePre::rs
+    // liquid iff Gamma_e Z53 < Gamma_melt, Gamma_e = 2 Ry / (kB T rs) (lattice_properties, dStar_eos_lib.f:84-98), i.e.
+    // iff T > T_melt.  The class only steers the schedule, so the comparison need not round as ion_mixture's does.
+    const double T_melt = 2.0 * dsc::Rydberg / dsc::boltzmann / rs * Z53 / a.eos.Gamma_melt;
+    for (int b = 0; b < 4; ++b) {
+        int n_solid = 0;
+        for (int q = 0; q < 32; ++q) n_solid += !(a.tab_T[32 * b + q] > T_melt);
+        k.cls[b] = (n_solid == 32) ? 0 : (n_solid == 0) ? 1 : 2;
+    }
+    int na = 0;
+    const double* Yg = a.Yion + (size_t)a.ncharged * g;
+    for (int i = 0; i < a.ncharged; ++i) na += Yg[i] > a.eos.Ythresh;
+    k.nkey = min(na, DS_BLK_NKEY - 1);
+    return k;
+}
+// Counting sort in three launches: histogram of the keys (MODE 0), exclusive prefix per class (ds_eos_prefix_kernel),
+// scatter (MODE 1).  blk_count: [0..3] list lengths (3 = redo list), then DS_BLK_NKEY bins per class.  One atomic per
+// warp and distinct key (the bins of a real crust are few and hot).
+template <int MODE>
+__global__ void ds_eos_classify_kernel(DsMicroArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_items = a.work_list ? a.n_work : a.total_zones;
+    const bool live = i < n_items;
+    const int g = live ? (a.work_list ? a.work_list[i] : i) : 0;
+    const DsBlkKey k = ds_blk_keys(a, g);
+    const int lane = threadIdx.x & 31;
+    for (int b = 0; b < 4; ++b) {
+        const int bin = live ? k.cls[b] * DS_BLK_NKEY + k.nkey : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, bin);
+        if (!live) continue;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(a.blk_count + 4 + bin, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        if (MODE == 1)
+            a.blk_list[(size_t)k.cls[b] * 4 * a.total_zones + base + __popc(m & ((1u << lane) - 1u))] = 4 * g + b;
+    }
+}
+// bins -> start offsets (in place) and list lengths: one thread per class
+template <int UNIT = 0>
+__global__ void ds_eos_prefix_kernel(int* blk_count) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    int run = 0;
+    for (int q = 0; q < DS_BLK_NKEY; ++q) { const int n = blk_count[4 + c * DS_BLK_NKEY + q]; blk_count[4 + c * DS_BLK_NKEY + q] = run; run += n; }
+    blk_count[c] = run;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_eos_block_kernel(DsMicroArgs a, DsHelmDev helm) {
+    constexpr int W = DS_BLK_W;
+    __shared__ DsZoneIn s_zone[W];
+    __shared__ DsZonePre s_pre[W];
+    __shared__ DsHelmZone s_hz[W];
+    __shared__ unsigned char s_act[W][DS_YMAX];
+    __shared__ int s_nact[W];
+    __shared__ double s_ZA[2][DS_YMAX];
+    __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];
+    extern __shared__ double s_dyn[];   // W * DS_YMAX abundances
+    double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_dyn);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool net_in_smem = a.ncharged <= DS_YMAX, ionz_in_smem = a.ncharged <= DS_IONZ_SMEM;
+    if (net_in_smem)
+        for (int i = threadIdx.x; i < a.ncharged; i += blockDim.x) { s_ZA[0][i] = a.Zion[i]; s_ZA[1][i] = a.Aion[i]; }
+    if (ionz_in_smem)
+        for (int i = threadIdx.x; i < a.ncharged * (int)(sizeof(DsIonZ) / sizeof(double)); i += blockDim.x)
+            reinterpret_cast<double*>(s_ionz)[i] = reinterpret_cast<const double*>(a.ionz)[i];
+    __syncthreads();
+    const double* Zn = net_in_smem ? s_ZA[0] : a.Zion;
+    const double* An = net_in_smem ? s_ZA[1] : a.Aion;
+    const DsIonZ* ionz = ionz_in_smem ? s_ionz : a.ionz;
+    // FAST: the three class lists one after the other; plain pass: the redo list (whatever the class)
+    for (int li = FAST ? 0 : 3; li < (FAST ? 3 : 4); ++li) {
+        const int* list = a.blk_list + (size_t)li * 4 * a.total_zones;
+        const int count = a.blk_count[li];
+        for (int base = blockIdx.x * W; base < count; base += gridDim.x * W) {
+            // warps past the end of the list redo its last block and discard it: the alignment barriers inside the
+            // evaluators are CTA-wide
+            const bool on = base + w < count;
+            const int item = list[on ? base + w : count - 1];
+            const int g = item >> 2, kn = ((item & 3) << 5) | lane;
+            const int star = a.zone_star[g];
+            const int iz = g - a.zone_offset[star];
+            // the zone's inputs into this warp's slots (the slots are the warp's own: no CTA barrier needed)
+            for (int q = lane; q < 16 + DS_PRE + DS_HZ; q += 32) {
+                const double v = (q < 11) ? a.ionic[(size_t)11 * g + q] : a.aux[(size_t)DS_AUX * g + (q - 11)];
+                if (q < 16) reinterpret_cast<double*>(&s_zone[w])[q] = v;
+                else if (q < 16 + DS_PRE) reinterpret_cast<double*>(&s_pre[w])[q - 16] = v;
+                else reinterpret_cast<double*>(&s_hz[w])[q - 16 - DS_PRE] = v;
+            }
+            const double* Yg = a.Yion + (size_t)a.ncharged * g;
+            if (net_in_smem) {   // abundances and the list of the species above the threshold (ascending, as the reference loops)
+                int na = 0;
+                for (int i0 = 0; i0 < a.ncharged; i0 += 32) {
+                    const int i = i0 + lane;
+                    const double y = (i < a.ncharged) ? Yg[i] : 0.0;
+                    if (i < a.ncharged) s_Y[w][i] = y;
+                    const unsigned m = __ballot_sync(0xffffffffu, i < a.ncharged && y > a.eos.Ythresh);
+                    if ((m >> lane) & 1u) s_act[w][na + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
+                    na += __popc(m);
+                }
+                if (lane == 0) s_nact[w] = na;
+            }
+            __syncwarp();
+            const DsComp& c = s_zone[w].c;
+            const double T = a.tab_T[kn], lgT = a.tab_lgT[kn];
+            DsEosRes r;
+            bool bad = false;
+            ds_eval_crust_eos<FAST>(helm, a.eos, s_zone[w].rho, T, lgT, c, s_pre[w], s_hz[w], a.ncharged, Zn, An, ionz,
+                                    net_in_smem ? s_Y[w] : Yg, s_zone[w].Tc[1], s_zone[w].chi, r, bad, nullptr,
+                                    net_in_smem ? s_act[w] : nullptr, net_in_smem ? s_nact[w] : 0);
+            // the two table values of this knot are parked at the head of the zone's (4,128) blocks (contiguous in the
+            // knot: coalesced here and in ds_eos_interp_kernel, which completes the blocks)
+            const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
+            const bool flagged = FAST && (__any_sync(0xffffffffu, bad) || a.force_redo);
+            if (on && !flagged) {
+                a.tab_lnCp[ob + kn] = dsm::log(r.Cp);
+                a.tab_lnGamma[ob + kn] = dsm::log(r.Gamma);
+                if (iz == 0 && kn == 0)  // create_model.f:367-369
+                    a.rho_bar1[star] = s_zone[w].rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+            }
+            if (on && r.ierr != 0) a.status[star] = r.ierr;
+            if (on && flagged && lane == 0) a.blk_list[(size_t)3 * 4 * a.total_zones + atomicAdd(a.blk_count + 3, 1)] = item;
+            __syncwarp();   // the slots are rewritten in the next round
+        }
+    }
+}
+
+// interp_pm of lnCp and lnGamma for the zones of the work list: DS_INTERP_G zones per CTA, 128 threads each.  The values
+// are read from the head of each block (where ds_eos_block_kernel parked them) before any of it is overwritten.
+constexpr int DS_INTERP_G = 4;
+template <int UNIT = 0>
+__global__ void __launch_bounds__(DS_NTAB* DS_INTERP_G) ds_eos_interp_kernel(DsMicroArgs a) {
+    constexpr int G = DS_INTERP_G;
+    __shared__ double s_h[DS_NTAB], s_v[G][2][DS_NTAB], s_m[G][2][DS_NTAB], s_s[G][2][DS_NTAB];
+    const int grp = threadIdx.x / DS_NTAB, i = threadIdx.x % DS_NTAB;
+    const int n_items = a.work_list ? a.n_work : a.total_zones;
+    const int idx = blockIdx.x * G + grp;
+    const bool on = idx < n_items;
+    const int g = on ? (a.work_list ? a.work_list[idx] : idx) : 0;
+    const int star = a.zone_star[g];
+    const int iz = g - a.zone_offset[star];
+    const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
+    if (threadIdx.x < DS_NTAB - 1) s_h[i] = a.tab_lnT[i + 1] - a.tab_lnT[i];
+    s_v[grp][0][i] = on ? a.tab_lnCp[ob + i] : 0.0;
+    s_v[grp][1][i] = on ? a.tab_lnGamma[ob + i] : 0.0;
+    __syncthreads();
+    ds_group_interp_pm2(on, i, s_h, s_v[grp][0], s_v[grp][1], s_m[grp][0], s_m[grp][1], s_s[grp][0], s_s[grp][1],
+                        a.tab_lnCp + ob, a.tab_lnGamma + ob);
 }

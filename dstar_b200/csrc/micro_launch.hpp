@@ -16,6 +16,9 @@ cudaError_t ds_launch_micro_cell(int G, bool fast, int sms, int n_items, cudaStr
                                  const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);   // EOS + neutrino fused
 cudaError_t ds_launch_micro_eos(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
                                 const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);    // lnCp, lnGamma, rho_bar(1)
+// the EOS half scheduled by 32-knot blocks (classification, branch-free pass, plain pass, interpolation)
+cudaError_t ds_launch_micro_eos_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
+                                       const DsHostConsts& hc);
 cudaError_t ds_launch_micro_nu(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
                                const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);     // lnEnu
 cudaError_t ds_launch_micro_face(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
