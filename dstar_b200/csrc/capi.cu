@@ -157,7 +157,7 @@ const MicroPlan& micro_plan() {
         q.g_face = geti("DSTAR_MICRO_G_FACE", q.g_face);
         q.g_eos = geti("DSTAR_MICRO_G_EOS", 7);
         q.g_nu = geti("DSTAR_MICRO_G_NU", 8);
-        q.blocks = geti("DSTAR_MICRO_BLOCKS", 1);   // EOS half scheduled by 32-knot blocks (0: by zones, ds_micro_kernel<EOS>)
+        q.blocks = geti("DSTAR_MICRO_BLOCKS", 7);   // parts scheduled by 32-knot blocks instead of by zones: 1 EOS half, 2 neutrino half, 4 faces
         return q;
     }();
     return p;
@@ -707,17 +707,25 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             const MicroPlan& mp = micro_plan();
             // branch-free pass, then the plain pass over the zones it flagged (normally none); the two halves of the
             // split pass keep separate lists
+            if (mp.blocks && !b->blk_list.p) { CK(b->blk_list.alloc((size_t)20 * b->total)); CK(b->blk_count.alloc(5 + 3 * DS_BLK_NKEY)); }
+            if (mp.blocks) {
+                CK(cudaMemsetAsync(b->blk_count.p, 0, (5 + 3 * DS_BLK_NKEY) * sizeof(int), s));
+                a.blk_list = b->blk_list.p; a.blk_count = b->blk_count.p;
+            }
             if (mp.split) {   // the neutrino half first: it needs no abundances, which may still be arriving (ev_Y_in)
                 a.redo = b->redo.p + b->total; a.redo_count = b->redo_count.p + 1;
-                CK(ds_launch_micro_nu(mp.g_nu, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
-                CK(ds_launch_micro_nu(mp.g_nu, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                if (mp.blocks & 2) {
+                    a.blk_redo = b->blk_list.p + (size_t)16 * b->total; a.blk_redo_count = b->blk_count.p + 4 + 3 * DS_BLK_NKEY;
+                    CK(ds_launch_micro_nu_blocks(sms, n_items, s, a, c->helm, c->hc));
+                    ++b->launches;
+                } else {
+                    CK(ds_launch_micro_nu(mp.g_nu, true, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                    CK(ds_launch_micro_nu(mp.g_nu, false, sms, n_items, s, a, c->helm, c->sf, c->hc));
+                }
                 CK(cudaEventRecord(b->ev_half, s));
                 CK(cudaStreamWaitEvent(s, b->ev_Y_in, 0));
                 a.redo = b->redo.p; a.redo_count = b->redo_count.p;
-                if (mp.blocks) {
-                    if (!b->blk_list.p) { CK(b->blk_list.alloc((size_t)16 * b->total)); CK(b->blk_count.alloc(4 + 3 * DS_BLK_NKEY)); }
-                    a.blk_list = b->blk_list.p; a.blk_count = b->blk_count.p;
-                    CK(cudaMemsetAsync(b->blk_count.p, 0, (4 + 3 * DS_BLK_NKEY) * sizeof(int), s));
+                if (mp.blocks & 1) {
                     CK(ds_launch_micro_eos_blocks(sms, n_items, s, a, c->helm, c->hc));
                     b->launches += 6;
                 } else {
@@ -745,7 +753,12 @@ int dstar_batch_micro_tables(dstar_batch* b, const dstar_micro_ctrl* ctrl, int w
             a.work_list = sh.on ? sh.d_work.p : nullptr; a.n_work = sh.n_work; a.tab_zone0 = sh.on ? sh.d_tab0.p : nullptr;
             CK(cudaStreamWaitEvent(s, b->ev_face_in, 0));   // face inputs may still be arriving on the copy stream
             ds_zone_aux_kernel<true><<<(b->total + 127) / 128, 128, 0, s>>>(a, c->helm, c->sf);
-            CK(ds_launch_micro_face(micro_plan().g_face, false, sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf, c->hc));
+            if (micro_plan().blocks & 4) {
+                CK(ds_launch_micro_face_blocks(sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->hc));
+                ++b->launches;
+            } else {
+                CK(ds_launch_micro_face(micro_plan().g_face, false, sms, sh.on ? sh.n_work : b->total, s, a, c->helm, c->sf, c->hc));
+            }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(b->ev3, s));
@@ -1128,11 +1141,12 @@ int dstar_batch_last_redo_counts(dstar_batch* b, int32_t* counts) {
     CK(cudaSetDevice(b->ctx->device));
     CK(b->redo_count.download(counts, 2, b->ctx->stream));
     CK(cudaStreamSynchronize(b->ctx->stream));
-    if (micro_plan().split && micro_plan().blocks && b->blk_count.p) {   // EOS half by blocks: flagged 32-knot blocks
-        int32_t bc[4] = {0, 0, 0, 0};
-        CK(b->blk_count.download(bc, 4, b->ctx->stream));
+    if (micro_plan().split && micro_plan().blocks && b->blk_count.p) {   // parts scheduled by blocks: flagged 32-knot blocks
+        std::vector<int32_t> bc(5 + 3 * DS_BLK_NKEY, 0);
+        CK(b->blk_count.download(bc.data(), bc.size(), b->ctx->stream));
         CK(cudaStreamSynchronize(b->ctx->stream));
-        counts[0] = bc[3];
+        if (micro_plan().blocks & 1) counts[0] = bc[3];
+        if (micro_plan().blocks & 2) counts[1] = bc[4 + 3 * DS_BLK_NKEY];
     }
     return DSTAR_OK;
 }

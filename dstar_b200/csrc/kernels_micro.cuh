@@ -90,6 +90,10 @@ struct DsMicroArgs {
     const int* tab_zone0;
     // block-scheduled EOS half (ds_eos_block_kernel): work items = (zone, 32-knot block), item = 4 * zone + block, in
     // four lists of capacity 4 * total_zones each -- all-solid, all-liquid and mixed blocks, then the redo list
+    // the neutrino half and the faces run through the same kernel in natural block order (no lists); their redo
+    // lists are blk_redo / blk_redo_count, set per launch
+    int* blk_redo;
+    int* blk_redo_count;
     int* blk_list;
     int* blk_count;   // (4 + 3 * DS_BLK_NKEY): list lengths, then the sort bins
 };
@@ -203,7 +207,7 @@ struct DsZoneIn {   // 16 doubles: the prologue fills it as a flat array (11 mom
 static_assert(sizeof(DsZoneIn) == 16 * sizeof(double), "DsZoneIn is loaded as 16 doubles");
 constexpr int DS_PRE = (int)(sizeof(DsZonePre) / sizeof(double)), DS_HZ = (int)(sizeof(DsHelmZone) / sizeof(double));
 constexpr int DS_CP = (int)(sizeof(dsk::DsCondPre) / sizeof(double));
-constexpr int DS_AUX = 5 + DS_PRE + DS_HZ + DS_CP;   // rho, chi, Tc(3), DsZonePre, DsHelmZone (raw 8-byte words), DsCondPre (faces)
+constexpr int DS_AUX = 5 + DS_PRE + DS_HZ + DS_CP + 2;   // rho, chi, Tc(3), DsZonePre, DsHelmZone (raw 8-byte words); faces: DsCondPre, lambda_imp, its ierr
 static_assert(sizeof(DsHelmZone) % sizeof(double) == 0, "DsHelmZone is copied as 8-byte words");
 constexpr int DS_YMAX = 96;   // species kept in shared memory per group (more: read from global memory)
 constexpr int DS_IONZ_SMEM = 20;  // species whose Z-only constants (136 B each) are kept in shared memory
@@ -233,6 +237,12 @@ __global__ void ds_zone_aux_kernel(DsMicroArgs a, DsHelmDev helm, DsSfDev sf) {
     if (FACE) {
         const dsk::DsCondPre cp = dsk::ds_cond_pre(a.cond, rho, c);
         for (int q = 0; q < DS_CP; ++q) o[5 + DS_PRE + DS_HZ + q] = reinterpret_cast<const double*>(&cp)[q];
+        // impurity Coulomb logarithm of the neutron channel: T-independent, once per zone (neutron_conductivity.f:382)
+        double lam = nan("");
+        int lam_ierr = 0;
+        if (a.cond.include_neutrons && c.Yn > 0.0) lam_ierr = dsk::ds_lambda_imp(rho / dsc::amu * c.Yn / (1.0 - chi), c, lam);
+        o[5 + DS_PRE + DS_HZ + DS_CP] = lam;
+        o[5 + DS_PRE + DS_HZ + DS_CP + 1] = (double)lam_ierr;
     }
 }
 
@@ -403,7 +413,7 @@ __global__ void __launch_bounds__(DS_NTAB* G, DS_MICRO_CTAS) ds_micro_kernel(DsM
 // 28 blocks of ONE class per round: every warp of a round has the same work.  The class only steers the schedule: a
 // misclassified block is evaluated correctly, its warp just diverges.
 #ifndef DS_BLK_W_X
-#define DS_BLK_W_X 28
+#define DS_BLK_W_X 24
 #endif
 constexpr int DS_BLK_W = DS_BLK_W_X;   // warps (blocks) per CTA and round
 
@@ -464,20 +474,23 @@ __global__ void ds_eos_prefix_kernel(int* blk_count) {
     blk_count[c] = run;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_eos_block_kernel(DsMicroArgs a, DsHelmDev helm) {
+template <int PART, bool FAST>
+__global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_block_kernel(DsMicroArgs a, DsHelmDev helm) {
     constexpr int W = DS_BLK_W;
+    constexpr bool FACE = PART == DS_PART_FACE, HAS_EOS = PART != DS_PART_NU, SPECIES = PART == DS_PART_EOS;
     __shared__ DsZoneIn s_zone[W];
     __shared__ DsZonePre s_pre[W];
-    __shared__ DsHelmZone s_hz[W];
-    __shared__ unsigned char s_act[W][DS_YMAX];
+    __shared__ DsHelmZone s_hz[HAS_EOS ? W : 1];
+    __shared__ dsk::DsCondPre s_cp[FACE ? W : 1];
+    __shared__ double s_lam[FACE ? W : 1][2];
+    __shared__ unsigned char s_act[SPECIES ? W : 1][DS_YMAX];
     __shared__ int s_nact[W];
-    __shared__ double s_ZA[2][DS_YMAX];
-    __shared__ DsIonZ s_ionz[DS_IONZ_SMEM];
-    extern __shared__ double s_dyn[];   // W * DS_YMAX abundances
+    __shared__ double s_ZA[2][SPECIES ? DS_YMAX : 1];
+    __shared__ DsIonZ s_ionz[SPECIES ? DS_IONZ_SMEM : 1];
+    extern __shared__ double s_dyn[];   // EOS half: W * DS_YMAX abundances
     double (*s_Y)[DS_YMAX] = reinterpret_cast<double (*)[DS_YMAX]>(s_dyn);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool net_in_smem = a.ncharged <= DS_YMAX, ionz_in_smem = a.ncharged <= DS_IONZ_SMEM;
+    const bool net_in_smem = SPECIES && a.ncharged <= DS_YMAX, ionz_in_smem = SPECIES && a.ncharged <= DS_IONZ_SMEM;
     if (net_in_smem)
         for (int i = threadIdx.x; i < a.ncharged; i += blockDim.x) { s_ZA[0][i] = a.Zion[i]; s_ZA[1][i] = a.Aion[i]; }
     if (ionz_in_smem)
@@ -487,26 +500,40 @@ __global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_eos_block_kernel(DsMicroA
     const double* Zn = net_in_smem ? s_ZA[0] : a.Zion;
     const double* An = net_in_smem ? s_ZA[1] : a.Aion;
     const DsIonZ* ionz = ionz_in_smem ? s_ionz : a.ionz;
-    // FAST: the three class lists one after the other; plain pass: the redo list (whatever the class)
-    for (int li = FAST ? 0 : 3; li < (FAST ? 3 : 4); ++li) {
-        const int* list = a.blk_list + (size_t)li * 4 * a.total_zones;
-        const int count = a.blk_count[li];
+    const int n_zones = a.work_list ? a.n_work : a.total_zones;
+    // EOS half, branch-free pass: the three class lists one after the other.  Otherwise one list: the redo list
+    // (plain pass after a branch-free one) or the natural order, 4 blocks per work zone (neutrino half, faces).
+    const bool redo_pass = !FAST && !FACE;
+    const int first = (SPECIES && FAST) ? 0 : 3, last = (SPECIES && FAST) ? 3 : 4;
+    for (int li = first; li < last; ++li) {
+        const int* list = (SPECIES && FAST) ? a.blk_list + (size_t)li * 4 * a.total_zones : (redo_pass ? a.blk_redo : nullptr);
+        const int count = (SPECIES && FAST) ? a.blk_count[li] : (redo_pass ? *a.blk_redo_count : 4 * n_zones);
         for (int base = blockIdx.x * W; base < count; base += gridDim.x * W) {
-            // warps past the end of the list redo its last block and discard it: the alignment barriers inside the
-            // evaluators are CTA-wide
+            // With the neutron / phonon channels on, a face evaluation is ~25 k instructions per lane (two DOP853
+            // quadratures): free-running warps then thrash the instruction caches (accretion faces 29.7 ms instead of
+            // 13.3), so the warps of a CTA start such rounds together.
+            if (FACE && (a.cond.include_neutrons | a.cond.include_sf_phonons)) __syncthreads();
+            // warps past the end of the list redo its last block and discard it (the EOS half's evaluators hold
+            // CTA-wide alignment barriers)
             const bool on = base + w < count;
-            const int item = list[on ? base + w : count - 1];
+            const int idx = on ? base + w : count - 1;
+            const int item = list ? list[idx] : 4 * (a.work_list ? a.work_list[idx >> 2] : (idx >> 2)) + (idx & 3);
             const int g = item >> 2, kn = ((item & 3) << 5) | lane;
             const int star = a.zone_star[g];
             const int iz = g - a.zone_offset[star];
+            const int nz = a.zone_offset[star + 1] - a.zone_offset[star];
             // the zone's inputs into this warp's slots (the slots are the warp's own: no CTA barrier needed)
-            for (int q = lane; q < 16 + DS_PRE + DS_HZ; q += 32) {
-                const double v = (q < 11) ? a.ionic[(size_t)11 * g + q] : a.aux[(size_t)DS_AUX * g + (q - 11)];
+            const double* ion_g = (FACE ? a.ionic_bar : a.ionic) + (size_t)11 * g;
+            constexpr int NIN = 16 + DS_PRE + (HAS_EOS ? DS_HZ : 0) + (FACE ? DS_CP + 2 : 0);
+            for (int q = lane; q < NIN; q += 32) {
+                const double v = (q < 11) ? ion_g[q] : a.aux[(size_t)DS_AUX * g + (q - 11)];
                 if (q < 16) reinterpret_cast<double*>(&s_zone[w])[q] = v;
                 else if (q < 16 + DS_PRE) reinterpret_cast<double*>(&s_pre[w])[q - 16] = v;
-                else reinterpret_cast<double*>(&s_hz[w])[q - 16 - DS_PRE] = v;
+                else if (q < 16 + DS_PRE + DS_HZ) reinterpret_cast<double*>(&s_hz[HAS_EOS ? w : 0])[q - 16 - DS_PRE] = v;
+                else if (q < 16 + DS_PRE + DS_HZ + DS_CP) reinterpret_cast<double*>(&s_cp[FACE ? w : 0])[q - 16 - DS_PRE - DS_HZ] = v;
+                else s_lam[FACE ? w : 0][q - 16 - DS_PRE - DS_HZ - DS_CP] = v;
             }
-            const double* Yg = a.Yion + (size_t)a.ncharged * g;
+            const double* Yg = (FACE ? a.Yion_bar : a.Yion) + (size_t)a.ncharged * g;
             if (net_in_smem) {   // abundances and the list of the species above the threshold (ascending, as the reference loops)
                 int na = 0;
                 for (int i0 = 0; i0 < a.ncharged; i0 += 32) {
@@ -514,31 +541,56 @@ __global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_eos_block_kernel(DsMicroA
                     const double y = (i < a.ncharged) ? Yg[i] : 0.0;
                     if (i < a.ncharged) s_Y[w][i] = y;
                     const unsigned m = __ballot_sync(0xffffffffu, i < a.ncharged && y > a.eos.Ythresh);
-                    if ((m >> lane) & 1u) s_act[w][na + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
+                    if ((m >> lane) & 1u) s_act[SPECIES ? w : 0][na + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
                     na += __popc(m);
                 }
                 if (lane == 0) s_nact[w] = na;
             }
             __syncwarp();
             const DsComp& c = s_zone[w].c;
+            const double rho = s_zone[w].rho, chi = s_zone[w].chi;
             const double T = a.tab_T[kn], lgT = a.tab_lgT[kn];
-            DsEosRes r;
             bool bad = false;
-            ds_eval_crust_eos<FAST>(helm, a.eos, s_zone[w].rho, T, lgT, c, s_pre[w], s_hz[w], a.ncharged, Zn, An, ionz,
-                                    net_in_smem ? s_Y[w] : Yg, s_zone[w].Tc[1], s_zone[w].chi, r, bad, nullptr,
-                                    net_in_smem ? s_act[w] : nullptr, net_in_smem ? s_nact[w] : 0);
-            // the two table values of this knot are parked at the head of the zone's (4,128) blocks (contiguous in the
-            // knot: coalesced here and in ds_eos_interp_kernel, which completes the blocks)
+            double v0 = 0.0, v1 = 0.0;
+            int ierr = 0;
+            if (HAS_EOS) {
+                DsEosRes r;
+                ds_eval_crust_eos<FAST>(helm, a.eos, rho, T, lgT, c, s_pre[w], s_hz[HAS_EOS ? w : 0], a.ncharged, Zn, An, ionz,
+                                        net_in_smem ? s_Y[w] : Yg, s_zone[w].Tc[1], chi, r, bad, nullptr,
+                                        net_in_smem ? s_act[SPECIES ? w : 0] : nullptr, net_in_smem ? s_nact[w] : 0);
+                ierr = r.ierr;
+                if (!FACE) {
+                    v0 = dsm::log(r.Cp); v1 = dsm::log(r.Gamma);
+                    if (on && iz == 0 && kn == 0 && !(FAST && (bad || a.force_redo)))  // create_model.f:367-369
+                        a.rho_bar1[star] = rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+                } else {
+                    DsCond K;
+                    dsk::ds_conductivity(a.cond, rho, T, chi, r.Gamma, r.Theta, r.mu_e, c, s_cp[FACE ? w : 0], s_zone[w].Tc[1],
+                                         s_lam[FACE ? w : 0][0], (int)s_lam[FACE ? w : 0][1], K);
+                    v0 = dsm::log(K.total);
+                }
+            } else {
+                DsNeutrino eps;
+                dsn::ds_crust_neutrino<FAST>(rho, T, c, s_pre[w], chi, s_zone[w].Tc[1], a.nu_channels, eps, bad);
+                double lnenu = dsm::log(eps.total / rho);
+                if (a.turn_on_shell_Urca && iz < nz - 1) {  // create_model.f:379-384
+                    if (dsm::log10(a.P_bar[g]) < a.lgP_shell_Urca && dsm::log10(a.P_bar[g + 1]) > a.lgP_shell_Urca)
+                        lnenu = dsm::log(dsm::exp(lnenu) + 1.0e36 * a.shell_Urca_luminosity_coeff *
+                                                     dsd::ipow<5>(T / 5.0e8) / a.dm[g]);
+                }
+                v0 = lnenu;
+            }
+            // the table values of this knot are parked at the head of the zone's (4,128) blocks (contiguous in the
+            // knot: coalesced here and in the interpolation kernels, which complete the blocks)
             const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
             const bool flagged = FAST && (__any_sync(0xffffffffu, bad) || a.force_redo);
             if (on && !flagged) {
-                a.tab_lnCp[ob + kn] = dsm::log(r.Cp);
-                a.tab_lnGamma[ob + kn] = dsm::log(r.Gamma);
-                if (iz == 0 && kn == 0)  // create_model.f:367-369
-                    a.rho_bar1[star] = s_zone[w].rho * dsm::pow(a.P_bar[g] / a.P[g], 1.0 / r.chiRho);
+                if (PART == DS_PART_EOS) { a.tab_lnCp[ob + kn] = v0; a.tab_lnGamma[ob + kn] = v1; }
+                else if (PART == DS_PART_NU) a.tab_lnEnu[ob + kn] = v0;
+                else a.tab_lnK[ob + kn] = v0;
             }
-            if (on && r.ierr != 0) a.status[star] = r.ierr;
-            if (on && flagged && lane == 0) a.blk_list[(size_t)3 * 4 * a.total_zones + atomicAdd(a.blk_count + 3, 1)] = item;
+            if (on && ierr != 0) a.status[star] = ierr;
+            if (on && flagged && lane == 0) a.blk_redo[atomicAdd(a.blk_redo_count, 1)] = item;
             __syncwarp();   // the slots are rewritten in the next round
         }
     }
@@ -566,3 +618,23 @@ __global__ void __launch_bounds__(DS_NTAB* DS_INTERP_G) ds_eos_interp_kernel(DsM
     ds_group_interp_pm2(on, i, s_h, s_v[grp][0], s_v[grp][1], s_m[grp][0], s_m[grp][1], s_s[grp][0], s_s[grp][1],
                         a.tab_lnCp + ob, a.tab_lnGamma + ob);
 }
+
+// interp_pm of ONE table (lnEnu or lnK) whose values the block kernel parked at the head of each zone's block
+template <int UNIT = 0>
+__global__ void __launch_bounds__(DS_NTAB* DS_INTERP_G) ds_interp1_kernel(DsMicroArgs a, double* __restrict__ tab) {
+    constexpr int G = DS_INTERP_G;
+    __shared__ double s_h[DS_NTAB], s_v[G][DS_NTAB], s_m[G][DS_NTAB], s_s[G][DS_NTAB];
+    const int grp = threadIdx.x / DS_NTAB, i = threadIdx.x % DS_NTAB;
+    const int n_items = a.work_list ? a.n_work : a.total_zones;
+    const int idx = blockIdx.x * G + grp;
+    const bool on = idx < n_items;
+    const int g = on ? (a.work_list ? a.work_list[idx] : idx) : 0;
+    const int star = a.zone_star[g];
+    const int iz = g - a.zone_offset[star];
+    const size_t ob = (size_t)4 * DS_NTAB * (a.tab_zone0 ? a.tab_zone0[star] + iz : g);
+    if (threadIdx.x < DS_NTAB - 1) s_h[i] = a.tab_lnT[i + 1] - a.tab_lnT[i];
+    s_v[grp][i] = on ? tab[ob + i] : 0.0;
+    __syncthreads();
+    ds_group_interp_pm(on, i, s_h, s_v[grp], s_m[grp], s_s[grp], tab + ob);
+}
+

@@ -12,10 +12,10 @@
 #define DS_MICRO_FAST 1
 #include "micro_part.cuh"
 
-// The same half scheduled by 32-knot blocks (kernels_micro.cuh, ds_eos_block_kernel): classification of the blocks,
-// branch-free pass over the three class lists, plain pass over the flagged blocks, interpolation.  a.blk_count must be
-// zeroed on the stream before the call.  Seven launches.
-cudaError_t ds_launch_micro_eos_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
+// The same half scheduled by 32-knot blocks (kernels_micro.cuh, ds_block_kernel): counting sort of the blocks by
+// phase class and species count, branch-free pass over the three class lists, plain pass over the flagged blocks,
+// interpolation.  a.blk_count must be zeroed on the stream before the call.  Seven launches.
+cudaError_t ds_launch_micro_eos_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a_in, const DsHelmDev& h,
                                        const DsHostConsts& hc) {
     static bool hc_set[64] = {};
     int dev = 0;
@@ -26,13 +26,15 @@ cudaError_t ds_launch_micro_eos_blocks(int sms, int n_items, cudaStream_t s, con
         hc_set[dev & 63] = true;
     }
     if (n_items <= 0) return cudaSuccess;
+    DsMicroArgs a = a_in;
+    a.blk_redo = a.blk_list + (size_t)3 * 4 * a.total_zones; a.blk_redo_count = a.blk_count + 3;
     const size_t dyn = (size_t)DS_BLK_W * DS_YMAX * sizeof(double);
     const int grid = std::max(1, std::min(sms, (4 * n_items + DS_BLK_W - 1) / DS_BLK_W));
     ds_eos_classify_kernel<0><<<(n_items + 127) / 128, 128, 0, s>>>(a);   // histogram of the sort keys
     ds_eos_prefix_kernel<0><<<1, 32, 0, s>>>(a.blk_count);
     ds_eos_classify_kernel<1><<<(n_items + 127) / 128, 128, 0, s>>>(a);   // scatter
-    ds_eos_block_kernel<true><<<grid, 32 * DS_BLK_W, dyn, s>>>(a, h);
-    ds_eos_block_kernel<false><<<grid, 32 * DS_BLK_W, dyn, s>>>(a, h);
+    ds_block_kernel<DS_PART_EOS, true><<<grid, 32 * DS_BLK_W, dyn, s>>>(a, h);
+    ds_block_kernel<DS_PART_EOS, false><<<grid, 32 * DS_BLK_W, dyn, s>>>(a, h);
     ds_eos_interp_kernel<0><<<(n_items + DS_INTERP_G - 1) / DS_INTERP_G, DS_NTAB * DS_INTERP_G, 0, s>>>(a);
     return cudaGetLastError();
 }

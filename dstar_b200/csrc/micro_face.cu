@@ -11,4 +11,5 @@
 #define DS_MICRO_GS(X) X(7)
 #endif
 #define DS_MICRO_FAST 0
+#define DS_MICRO_BLOCK_FN ds_launch_micro_face_blocks
 #include "micro_part.cuh"

@@ -19,6 +19,11 @@ cudaError_t ds_launch_micro_eos(int G, bool fast, int sms, int n_items, cudaStre
 // the EOS half scheduled by 32-knot blocks (classification, branch-free pass, plain pass, interpolation)
 cudaError_t ds_launch_micro_eos_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
                                        const DsHostConsts& hc);
+// the neutrino half / the faces scheduled by 32-knot blocks in natural order (+ the interpolation of their table)
+cudaError_t ds_launch_micro_nu_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
+                                      const DsHostConsts& hc);
+cudaError_t ds_launch_micro_face_blocks(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h,
+                                        const DsHostConsts& hc);
 cudaError_t ds_launch_micro_nu(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,
                                const DsHelmDev& h, const DsSfDev& sf, const DsHostConsts& hc);     // lnEnu
 cudaError_t ds_launch_micro_face(int G, bool fast, int sms, int n_items, cudaStream_t s, const DsMicroArgs& a,

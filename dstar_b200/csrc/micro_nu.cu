@@ -10,4 +10,5 @@
 #define DS_MICRO_GS(X) X(8)
 #endif
 #define DS_MICRO_FAST 1
+#define DS_MICRO_BLOCK_FN ds_launch_micro_nu_blocks
 #include "micro_part.cuh"

@@ -59,3 +59,28 @@ cudaError_t DS_MICRO_FN(int G, bool fast, int sms, int n_items, cudaStream_t s, 
 #undef DS_X
     return cudaErrorInvalidValue;
 }
+
+#ifdef DS_MICRO_BLOCK_FN
+// The same part scheduled by 32-knot blocks in natural order (kernels_micro.cuh, ds_block_kernel): every warp works
+// on its own (zone, knot block), no CTA barrier inside a round; then the interpolation of the part's table.
+// a.blk_redo / a.blk_redo_count must be set, the count zeroed on the stream.
+cudaError_t DS_MICRO_BLOCK_FN(int sms, int n_items, cudaStream_t s, const DsMicroArgs& a, const DsHelmDev& h, const DsHostConsts& hc) {
+    static bool hc_set[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!hc_set[dev & 63]) {
+        if ((e = cudaMemcpyToSymbol(ds_hc, &hc, sizeof hc)) != cudaSuccess) return e;
+        hc_set[dev & 63] = true;
+    }
+    if (n_items <= 0) return cudaSuccess;
+    constexpr int PART = DS_MICRO_PART;
+    const int grid = std::max(1, std::min(sms, (4 * n_items + DS_BLK_W - 1) / DS_BLK_W));
+#if DS_MICRO_FAST
+    ds_block_kernel<PART, true><<<grid, 32 * DS_BLK_W, 0, s>>>(a, h);
+#endif
+    ds_block_kernel<PART, false><<<grid, 32 * DS_BLK_W, 0, s>>>(a, h);
+    ds_interp1_kernel<0><<<(n_items + DS_INTERP_G - 1) / DS_INTERP_G, DS_NTAB * DS_INTERP_G, 0, s>>>(a, PART == DS_PART_NU ? a.tab_lnEnu : a.tab_lnK);
+    return cudaGetLastError();
+}
+#endif
