@@ -486,10 +486,10 @@ def run_b200(args):
         bs_.close()
     # ---------------- roofline of the dominant kernel, FP64 pipe
     fp64_peak = ctx.fp64_peak_tflops()
-    # The cell pass runs as two kernels: ds_micro_kernel<EOS> (eval_crust_eos -> lnCp, lnGamma; the dominant kernel,
-    # ~44 % of the step) and ds_micro_kernel<NU> (crust neutrino emissivity -> lnEnu).  Durations are the library's
-    # CUDA-event times on the launching stream, averaged over the timed steps; the EOS time includes its (normally
-    # empty) plain-division launch.  `roofline` is the EOS kernel; `cell_pass` is both kernels together, the figure
+    # The cell pass runs as two halves: the EOS half (eval_crust_eos -> lnCp, lnGamma; ds_block_kernel<EOS> is the
+    # dominant kernel, ~46 % of the step) and the neutrino half (crust neutrino emissivity -> lnEnu).  Durations are the
+    # library's CUDA-event times on the launching stream, averaged over the timed steps; the EOS time includes its
+    # block sort, its (normally empty) plain-division launch and its interpolation kernel.  `roofline` is the EOS kernel; `cell_pass` is both kernels together, the figure
     # comparable with round 1's fused kernel (6.0 kflop per evaluation over the cell time).
     cell_ms = tc / args.steps
     eos_ms = m["eos_ms"] if m["eos_ms"] > 0 else cell_ms
@@ -518,7 +518,7 @@ def run_b200(args):
         traffic_note = "bytes per launch from %s (%d zones), scaled to %d zones; algorithmic bytes per launch %.3g" % (
             tr["capture"], tr["zones"], total, alg_bytes_dom)
     wr = workload_roofline(args.workload, W, m, fp64_peak)
-    roofline = {"bound": "fp64", "kernel": "ds_micro_kernel<EOS> (cell pass, EOS half)" if split else "ds_micro_kernel<cell>",
+    roofline = {"bound": "fp64", "kernel": "ds_block_kernel<EOS> (cell pass, EOS half: evaluation + block sort + interpolation)" if split else "ds_micro_kernel<cell>",
                 "achieved": achieved_tf, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
                 "traffic_note": traffic_note,

@@ -40,11 +40,13 @@ def main():
         zones = line["config"]["zones_total_per_gpu"]
         evals = zones * 128.0
         ent = {"source": "ncu hardware counters, %s, %d zones x 128 knots per launch (tools/count_flops.py)" % (csv_path.split("/")[-1], zones)}
-        # ds_micro_kernel<PART, G, FAST>: PART 1 = EOS half, 2 = neutrino half (cells), 3 = faces (kernels_micro.cuh)
+        # ds_block_kernel<PART, FAST> (or ds_micro_kernel<PART, G, FAST> with DSTAR_MICRO_BLOCKS=0): PART 1 = EOS half,
+        # 2 = neutrino half (cells), 3 = faces (kernels_micro.cuh); the interpolation kernels (~30 flop per evaluation) are
+        # not counted
         launches = read(csv_path)
         for kind, part in (("eos", 1), ("nu", 2), ("face", 3)):
-            pat = "ds_micro_kernel<%d," % part
-            ls = [l for l in launches if pat in l["kernel"].replace(" ", "").replace("(bool)", "").replace("(int)", "")]
+            pats = ("ds_block_kernel<%d," % part, "ds_micro_kernel<%d," % part)
+            ls = [l for l in launches if any(p_ in l["kernel"].replace(" ", "").replace("(bool)", "").replace("(int)", "") for p_ in pats)]
             ls = [l for l in ls if l.get("smsp__thread_inst_executed.sum", 0.0) > 1.0e6]   # skip the (empty) plain-division passes
             if not ls:
                 continue
