@@ -112,7 +112,8 @@ def test_dsmath_bits(oracle):
 def test_shared_denominator_division_bits():
     """DsDen (dstar_b200/csrc/dconst.cuh): the branch-free division returns exactly the bits of the IEEE quotient
     x / y -- moderate operands (fast path), extreme exponents, subnormals, zeros, infinities and NaN (flag raised,
-    plain division)."""
+    plain division).  One stated exception: a zero numerator gives a zero whose SIGN may differ from IEEE's (-0 / b
+    with b > 0 comes out +0; see the comment in operator/)."""
     import dstar_b200 as ds
     from dstar_b200._capi import check, p
     ctx = ds.Context(0, gaps=None)
@@ -140,12 +141,16 @@ def test_shared_denominator_division_bits():
             nan = np.isnan(host)
             assert np.array_equal(q_plain.view(np.uint64)[~nan], host.view(np.uint64)[~nan])
             assert np.array_equal(np.isnan(q_den), nan)
-            assert np.array_equal(q_den.view(np.uint64)[~nan], host.view(np.uint64)[~nan])
+            zn = (x == 0.0) & ~nan          # zero numerators: a zero, sign not asserted
+            ok = ~nan & ~zn
+            assert np.array_equal(q_den.view(np.uint64)[ok], host.view(np.uint64)[ok])
+            assert np.all(q_den[zn] == 0.0)
             # fast path alone: wherever the validity flag stays down the bits are the IEEE quotient's
             q_fast = np.zeros_like(x)
             check(ctx.L.dstar_dsmath_eval(ctx.h, 11, len(x), p(x), p(y), p(q_fast)), "dsmath_eval")
             took = ~np.isnan(q_fast)
-            assert np.array_equal(q_fast.view(np.uint64)[took], host.view(np.uint64)[took])
+            assert np.array_equal(q_fast.view(np.uint64)[took & ~zn], host.view(np.uint64)[took & ~zn])
+            assert np.all(q_fast[took & zn] == 0.0)
             with np.errstate(all="ignore"):
                 moderate = ((np.abs(np.log2(np.abs(y))) < 299) & (np.log2(np.abs(x)) > -959) & (np.log2(np.abs(host)) > -999)
                             & (np.log2(np.abs(host)) < 699) & ~nan)

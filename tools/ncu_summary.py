@@ -1,5 +1,6 @@
 """Markdown table from an `ncu --set full` report: python tools/ncu_summary.py file.ncu-rep
-(the tables under profiles/*_ncu_full_summary.md).  Reads `ncu -i <rep> --page raw --csv`."""
+(the tables under profiles/*_ncu_full_summary.md).  Reads `ncu -i <rep> --page raw --csv`, or that page already exported
+to a .csv file (the reports of one session exceed what the GPU box copies back, so tools/_scan_job.sh exports there)."""
 import csv
 import io
 import subprocess
@@ -14,7 +15,10 @@ def num(x):
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     head, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(head)}
