@@ -186,10 +186,12 @@ DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
 // CTA-per-star evolve kernel: block size from the largest star, CTAs per SM from the batch size (kernels_evolve.cuh)
 cudaError_t launch_evolve_cta(const DsEvolveArgs& a, const int* list, int count, int max_nz, int sms, int minb_override, cudaStream_t s) {
     const int threads = ((max_nz + 31) / 32) * 32;
-    // resident stars per SM (B200, 253-zone stars, ms for 148 / 256 / 512 / 768 / 1024 stars -- profiles/r02_notes.md):
-    //   1: 1.32 / 1.87 / 3.60 / 5.20 / 6.64    2: 1.93 / 2.16 / 3.30 / 4.77 / 6.18    4: 2.50 / 2.87 / 3.43 / 4.91 / 6.18
-    // one star per SM (255 registers, no spills) wins until three waves' worth, then two per SM
-    int minb = minb_override > 0 ? minb_override : (count <= 3 * sms ? 1 : count <= 8 * sms ? 2 : 4);
+    // resident stars per SM (B200, 253-zone stars, ms for 148 / 256 / 512 / 1024 / 4096 stars -- profiles/r02_notes.md):
+    //   1: 0.93 / 1.30 / 2.50 / 4.64 / 18.3    2: 1.25 / 1.49 / 2.27 / 4.23 / 16.2    4: 1.87 / 2.21 / 2.84 / 4.97 / 18.0
+    // one star per SM (255 registers) wins up to two waves' worth of stars, then two per SM (128 registers); three and four
+    // per SM spill too much to pay at any size.  Stars of 257-384 zones: one per SM throughout (1024 stars of 271 zones:
+    // 6.84 against 7.83 ms).
+    int minb = minb_override > 0 ? minb_override : (threads <= 256 ? (count <= 2 * sms ? 1 : 2) : 1);
     if (threads <= 256) {
         switch (minb) {
             case 1: ds_evolve_kernel<256, 1><<<count, threads, 0, s>>>(a, list); break;

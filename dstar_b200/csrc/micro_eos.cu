@@ -2,6 +2,12 @@
 // (NScool_create_model.f:344-369, :386-397).
 // alignment barriers between the components only, not inside ee_exchange (4.04 -> 4.00 ms).
 #define DS_NO_PHASE_INNER
+// one-test validity check of the branch-free divisions (dconst.cuh, DS_DEN_LEAN): the EOS has no quotients below 2^-650
+// (no block of any workload takes the plain-division pass); EOS half 3.45 -> 3.41 ms, INT-16 10.35 -> 10.09.
+// -DDS_DEN_FULL_EOS keeps the three-test form.
+#ifndef DS_DEN_FULL_EOS
+#define DS_DEN_LEAN
+#endif
 #define DS_MICRO_PART DS_PART_EOS
 #define DS_MICRO_FN ds_launch_micro_eos
 #ifdef DS_MICRO_SCAN
