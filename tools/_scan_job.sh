@@ -1,6 +1,9 @@
 #!/bin/bash
-# experiment job: resident stars per SM for large batches after the evolve changes
+# experiment job: persistent interpolation kernels (CTAs per SM 4 / 3 / 2) against the one-round form
 cd /root/repo
-timeout 600 python tools/evolve_scan.py custom_Tc_Qimp 444,592,1184,2048,4096 2>&1 | grep "stars\|workload"
-timeout 900 python tools/evolve_scan.py accretion 444,1024,4096 2>&1 | grep "stars\|workload"
-timeout 600 python tools/evolve_scan.py int16_demo 1024 2>&1 | grep "stars\|workload"
+timeout 300 python tools/micro_scan.py custom_Tc_Qimp 256 ic4 2>&1 | grep SCAN
+for v in ic3 ic2 ione; do DSTAR_B200_LIB=build/exp/lib_$v.so timeout 300 python tools/micro_scan.py custom_Tc_Qimp 256 $v 2>&1 | grep SCAN; done
+timeout 300 python tools/micro_scan.py accretion 256 ic4 2>&1 | grep SCAN
+timeout 300 python tools/micro_scan.py int16_demo 64 ic4 2>&1 | grep SCAN
+timeout 300 python tools/micro_scan.py fit_lightcurve 256 ic4 2>&1 | grep SCAN
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
