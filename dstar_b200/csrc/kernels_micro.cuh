@@ -410,10 +410,12 @@ __global__ void __launch_bounds__(DS_NTAB* G, DS_MICRO_CTAS) ds_micro_kernel(DsM
 // every round (9 % of the EOS kernel's stall samples at that one barrier, profiles/r02_ncu_full_summary.md).  Here the
 // evaluation and the interpolation are separate kernels, so the unit of work is one warp = one (zone, 32-knot block);
 // the blocks are sorted into all-solid, all-liquid and mixed ones (ds_eos_classify_kernel) and a persistent CTA takes
-// 28 blocks of ONE class per round: every warp of a round has the same work.  The class only steers the schedule: a
+// DS_BLK_W blocks of ONE class per round: every warp of a round has the same work.  The class only steers the schedule: a
 // misclassified block is evaluated correctly, its warp just diverges.
+// EOS half, warps per CTA 16 / 20 / 24 / 28 (128 / 96 / 80 / 72 registers): 3.36 / 3.38 / 3.41 / 3.47 ms; INT-16 (80 species)
+// 10.34 / 10.10 / 10.10 / - ms: 20.  The neutrino and face units set their own (32 and 28).
 #ifndef DS_BLK_W_X
-#define DS_BLK_W_X 24
+#define DS_BLK_W_X 20
 #endif
 constexpr int DS_BLK_W = DS_BLK_W_X;   // warps (blocks) per CTA and round
 
@@ -598,7 +600,12 @@ __global__ void __launch_bounds__(32 * DS_BLK_W, 1) ds_block_kernel(DsMicroArgs 
 
 // interp_pm of lnCp and lnGamma for the zones of the work list: DS_INTERP_G zones per CTA, 128 threads each.  The values
 // are read from the head of each block (where ds_eos_block_kernel parked them) before any of it is overwritten.
-constexpr int DS_INTERP_G = 4;
+// zones per CTA: 1 / 2 / 4 -> the three interpolation launches of a step together 0.40 / 0.42 / 0.47 ms (the phases of many
+// small CTAs overlap better)
+#ifndef DS_INTERP_G_X
+#define DS_INTERP_G_X 1
+#endif
+constexpr int DS_INTERP_G = DS_INTERP_G_X;
 template <int UNIT = 0>
 __global__ void __launch_bounds__(DS_NTAB* DS_INTERP_G) ds_eos_interp_kernel(DsMicroArgs a) {
     constexpr int G = DS_INTERP_G;
