@@ -29,7 +29,10 @@ def test_bench_line_has_contract_keys():
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in d["e2e"], k
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
-    assert 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    # the serial end-to-end loop cannot beat the kernels-only figure; with two batches in flight (e2e.mode) the tail of one
+    # batch's launches overlaps the other's, so only the serial entry is bounded
+    assert 0 < d["e2e"]["one_batch_at_a_time"]["value"] <= d["value"] * 1.05
+    assert d["e2e"]["value"] >= d["e2e"]["one_batch_at_a_time"]["value"] and "mode" in d["e2e"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in d["roofline"], k
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
