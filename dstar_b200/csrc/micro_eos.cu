@@ -1,7 +1,15 @@
 // Coefficient pass, cell half 1: eval_crust_eos per (zone, knot) -> lnCp, lnGamma tables and the rho_bar(1) fix-up
 // (NScool_create_model.f:344-369, :386-397).
 // alignment barriers between the components only, not inside ee_exchange (4.04 -> 4.00 ms).
+#ifndef DS_EOS_PHASE_INNER  // experiment switch: keep the eight barriers inside ee_exchange
 #define DS_NO_PHASE_INNER
+#endif
+#ifdef DS_EOS_NO_PHASE     // experiment: no alignment barrier at all in the EOS unit
+#define DS_NO_PHASE_SYNC
+#endif
+#ifdef DS_EOS_NO_PHASE_ION // experiment: none inside the species loop of ion_mixture
+#define DS_NO_PHASE_ION
+#endif
 // one-test validity check of the branch-free divisions (dconst.cuh, DS_DEN_LEAN): the EOS has no quotients below 2^-650
 // (no block of any workload takes the plain-division pass); EOS half 3.45 -> 3.41 ms, INT-16 10.35 -> 10.09.
 // -DDS_DEN_FULL_EOS keeps the three-test form.
