@@ -52,3 +52,17 @@ def test_bench_reference_arm():
     assert d["impl"] == "reference" and d["value"] > 0 and d["metric"] == "zone_microphysics_evals_per_sec"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_e2e_entry_reports_both_loops():
+    """bench.e2e_entry: `value` is the faster of the serial loop and the loop with two batches in flight, `mode` says
+    which, and both figures stay in the line."""
+    sys.path.insert(0, ROOT)
+    import bench
+    e = bench.e2e_entry(1.0e6, 100.0, 2.0e-3, 1.6e-3, 10, 20)
+    assert e["value"] == 1.0e6 / 1.6e-3 and "two batches" in e["mode"] and e["h2d_bytes_per_step"] == 10
+    assert e["one_batch_at_a_time"]["ms_per_step"] == 2.0 and abs(e["two_batches_in_flight"]["ms_per_step"] - 1.6) < 1e-12
+    e = bench.e2e_entry(1.0e6, 100.0, 2.0e-3, None, 10, 20)
+    assert e["value"] == 1.0e6 / 2.0e-3 and "two_batches_in_flight" not in e and e["mode"] == "one batch at a time"
+    e = bench.e2e_entry(1.0e6, 100.0, 2.0e-3, 2.5e-3, 10, 20)
+    assert e["value"] == 1.0e6 / 2.0e-3 and e["mode"] == "one batch at a time" and "two_batches_in_flight" in e
