@@ -187,10 +187,11 @@ DsCondCtrl cond_ctrl_from(const dstar_micro_ctrl* c) {
 cudaError_t launch_evolve_cta(const DsEvolveArgs& a, const int* list, int count, int max_nz, int sms, int minb_override, cudaStream_t s) {
     const int threads = ((max_nz + 31) / 32) * 32;
     // resident stars per SM (B200, 253-zone stars, ms for 148 / 256 / 512 / 1024 / 4096 stars -- profiles/r02_notes.md):
-    //   1: 0.93 / 1.30 / 2.50 / 4.64 / 18.3    2: 1.25 / 1.49 / 2.27 / 4.23 / 16.2    4: 1.87 / 2.21 / 2.84 / 4.97 / 18.0
+    //   1: 0.91 / 1.28 / 2.47 / 4.60 / 18.3    2: 1.15 / 1.32 / 2.03 / 3.80 / 16.2    4: 1.69 / 2.03 / 2.50 / 4.57 / 18.0
     // one star per SM (255 registers) wins up to two waves' worth of stars, then two per SM (128 registers); three and four
     // per SM spill too much to pay at any size.  Stars of 257-384 zones: one per SM throughout (1024 stars of 271 zones:
-    // 6.84 against 7.83 ms).
+    // 6.84 against 7.83 ms).  (Long, uneven histories prefer two per SM earlier: accretion, 256 stars, 4.36 against 3.70 ms;
+    // dstar_batch_set_evolve_occupancy / DSTAR_EVOLVE_MINB override the rule.)
     int minb = minb_override > 0 ? minb_override : (threads <= 256 ? (count <= 2 * sms ? 1 : 2) : 1);
     if (threads <= 256) {
         switch (minb) {
