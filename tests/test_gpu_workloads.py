@@ -1,5 +1,8 @@
 """The synthetic workloads of BASELINE.json's configs (dstar_b200/workloads.py) at test sizes: parity against the
 CPU oracle, and size-independent properties (batch invariance, idempotence, ragged batches, extreme zone counts)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -402,3 +405,54 @@ def test_run_batch_driver_matches_create_and_evolve(nscool):
             s.free()
     for s in ref:
         s.free()
+
+
+def test_two_batches_in_flight_on_one_device(nscool):
+    """Two kernel-level contexts on the same device, one host thread each, stepping their own batch at the same time (the
+    usage bench.py's `e2e.two_batches_in_flight` times and INTEGRATION.md section 2 recommends): every table and every
+    monitor equals the one-batch-at-a-time result bit for bit, whichever way the two streams interleave."""
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    ds = nscool
+    W = bench.prepare_workload(ds, "custom_Tc_Qimp", 16, 0.2, 0)
+    gaps = ("ns", "sfb03", "t72")
+    ctxs = [ds.Context(0, gaps=gaps), ds.Context(0, gaps=gaps)]
+    batches = [ds.Batch(c, W["zoff"], W["H"]["ncharged"]) for c in ctxs]
+    try:
+        def step(b):
+            bench.upload_all(b, W)
+            b.micro_tables(W["mc"], 3)
+            b.evolve(W["ec"], 0)
+            r = b.download_results(full=False)
+            t = b.download_tables()
+            return {k: np.array(r[k]).copy() for k in ("Teff_monitor", "t_monitor", "Qb_monitor", "counters", "idid")}, \
+                   {k: np.array(t[k]).copy() for k in ("tab_lnCp", "tab_lnGamma", "tab_lnEnu", "tab_lnK")}
+        ref_r, ref_t = step(batches[0])
+        assert np.all(ref_r["idid"] >= 0)
+        out, errs = [[], []], []
+
+        def worker(i):
+            try:
+                for _ in range(4):
+                    out[i].append(step(batches[i]))
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errs, errs
+        for i in range(2):
+            assert len(out[i]) == 4
+            for r, t in out[i]:
+                for k in ref_r:
+                    np.testing.assert_array_equal(r[k], ref_r[k])
+                for k in ref_t:
+                    np.testing.assert_array_equal(t[k], ref_t[k])
+    finally:
+        for b in batches:
+            b.close()
+        for c in ctxs:
+            c.close()
